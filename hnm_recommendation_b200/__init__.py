@@ -1,0 +1,4 @@
+"""B200-native scoring hot path of hyunlord/hnm_recommendation (LightGCN / NeuralCF)."""
+from .lightgcn import LightGCN  # noqa: F401
+
+__all__ = ["LightGCN"]

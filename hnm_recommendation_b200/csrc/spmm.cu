@@ -1,0 +1,315 @@
+// LightGCN propagation: E <- A_hat E with the degree normalisation and the layer sum fused.
+// Replaces src/models/lightgcn.py:151-158 (L x torch_sparse SpMM + 2(L+1) elementwise passes).
+//
+// Formulation (DESIGN.md "propagate"): with xs = dis (.) E kept between layers,
+//     (A_hat E)_i = dis_i * sum_{j in row i} w_ij * xs[col_j]
+// so the gather loop needs neither a per-edge value array (w_ij = 1 when the reference is
+// given edge_weight=None) nor a per-edge dis[col] gather.  HBM-bound integer/gather work:
+// one warp per row, D/4 lanes x 128-bit loads per embedding row, several rows in flight per
+// lane, column indices read coalesced and broadcast by shuffle.  Rows longer than
+// `heavy_threshold` are summed by a whole CTA in a fixed order (deterministic).
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kRowsPerWarp = 4;
+constexpr int kHeavyThreads = 512;
+
+template <int D>
+struct Shape {
+  static constexpr int LPR = (D / 4 < 32) ? D / 4 : 32;  // lanes per embedding row
+  static constexpr int VEC = D / (4 * LPR);              // float4 per lane per row
+  static constexpr int G = 32 / LPR;                     // rows gathered side by side in a warp
+  static constexpr int UNROLL_ = (VEC >= 2) ? 4 : 8;     // independent loads in flight per lane = UNROLL*VEC
+  static constexpr int UNROLL = (G * UNROLL_ > 32) ? 32 / G : UNROLL_;  // one step never spans more than 32 entries
+};
+
+__device__ __forceinline__ void add4(float4& a, const float4& b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& b) {
+  a.x = fmaf(w, b.x, a.x); a.y = fmaf(w, b.y, a.y); a.z = fmaf(w, b.z, a.z); a.w = fmaf(w, b.w, a.w);
+}
+
+// Sum w * xs[col] over CSR entries [beg, end) with one warp.  On return every lane of
+// group 0 (lane < LPR) holds the full sum for its float4 slots.
+template <int D, bool WEIGHTED>
+__device__ __forceinline__ void warp_gather(const int32_t* __restrict__ col, const float* __restrict__ w,
+                                            const float* __restrict__ xs, int beg, int end, int lane,
+                                            float4 (&acc)[Shape<D>::VEC]) {
+  using S = Shape<D>;
+  const int g = lane / S::LPR;
+  const int sub = lane % S::LPR;
+#pragma unroll
+  for (int t = 0; t < S::VEC; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = beg; base < end; base += 32) {
+    const int idx = base + lane;
+    const int c = idx < end ? __ldg(col + idx) : 0;
+    float wv = 1.f;
+    if (WEIGHTED) wv = idx < end ? __ldg(w + idx) : 0.f;
+    const int cnt = min(32, end - base);
+    for (int j0 = 0; j0 < cnt; j0 += S::G * S::UNROLL) {
+      float4 v[S::UNROLL][S::VEC];
+      float wj[S::UNROLL];
+#pragma unroll
+      for (int u = 0; u < S::UNROLL; ++u) {
+        const int j = j0 + u * S::G + g;
+        const int cj = __shfl_sync(0xffffffffu, c, j & 31);
+        if (WEIGHTED) wj[u] = __shfl_sync(0xffffffffu, wv, j & 31);
+        const bool ok = j < cnt;
+        const float* p = xs + (size_t)cj * D + sub * 4;
+#pragma unroll
+        for (int t = 0; t < S::VEC; ++t)
+          v[u][t] = ok ? ldg_f4(p + t * S::LPR * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < S::UNROLL; ++u) {
+#pragma unroll
+        for (int t = 0; t < S::VEC; ++t) {
+          if (WEIGHTED) fma4(acc[t], wj[u], v[u][t]);
+          else add4(acc[t], v[u][t]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = S::LPR; off < 32; off <<= 1) {
+#pragma unroll
+    for (int t = 0; t < S::VEC; ++t) {
+      acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, off);
+      acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, off);
+      acc[t].z += __shfl_xor_sync(0xffffffffu, acc[t].z, off);
+      acc[t].w += __shfl_xor_sync(0xffffffffu, acc[t].w, off);
+    }
+  }
+}
+
+// e = dis_i * sum;  xs_out = dis_i * e;  acc += alpha * e   (lightgcn.py:152,158)
+__device__ __forceinline__ void row_epilogue(float4 s, float di, float alpha, float* __restrict__ xs_out_p,
+                                             float* __restrict__ acc_p) {
+  float4 e = make_float4(__fmul_rn(di, s.x), __fmul_rn(di, s.y), __fmul_rn(di, s.z), __fmul_rn(di, s.w));
+  if (xs_out_p) {
+    float4 x = make_float4(__fmul_rn(di, e.x), __fmul_rn(di, e.y), __fmul_rn(di, e.z), __fmul_rn(di, e.w));
+    *reinterpret_cast<float4*>(xs_out_p) = x;
+  }
+  float4 a = *reinterpret_cast<const float4*>(acc_p);
+  a.x = __fadd_rn(a.x, __fmul_rn(alpha, e.x));
+  a.y = __fadd_rn(a.y, __fmul_rn(alpha, e.y));
+  a.z = __fadd_rn(a.z, __fmul_rn(alpha, e.z));
+  a.w = __fadd_rn(a.w, __fmul_rn(alpha, e.w));
+  *reinterpret_cast<float4*>(acc_p) = a;
+}
+
+template <int D, bool WEIGHTED>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+                 const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
+                 float* __restrict__ accbuf, float alpha, int64_t row_begin, int64_t row_end,
+                 int32_t heavy_threshold) {
+  using S = Shape<D>;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t first = row_begin + ((int64_t)blockIdx.x * kWarpsPerCta + warp) * kRowsPerWarp;
+#pragma unroll 1
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const int64_t row = first + r;
+    if (row >= row_end) return;
+    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    if (end - beg > heavy_threshold) continue;  // summed by spmm_heavy_kernel
+    float4 acc[S::VEC];
+    warp_gather<D, WEIGHTED>(col, w, xs_in, beg, end, lane, acc);
+    if (lane < S::LPR) {
+      const float di = __ldg(dis + row);
+#pragma unroll
+      for (int t = 0; t < S::VEC; ++t) {
+        const size_t off = (size_t)row * D + (size_t)(t * S::LPR + lane) * 4;
+        row_epilogue(acc[t], di, alpha, xs_out ? xs_out + off : nullptr, accbuf + off);
+      }
+    }
+  }
+}
+
+template <int D, bool WEIGHTED>
+__global__ void __launch_bounds__(kHeavyThreads)
+spmm_heavy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+                  const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
+                  float* __restrict__ accbuf, float alpha, const int32_t* __restrict__ heavy_rows,
+                  int64_t row_begin, int64_t row_end) {
+  using S = Shape<D>;
+  constexpr int NW = kHeavyThreads / 32;
+  __shared__ float4 part[NW][D / 4];
+  const int64_t row = heavy_rows[blockIdx.x];
+  if (row < row_begin || row >= row_end) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  // contiguous 32-aligned chunk per warp keeps the col[] reads coalesced
+  const int per = ((end - beg + NW - 1) / NW + 31) & ~31;
+  const int b = min(end, beg + warp * per), e = min(end, b + per);
+  float4 acc[S::VEC];
+  warp_gather<D, WEIGHTED>(col, w, xs_in, b, e, lane, acc);
+  if (lane < S::LPR) {
+#pragma unroll
+    for (int t = 0; t < S::VEC; ++t) part[warp][t * S::LPR + lane] = acc[t];
+  }
+  __syncthreads();
+  if (threadIdx.x < D / 4) {
+    float4 s = part[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < NW; ++k) add4(s, part[k][threadIdx.x]);
+    const size_t off = (size_t)row * D + (size_t)threadIdx.x * 4;
+    row_epilogue(s, __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off);
+  }
+}
+
+// Any dimension: one warp per row, lanes stride over the columns, edges in order.
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_generic_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+                    const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
+                    float* __restrict__ accbuf, float alpha, int dim, int64_t row_begin, int64_t row_end) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = row_begin + (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= row_end) return;
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  const float di = dis[row];
+  for (int c0 = 0; c0 < dim; c0 += 32 * 8) {
+    float s[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s[t] = 0.f;
+    for (int p = beg; p < end; ++p) {
+      const float* x = xs_in + (size_t)col[p] * dim;
+      const float wv = WEIGHTED ? w[p] : 1.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = c0 + t * 32 + lane;
+        if (c < dim) s[t] = WEIGHTED ? fmaf(wv, __ldg(x + c), s[t]) : s[t] + __ldg(x + c);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int c = c0 + t * 32 + lane;
+      if (c < dim) {
+        const size_t off = (size_t)row * dim + c;
+        const float e = __fmul_rn(di, s[t]);
+        if (xs_out) xs_out[off] = __fmul_rn(di, e);
+        accbuf[off] = __fadd_rn(accbuf[off], __fmul_rn(alpha, e));
+      }
+    }
+  }
+}
+
+__global__ void prescale_kernel(const float* __restrict__ e0, const float* __restrict__ dis, float alpha0,
+                                float* __restrict__ xs, float* __restrict__ acc, int64_t total, int dim) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = e0[i];
+    const float di = dis[i / dim];
+    xs[i] = __fmul_rn(di, v);
+    acc[i] = __fmul_rn(alpha0, v);   // 0 + alpha0 * E0 == alpha0 * E0 exactly (lightgcn.py:156-158)
+  }
+}
+
+__global__ void prescale_kernel_v4(const float4* __restrict__ e0, const float* __restrict__ dis, float alpha0,
+                                   float4* __restrict__ xs, float4* __restrict__ acc, int64_t total4, int dim4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = e0[i];
+    const float di = __ldg(dis + i / dim4);
+    xs[i] = make_float4(__fmul_rn(di, v.x), __fmul_rn(di, v.y), __fmul_rn(di, v.z), __fmul_rn(di, v.w));
+    acc[i] = make_float4(__fmul_rn(alpha0, v.x), __fmul_rn(alpha0, v.y), __fmul_rn(alpha0, v.z),
+                         __fmul_rn(alpha0, v.w));
+  }
+}
+
+template <int D, bool WEIGHTED>
+int launch_layer(const int32_t* rowptr, const int32_t* col, const float* w, const float* dis, const float* xs_in,
+                 float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
+                 const int32_t* heavy_rows, int32_t num_heavy, int32_t heavy_threshold, cudaStream_t stream) {
+  if (num_heavy > 0) {
+    spmm_heavy_kernel<D, WEIGHTED><<<num_heavy, kHeavyThreads, 0, stream>>>(rowptr, col, w, dis, xs_in, xs_out, acc,
+                                                                         alpha, heavy_rows, row_begin, row_end);
+    HNM_LAUNCH_CHECK();
+  }
+  const int64_t rows = row_end - row_begin;
+  const int64_t per_cta = (int64_t)kWarpsPerCta * kRowsPerWarp;
+  const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);
+  if (grid > 0) {
+    spmm_rows_kernel<D, WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(
+        rowptr, col, w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+        num_heavy > 0 ? heavy_threshold : INT32_MAX);
+    HNM_LAUNCH_CHECK();
+  }
+  return HNM_OK;
+}
+
+template <bool WEIGHTED>
+int dispatch_layer(int dim, const int32_t* rowptr, const int32_t* col, const float* w, const float* dis,
+                   const float* xs_in, float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
+                   const int32_t* heavy_rows, int32_t num_heavy, int32_t heavy_threshold, cudaStream_t stream) {
+#define HNM_CASE(DD)                                                                                          \
+  case DD:                                                                                                    \
+    return launch_layer<DD, WEIGHTED>(rowptr, col, w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,   \
+                                      heavy_rows, num_heavy, heavy_threshold, stream)
+  switch (dim) {
+    HNM_CASE(8);
+    HNM_CASE(16);
+    HNM_CASE(32);
+    HNM_CASE(64);
+    HNM_CASE(128);
+    HNM_CASE(256);
+    default: break;
+  }
+#undef HNM_CASE
+  if (dim > 256 * 8) return HNM_E_DIM;
+  const int64_t rows = row_end - row_begin;
+  const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  if (grid > 0) {
+    spmm_generic_kernel<WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(rowptr, col, w, dis, xs_in, xs_out, acc,
+                                                                       alpha, dim, row_begin, row_end);
+    HNM_LAUNCH_CHECK();
+  }
+  return HNM_OK;
+}
+
+}  // namespace
+
+extern "C" int hnm_lightgcn_prescale(const float* e0, const float* dis, float alpha0, float* xs, float* acc,
+                                     int64_t num_rows, int32_t dim, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!e0 || !dis || !xs || !acc) return HNM_E_NULL;
+  if (num_rows <= 0 || dim <= 0) return HNM_E_RANGE;
+  const int64_t total = num_rows * dim;
+  const int T = 256;
+  const int max_grid = hnm_num_sms() * 16;
+  if (dim % 4 == 0 && hnm_aligned16(e0) && hnm_aligned16(xs) && hnm_aligned16(acc)) {
+    const int64_t t4 = total / 4;
+    const unsigned grid = (unsigned)std::min<int64_t>((t4 + T - 1) / T, max_grid);
+    prescale_kernel_v4<<<grid, T, 0, stream>>>((const float4*)e0, dis, alpha0, (float4*)xs, (float4*)acc, t4, dim / 4);
+  } else {
+    const unsigned grid = (unsigned)std::min<int64_t>((total + T - 1) / T, max_grid);
+    prescale_kernel<<<grid, T, 0, stream>>>(e0, dis, alpha0, xs, acc, total, dim);
+  }
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
+}
+
+extern "C" int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_col, const float* csr_w,
+                                  const float* dis, const float* xs_in, float* xs_out, float* acc, float alpha,
+                                  int64_t num_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
+                                  const int32_t* heavy_rows, int32_t num_heavy, int32_t heavy_threshold,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!csr_rowptr || !csr_col || !dis || !xs_in || !acc) return HNM_E_NULL;
+  if (num_heavy > 0 && !heavy_rows) return HNM_E_NULL;
+  if (num_nodes <= 0 || dim <= 0 || row_begin < 0 || row_end > num_nodes || row_begin > row_end) return HNM_E_RANGE;
+  if (xs_in == xs_out) return HNM_E_RANGE;  // rows are gathered while others are written
+  if (dim % 4 == 0 && !(hnm_aligned16(xs_in) && hnm_aligned16(acc) && (!xs_out || hnm_aligned16(xs_out))))
+    return HNM_E_ALIGN;
+  if (row_begin == row_end) return HNM_OK;
+  if (csr_w)
+    return dispatch_layer<true>(dim, csr_rowptr, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+                                heavy_rows, num_heavy, heavy_threshold, stream);
+  return dispatch_layer<false>(dim, csr_rowptr, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+                               heavy_rows, num_heavy, heavy_threshold, stream);
+}

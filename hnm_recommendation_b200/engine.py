@@ -1,0 +1,198 @@
+"""Host-side orchestration of the B200 kernels (thin: allocation + call order).
+
+Each function maps onto one call site of the reference's hot path; the kernels
+themselves live in csrc/ behind the C ABI (include/hnm_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+HEAVY_THRESHOLD = 1024          # CSR rows longer than this are summed by a whole CTA
+EXACT_K_MAX = 256               # hnm_topk_exact limit (XCAP - XT in score_exact.cu)
+FUSED_DIM = 64
+FUSED_USER_TILE = 128
+FUSED_ITEM_TILE = 256
+FUSED_CAND = 32
+FUSED_K_MAX = 16
+
+
+@dataclass
+class Graph:
+    """Normalised adjacency of LightGCN.set_graph in device CSR form (lightgcn.py:92-112)."""
+    num_nodes: int
+    nnz: int
+    rowptr: torch.Tensor          # int32 [N+1]
+    col: torch.Tensor             # int32 [nnz]
+    w: Optional[torch.Tensor]     # fp32 [nnz] raw edge weights in CSR order, None when all ones
+    dis: torch.Tensor             # fp32 [N]  deg^-1/2
+    heavy_rows: torch.Tensor      # int32 [H]
+    heavy_threshold: int = HEAVY_THRESHOLD
+
+    @property
+    def num_heavy(self) -> int:
+        return int(self.heavy_rows.numel())
+
+
+def build_graph(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int,
+                device: torch.device, heavy_threshold: int = HEAVY_THRESHOLD) -> Graph:
+    """LightGCN.set_graph (lightgcn.py:81-112): self loops, row degree, deg^-1/2, (row,col)-sorted CSR."""
+    _lib.require_device()
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must have shape [2, num_edges]")
+    ei = edge_index.to(device=device, dtype=torch.int64).contiguous()
+    m = int(ei.size(1))
+    ew = None
+    if edge_weight is not None:
+        ew = edge_weight.detach().to(device=device, dtype=torch.float32).contiguous()
+        if ew.numel() != m:
+            raise ValueError("edge_weight must have one entry per edge")
+    nnz = m + num_nodes
+    rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=device)
+    col = torch.empty(nnz, dtype=torch.int32, device=device)
+    w = torch.empty(nnz, dtype=torch.float32, device=device) if ew is not None else None
+    dis = torch.empty(num_nodes, dtype=torch.float32, device=device)
+    heavy = torch.empty(num_nodes, dtype=torch.int32, device=device)
+    ws_bytes = _lib.load().hnm_graph_build_workspace_bytes(num_nodes, m, 1 if ew is not None else 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    n_heavy = C.c_int32(0)
+    with torch.cuda.device(device):
+        call("hnm_graph_build", ptr(ei[0]), ptr(ei[1]), ptr(ew), m, num_nodes, ptr(rowptr), ptr(col), ptr(w),
+             ptr(dis), heavy_threshold, ptr(heavy), C.addressof(n_heavy), ptr(ws), ws_bytes, stream())
+    heavy_rows = torch.sort(heavy[: n_heavy.value]).values.contiguous()
+    return Graph(num_nodes, nnz, rowptr, col, w, dis, heavy_rows, heavy_threshold)
+
+
+def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
+              row_range: Optional[Tuple[int, int]] = None, exchange=None) -> torch.Tensor:
+    """LightGCN.forward (lightgcn.py:147-158): returns final [N, d] = sum_l alpha_l * A_hat^l E0.
+
+    row_range/exchange serve the row-sharded multi-GPU form: this rank computes rows
+    [r0, r1) of every layer and ``exchange(buf)`` makes all rows of ``buf`` visible
+    (an allgather of row slices) before the next layer gathers from it.
+    """
+    _lib.require_device()
+    if not e0.is_cuda:
+        raise RuntimeError("LightGCN parameters must live on a CUDA device; there is no CPU path")
+    e0 = e0.detach().to(torch.float32).contiguous()
+    n, d = e0.shape
+    if n != graph.num_nodes:
+        raise ValueError("embedding rows != graph nodes")
+    r0, r1 = row_range if row_range is not None else (0, n)
+    acc = torch.empty_like(e0)
+    xs_a = torch.empty_like(e0)
+    xs_b = torch.empty_like(e0) if num_layers > 1 else None
+    with torch.cuda.device(e0.device):
+        s = stream()
+        call("hnm_lightgcn_prescale", ptr(e0), ptr(graph.dis), float(alphas[0]), ptr(xs_a), ptr(acc), n, d, s)
+        cur, nxt = xs_a, xs_b
+        for layer in range(1, num_layers + 1):
+            last = layer == num_layers
+            call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
+                 None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, r0, r1,
+                 ptr(graph.heavy_rows) if graph.num_heavy else None, graph.num_heavy, graph.heavy_threshold, s)
+            if not last:
+                if exchange is not None:
+                    exchange(nxt)
+                cur, nxt = nxt, cur
+        if exchange is not None:
+            exchange(acc)
+    return acc
+
+
+def exclusion_csr(user_ids: torch.Tensor, filter_items: Optional[Dict[int, set]], device) -> Tuple[
+        Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """filter_items dict (lightgcn.py:349-353) -> CSR over the listed users, item ids sorted ascending."""
+    if filter_items is None:
+        return None, None
+    ptrs: List[int] = [0]
+    items: List[int] = []
+    for uid in user_ids.tolist():
+        if uid in filter_items:
+            items.extend(sorted(int(i) for i in filter_items[uid]))
+        ptrs.append(len(items))
+    if not items:
+        return None, None
+    return (torch.tensor(ptrs, dtype=torch.int64, device=device),
+            torch.tensor(items, dtype=torch.int64, device=device))
+
+
+def _norm_ids(ids: Optional[torch.Tensor], limit: int, device) -> Optional[torch.Tensor]:
+    if ids is None:
+        return None
+    ids = ids.to(device=device, dtype=torch.int64).contiguous().view(-1)
+    if ids.numel():
+        lo, hi = int(ids.min()), int(ids.max())
+        if lo < -limit or hi >= limit:
+            raise IndexError(f"index out of range in self (valid: [{-limit}, {limit - 1}])")
+        if lo < 0:
+            ids = torch.where(ids < 0, ids + limit, ids)
+    return ids
+
+
+def pair_scores(user_emb, item_emb, user_ids, item_ids) -> torch.Tensor:
+    """LightGCN.predict tail (lightgcn.py:180-184)."""
+    _lib.require_device()
+    dev = user_emb.device
+    u = user_ids.to(device=dev, dtype=torch.int64).contiguous().view(-1)
+    i = item_ids.to(device=dev, dtype=torch.int64).contiguous().view(-1)
+    if u.numel() != i.numel():
+        raise RuntimeError("user_ids and item_ids must have the same length")
+    out = torch.empty(u.numel(), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        try:
+            call("hnm_pair_scores", ptr(user_emb), ptr(item_emb), ptr(u), ptr(i), u.numel(), user_emb.size(1),
+                 user_emb.size(0), item_emb.size(0), ptr(out), stream())
+        except _lib.HnmError as e:
+            if e.code == -2:
+                raise IndexError("index out of range in self") from None
+            raise
+    return out
+
+
+def score_all_items(user_emb, item_emb, user_ids) -> torch.Tensor:
+    """LightGCN.predict_all_items tail (lightgcn.py:199-202): [B, I] fp32."""
+    _lib.require_device()
+    dev = user_emb.device
+    u = _norm_ids(user_ids, user_emb.size(0), dev)
+    b = u.numel()
+    out = torch.empty(b, item_emb.size(0), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("hnm_score_all_items", ptr(user_emb), ptr(item_emb), ptr(u), b, item_emb.size(0), user_emb.size(1),
+             ptr(out), stream())
+    return out
+
+
+def topk_exact(user_emb, item_emb, user_ids: Optional[torch.Tensor], k: int,
+               excl: Tuple[Optional[torch.Tensor], Optional[torch.Tensor]] = (None, None),
+               item_begin: int = 0, batch: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact canonical top-k (fp64 scores; score desc, id asc).  item_emb holds the local shard
+    [item_begin, item_begin + rows)."""
+    _lib.require_device()
+    dev = user_emb.device
+    u = _norm_ids(user_ids, user_emb.size(0), dev)
+    b = u.numel() if u is not None else (batch if batch is not None else user_emb.size(0))
+    ids = torch.empty(b, k, dtype=torch.int64, device=dev)
+    sc = torch.empty(b, k, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        call("hnm_topk_exact", ptr(user_emb), ptr(item_emb), ptr(u), b, item_begin, item_begin + item_emb.size(0),
+             user_emb.size(1), k, ptr(excl[0]), ptr(excl[1]), ptr(ids), ptr(sc), stream())
+    return ids, sc
+
+
+def merge_topk(ids: torch.Tensor, scores: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[G, B, k] per-shard sorted lists -> global [B, k]."""
+    _lib.require_device()
+    g, b, k = ids.shape
+    out_i = torch.empty(b, k, dtype=torch.int64, device=ids.device)
+    out_s = torch.empty(b, k, dtype=torch.float64, device=ids.device)
+    with torch.cuda.device(ids.device):
+        call("hnm_merge_topk", ptr(ids.contiguous()), ptr(scores.contiguous()), g, b, k, ptr(out_i), ptr(out_s),
+             stream())
+    return out_i, out_s

@@ -1,0 +1,186 @@
+"""LightGCN with the reference's model API, computed by the B200 kernels.
+
+Drop-in for ``src.models.LightGCN`` (src/models/lightgcn.py:13-357) on the
+inference path: same constructor, attributes, ``state_dict`` key
+(``embeddings.weight``) and method signatures.  ``set_graph`` / ``forward`` /
+``predict`` / ``predict_all_items`` / ``recommend`` run hand-written sm_100a
+kernels through the C ABI in include/hnm_b200.h; there is no CPU fallback, so
+the module must be moved to a CUDA device before they are called.
+
+Differences from the reference, all deliberate:
+  * ties in ``recommend`` are ordered by item id ascending (the reference's
+    ``torch.topk`` order is unspecified; BASELINE.json fixes this rule);
+  * ``recommend`` ranks by the exact (fp64-accumulated) dot products of the fp32
+    embeddings, i.e. the ordering the reference's fp32 sgemm approximates;
+  * ``forward()`` is cached until the weights or the graph change
+    (the reference recomputes it on every call) -- results are identical;
+  * ``forward()`` is inference-only (no autograd through the propagate kernel);
+    training (``bpr_loss``) is outside the accelerated path;
+  * ``recommend(user_ids, filter_items=None, k=None)`` accepts ``k`` (README.md:131).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from .base import ModelBase
+from .metrics import RecommendationMetrics
+
+
+class LightGCN(ModelBase):
+    def __init__(
+        self,
+        num_users: int,
+        num_items: int,
+        embedding_dim: int = 64,
+        num_layers: int = 3,
+        learning_rate: float = 0.001,
+        weight_decay: float = 1e-4,
+        top_k: int = 12,
+        alpha: Optional[float] = None,
+    ):
+        super().__init__()
+        self.save_hyperparameters()
+
+        self.num_users = num_users
+        self.num_items = num_items
+        self.num_nodes = num_users + num_items
+        self.embedding_dim = embedding_dim
+        self.num_layers = num_layers
+        self.learning_rate = learning_rate
+        self.weight_decay = weight_decay
+        self.top_k = top_k
+
+        # layer-combination weights (lightgcn.py:59-67)
+        if alpha is None:
+            self.alpha = [1.0 / (num_layers + 1)] * (num_layers + 1)
+        else:
+            self.alpha = [alpha ** i for i in range(num_layers + 1)]
+            alpha_sum = sum(self.alpha)
+            self.alpha = [a / alpha_sum for a in self.alpha]
+
+        # one table for users then items (lightgcn.py:70-71)
+        self.embeddings = nn.Embedding(self.num_nodes, embedding_dim)
+        nn.init.xavier_uniform_(self.embeddings.weight)
+
+        self.graph: Optional[engine.Graph] = None
+        self.edge_index = None
+        self.edge_weight = None
+        self.metrics = RecommendationMetrics(top_k=top_k)
+
+        self.cache_embeddings = True
+        self._cache_key = None
+        self._cache_val: Optional[torch.Tensor] = None
+        self._scorer = None
+
+    # ------------------------------------------------------------------ graph
+    def set_graph(self, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor] = None) -> None:
+        """lightgcn.py:81-112.  The CSR lives on the device the parameters are on."""
+        self.edge_index = edge_index
+        self.edge_weight = edge_weight
+        self.graph = engine.build_graph(edge_index, edge_weight, self.num_nodes, self.embeddings.weight.device)
+        self._cache_key = None
+
+    # ---------------------------------------------------------------- forward
+    def _final_embeddings(self) -> torch.Tensor:
+        if self.graph is None:
+            raise RuntimeError("Graph not set. Call set_graph() first.")
+        w = self.embeddings.weight
+        if self.graph.rowptr.device != w.device:
+            raise RuntimeError("graph and parameters are on different devices; call set_graph() after .to(device)")
+        key = (w.data_ptr(), w._version, id(self.graph), tuple(self.alpha), self.num_layers)
+        if self.cache_embeddings and self._cache_key == key and self._cache_val is not None:
+            return self._cache_val
+        final = engine.propagate(self.graph, w, self.alpha, self.num_layers)
+        self._cache_key, self._cache_val = key, final
+        self._scorer = None
+        return final
+
+    def forward(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """lightgcn.py:136-164: (user_embeddings [U,d], item_embeddings [I,d]), views of one buffer."""
+        final = self._final_embeddings()
+        return final[: self.num_users], final[self.num_users:]
+
+    def predict(self, user_ids: torch.Tensor, item_ids: torch.Tensor) -> torch.Tensor:
+        """lightgcn.py:166-186."""
+        ue, ie = self.forward()
+        return engine.pair_scores(ue, ie, user_ids, item_ids)
+
+    def predict_all_items(self, user_ids: torch.Tensor) -> torch.Tensor:
+        """lightgcn.py:188-204: [batch, num_items] fp32 scores."""
+        ue, ie = self.forward()
+        return engine.score_all_items(ue, ie, user_ids)
+
+    # -------------------------------------------------------------- recommend
+    def recommend(self, user_ids: torch.Tensor, filter_items: Optional[Dict[int, set]] = None,
+                  k: Optional[int] = None) -> torch.Tensor:
+        """lightgcn.py:332-357: top-k item indices [batch, k] int64, (score desc, item id asc)."""
+        self.eval()
+        k = self.top_k if k is None else int(k)
+        if k > self.num_items or k <= 0:
+            raise RuntimeError("selected index k out of range")
+        with torch.no_grad():
+            ue, ie = self.forward()
+            dev = ue.device
+            uids = user_ids.to(dev).view(-1)
+            if k > engine.EXACT_K_MAX:
+                return self._recommend_by_sort(ue, ie, uids, filter_items, k)
+            from .scorer import FusedScorer
+            if FusedScorer.supports(self.embedding_dim, k, self.num_items):
+                if self._scorer is None:
+                    self._scorer = FusedScorer(ue, ie)
+                ids, _ = self._scorer.topk(uids, k, filter_items)
+                return ids
+            excl = engine.exclusion_csr(uids, filter_items, dev)
+            ids, _ = engine.topk_exact(ue, ie, uids, k, excl)
+        return ids
+
+    def recommend_all(self, k: Optional[int] = None, return_scores: bool = False):
+        """Full-catalog top-k for every user (the BASELINE.json headline path): [num_users, k]."""
+        self.eval()
+        k = self.top_k if k is None else int(k)
+        if k > self.num_items or k <= 0:
+            raise RuntimeError("selected index k out of range")
+        with torch.no_grad():
+            ue, ie = self.forward()
+            from .scorer import FusedScorer
+            if FusedScorer.supports(self.embedding_dim, k, self.num_items):
+                if self._scorer is None:
+                    self._scorer = FusedScorer(ue, ie)
+                ids, sc = self._scorer.topk(None, k, None)
+            else:
+                ids, sc = engine.topk_exact(ue, ie, None, k)
+        return (ids, sc) if return_scores else ids
+
+    def _recommend_by_sort(self, ue, ie, uids, filter_items, k):
+        # k beyond the select kernels' capacity: materialise the rows and stable-sort them on the device
+        scores = engine.score_all_items(ue, ie, uids).double()
+        if filter_items is not None:
+            for i, uid in enumerate(uids.tolist()):
+                if uid in filter_items:
+                    scores[i, list(filter_items[uid])] = float("-inf")
+        return torch.sort(scores, dim=1, descending=True, stable=True).indices[:, :k].contiguous()
+
+    # ------------------------------------------------- Lightning-facing hooks
+    def validation_step(self, batch: Dict[str, Any], batch_idx: int):
+        """lightgcn.py:267-284 with the fused top-k instead of predict_all_items + torch.topk."""
+        top_k_items = self.recommend(batch["user_ids"])
+        self.metrics.update(top_k_items.cpu(), batch["ground_truth"])
+
+    def on_validation_epoch_end(self):
+        metrics = self.metrics.compute()
+        self.metrics.reset()
+        for name, value in metrics.items():
+            self.log(f"val_{name}", value, prog_bar=True)
+
+    def test_step(self, batch: Dict[str, Any], batch_idx: int):
+        self.validation_step(batch, batch_idx)
+
+    def on_test_epoch_end(self):
+        metrics = self.metrics.compute()
+        self.metrics.reset()
+        for name, value in metrics.items():
+            self.log(f"test_{name}", value)

@@ -1,0 +1,209 @@
+/*
+ * hnm_b200.h -- C ABI of libhnm_b200.so: the B200 (sm_100a) scoring hot path of
+ * hyunlord/hnm_recommendation (LightGCN propagate -> full-catalog score -> top-k,
+ * NeuralCF candidate scoring).
+ *
+ * The reference has no FFI of its own: its hot path is a handful of torch /
+ * torch_sparse library calls inside two Python model classes.  Each entry point
+ * below replaces one of those call sites (cited as file:line relative to the
+ * reference repository root); INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory (outputs and workspaces are caller-allocated);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
+ *     unless stated otherwise and re-entrant across streams;
+ *   - return value: 0 = ok, < 0 = HNM_E_* argument error, > 0 = cudaError_t;
+ *   - nodes [0, num_users) are users and [num_users, num_users+num_items) items
+ *     (src/models/lightgcn.py:70,161-162); embeddings are row-major fp32 [rows, dim].
+ */
+#ifndef HNM_B200_H_
+#define HNM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HNM_API __attribute__((visibility("default")))
+#else
+#define HNM_API
+#endif
+
+#define HNM_ABI_VERSION 1
+
+#define HNM_OK 0
+#define HNM_E_NULL (-1)      /* required pointer is NULL */
+#define HNM_E_RANGE (-2)     /* size / index argument out of range */
+#define HNM_E_DIM (-3)       /* unsupported embedding dimension */
+#define HNM_E_WORKSPACE (-4) /* workspace too small */
+#define HNM_E_ALIGN (-5)     /* pointer not 16-byte aligned */
+#define HNM_E_ARCH (-6)      /* device is not sm_100 */
+#define HNM_E_DRIVER (-7)    /* driver entry point (tensor map) unavailable */
+
+HNM_API int hnm_abi_version(void);
+/* Static string for any value returned by this library. */
+HNM_API const char* hnm_strerror(int code);
+/* 0 when the current device can run the sm_100a kernels, HNM_E_ARCH otherwise. */
+HNM_API int hnm_check_device(void);
+
+/* ------------------------------------------------------------------------
+ * LightGCN.set_graph                      src/models/lightgcn.py:81-112,114-134
+ *
+ * COO edge list (both directions already present, duplicates allowed, int64 as
+ * the reference passes them) -> self loops appended -> CSR sorted by (row, col)
+ * with duplicates retained, plus dis[i] = deg[i]^-1/2 (inf -> 0) where deg is the
+ * weighted ROW sum.  nnz = num_edges + num_nodes.  The per-edge normalised value
+ * dis[row]*w*dis[col] of the reference is not stored: the propagate kernels fuse
+ * it.  `edge_w` NULL means all ones; then `csr_w` must be NULL too.
+ * `heavy_rows` receives the ids of rows with more than `heavy_threshold`
+ * entries (capacity num_nodes); their count is written to *num_heavy_host.
+ * Synchronises the stream before returning (the count is read back).
+ * ---------------------------------------------------------------------- */
+HNM_API size_t hnm_graph_build_workspace_bytes(int64_t num_nodes, int64_t num_edges, int weighted);
+HNM_API int hnm_graph_build(const int64_t* edge_row, const int64_t* edge_col, const float* edge_w,
+                    int64_t num_edges, int64_t num_nodes,
+                    int32_t* csr_rowptr /* [num_nodes+1] */, int32_t* csr_col /* [nnz] */,
+                    float* csr_w /* [nnz] or NULL */, float* dis /* [num_nodes] */,
+                    int32_t heavy_threshold, int32_t* heavy_rows, int32_t* num_heavy_host,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * LightGCN.forward                              src/models/lightgcn.py:147-158
+ *
+ * hnm_lightgcn_prescale:  xs[i] = dis[i] * e0[i];  acc[i] = alpha0 * e0[i]
+ *     (the `final = 0; final += alpha[0] * E_0` step, :156-158, fused with the
+ *     degree pre-scaling that lets the gather loop skip per-edge weights).
+ * hnm_lightgcn_layer:  for rows in [row_begin, row_end):
+ *         e      = dis[i] * sum_{j in row i} w_ij * xs_in[col_j]      (= (A_hat E)_i, :152)
+ *         xs_out[i] = dis[i] * e            (skipped when xs_out is NULL: last layer)
+ *         acc[i]   += alpha * e             (:158)
+ *     Rows listed in heavy_rows are summed by a whole thread block, the rest by
+ *     one warp each.  Row ranges let several GPUs own disjoint row shards.
+ * ---------------------------------------------------------------------- */
+HNM_API int hnm_lightgcn_prescale(const float* e0, const float* dis, float alpha0, float* xs, float* acc,
+                          int64_t num_rows, int32_t dim, void* stream);
+HNM_API int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_col, const float* csr_w,
+                       const float* dis, const float* xs_in, float* xs_out, float* acc, float alpha,
+                       int64_t num_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
+                       const int32_t* heavy_rows, int32_t num_heavy, int32_t heavy_threshold,
+                       void* stream);
+
+/* ------------------------------------------------------------------------
+ * LightGCN.predict                              src/models/lightgcn.py:180-184
+ * out[b] = dot(user_emb[user_ids[b]], item_emb[item_ids[b]]) in fp32.
+ * ---------------------------------------------------------------------- */
+HNM_API int hnm_pair_scores(const float* user_emb, const float* item_emb, const int64_t* user_ids,
+                    const int64_t* item_ids, int64_t batch, int32_t dim, int64_t num_users,
+                    int64_t num_items, float* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * LightGCN.predict_all_items                    src/models/lightgcn.py:199-202
+ * scores[b, j] = dot(user_emb[user_ids[b]], item_emb[j]) for all j, fp32 FMA.
+ * user_ids NULL means users 0..batch-1.
+ * ---------------------------------------------------------------------- */
+HNM_API int hnm_score_all_items(const float* user_emb, const float* item_emb, const int64_t* user_ids,
+                        int64_t batch, int64_t num_items, int32_t dim, float* scores /* [batch, num_items] */,
+                        void* stream);
+
+/* ------------------------------------------------------------------------
+ * LightGCN.recommend, exact reference path      src/models/lightgcn.py:345-356
+ *
+ * For each listed user: fp64 score of every item in [item_begin, item_end)
+ * (products of fp32 inputs are exact in fp64; accumulated k = 0..dim-1 in that
+ * order), optional exclusion (scores[i, filter] = -inf, :349-353) and the top-k
+ * by (score desc, item id asc).  Never materialises the score matrix.  This is
+ * the correctness anchor and the fallback for users the tensor-core path cannot
+ * certify.  excl_ptr/excl_items: CSR over the `batch` listed users of excluded
+ * GLOBAL item ids (NULL = none).  When fewer than k items remain, the tail is
+ * filled with score -inf and the smallest excluded ids (ascending).
+ * out_ids are GLOBAL item indices (item_begin is added).
+ * ---------------------------------------------------------------------- */
+HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const int64_t* user_ids, int64_t batch,
+                   int64_t item_begin, int64_t item_end, int32_t dim, int32_t k,
+                   const int64_t* excl_ptr, const int64_t* excl_items,
+                   int64_t* out_ids /* [batch, k] */, double* out_scores /* [batch, k] */, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused full-catalog score + top-k (tensor cores)   replaces lightgcn.py:202 + :356
+ *
+ * Stage 1  hnm_score_pack:      fp32 rows -> fp16 rows scaled by a power of two
+ *          (row-major [rows_padded, dim], zero padded), also sum-of-squares per row.
+ * Stage 2  hnm_score_topk_fused: TMA-fed tcgen05.mma (fp16 x fp16 -> fp32 in TMEM),
+ *          epilogue keeps, per user, every item whose approximate score beats a
+ *          running threshold; emits `cand_per_user` candidate ids + the final
+ *          threshold.  The [users, items] score matrix never exists in memory.
+ * Stage 3  hnm_rescore_topk:    exact fp64 scores of the candidates, canonical
+ *          (score desc, id asc) top-k, and a per-user certificate that no
+ *          non-candidate can belong to the top-k given the fp16 error bound.
+ * Users whose certificate fails are re-run through hnm_topk_exact by the caller.
+ * ---------------------------------------------------------------------- */
+#define HNM_FUSED_DIM 64            /* embedding dimension of the tensor-core path */
+#define HNM_FUSED_USER_TILE 128     /* users per CTA tile (UMMA M) */
+#define HNM_FUSED_ITEM_TILE 256     /* items per MMA tile (UMMA N) */
+#define HNM_FUSED_CAND 32           /* candidates emitted per user */
+
+HNM_API int hnm_score_pack(const float* emb, const int64_t* row_ids /* NULL = identity */, int64_t num_rows,
+                   int64_t rows_padded, int32_t dim, float scale /* power of two */,
+                   void* out_f16 /* [rows_padded, dim] __half */, float* out_sumsq /* [num_rows] or NULL */,
+                   void* stream);
+/* max |x| over a [rows, dim] fp32 table -> *out_absmax (device float, must be zeroed by the caller). */
+HNM_API int hnm_absmax(const float* emb, int64_t count, float* out_absmax, void* stream);
+
+HNM_API size_t hnm_score_topk_fused_workspace_bytes(int64_t users_padded, int64_t items_padded);
+HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */, int64_t num_users, int64_t users_padded,
+                         const void* items_f16 /* [items_padded, 64] */, int64_t num_items, int64_t items_padded,
+                         int32_t* cand_ids /* [num_users, HNM_FUSED_CAND], -1 = empty, LOCAL item index */,
+                         float* cand_thresh /* [num_users] largest approx score any non-candidate may have */,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb, const int64_t* user_ids /* NULL = identity */,
+                     int64_t batch, int32_t dim, int64_t item_begin, int64_t num_items_local,
+                     const int32_t* cand_ids, int32_t cand_per_user, const float* cand_thresh,
+                     float inv_scale_product /* 1/(user_scale*item_scale) */, float max_item_norm,
+                     const int64_t* excl_ptr, const int64_t* excl_items,
+                     int32_t k, int64_t* out_ids /* [batch,k] GLOBAL item ids */, double* out_scores /* [batch,k] */,
+                     int32_t* out_certified /* [batch] 1 = provably exact */, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU merge of per-shard exact top-k lists (no reference counterpart;
+ * BASELINE.json north_star: item-catalog shards + allgather + merge).
+ * in_ids/in_scores: [num_shards, batch, k]; output the global top-k by
+ * (score desc, id asc).
+ * ---------------------------------------------------------------------- */
+HNM_API int hnm_merge_topk(const int64_t* in_ids, const double* in_scores, int32_t num_shards, int64_t batch,
+                   int32_t k, int64_t* out_ids, double* out_scores, void* stream);
+
+/* ------------------------------------------------------------------------
+ * NeuralCF.forward / predict_all_items          src/models/neural_cf.py:125-139,167-206
+ *
+ * Architecture handled by the fused kernels: GMF(mf_dim) + MLP with exactly
+ * two Linear layers [2h -> h1 -> h2] + Linear(mf_dim + h2 -> 1), the reference
+ * default (mf_dim 64, mlp_dims [128, 64, 32]; configs/model/neural_cf.yaml).
+ * Layer 1 is separable:  W1 [mu; mi] + b1 = (W1[:, :h] mu) + (W1[:, h:] mi + b1);
+ * hnm_ncf_precompute builds those two tables once per weight update.
+ * ---------------------------------------------------------------------- */
+HNM_API int hnm_ncf_precompute(const float* mlp_emb /* [rows, h] */, int64_t rows, int32_t h,
+                       const float* w1 /* [h1, 2h] row-major */, int32_t h1, int32_t col_offset /* 0 users, h items */,
+                       const float* bias /* [h1] or NULL */, float* out /* [rows, h1] */, void* stream);
+HNM_API int hnm_ncf_score_pairs(const float* gmf_user, const float* gmf_item, const float* pu /* [U,h1] */,
+                        const float* qi /* [I,h1] */, const float* w2 /* [h2,h1] */, const float* b2,
+                        const float* wp /* [mf_dim + h2] */, float bp, const int64_t* user_ids,
+                        const int64_t* item_ids, int64_t num_pairs, int32_t mf_dim, int32_t h1, int32_t h2,
+                        float* out, void* stream);
+/* candidates laid out [num_users_listed, cand_per_user]; user_ids has one id per row. */
+HNM_API int hnm_ncf_score_candidates(const float* gmf_user, const float* gmf_item, const float* pu, const float* qi,
+                             const float* w2, const float* b2, const float* wp, float bp,
+                             const int64_t* user_ids /* NULL = identity */, int64_t num_rows,
+                             const int32_t* cand_items /* [num_rows, cand_per_user] or NULL = items 0..cand_per_user-1 */,
+                             int32_t cand_per_user, int32_t mf_dim, int32_t h1, int32_t h2,
+                             float* out /* [num_rows, cand_per_user] */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNM_B200_H_ */

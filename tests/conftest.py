@@ -60,3 +60,39 @@ def assert_close(actual, expected, rtol=1e-5, atol_scale=1e-6, what=""):
     assert not bool(bad.any()), (
         f"{what}: {int(bad.sum())} of {bad.numel()} outside rtol={rtol} atol={atol:.3e}; "
         f"max err {float(err.max()):.3e}")
+
+
+@pytest.fixture(scope="session")
+def hnm_lib():
+    """The built C-ABI library (compiled in-tree on first use; no GPU needed to build or load)."""
+    from hnm_recommendation_b200 import _lib, build
+    build.build_library()
+    return _lib.load()
+
+
+def assert_topk_matches_scores(got_ids, ref_scores, k, rel_tol=1e-6):
+    """Near-tie-aware top-k check against a full fp64 reference score matrix.
+
+    Row r passes when got_ids[r] are distinct, and ranking them by the reference scores
+    is as good as the true ranking position by position up to rel_tol * max|score| --
+    i.e. a mismatch against the canonical list can only involve items whose reference
+    scores differ by less than the tolerance.  Returns the number of rows that differ
+    from the canonical (score desc, id asc) list at all.
+    """
+    got = torch.as_tensor(got_ids).cpu()
+    s = torch.as_tensor(ref_scores).double().cpu()
+    canon = torch.sort(s, dim=1, descending=True, stable=True)
+    want_ids, want_s = canon.indices[:, :k], canon.values[:, :k]
+    assert got.shape == want_ids.shape
+    differ = (got != want_ids).any(dim=1)
+    if differ.any():
+        rows = differ.nonzero().view(-1)
+        g = torch.gather(s[rows], 1, got[rows])
+        finite = torch.where(torch.isfinite(s[rows]), s[rows].abs(), torch.zeros_like(s[rows]))
+        tol = rel_tol * finite.max(dim=1, keepdim=True).values
+        w = want_s[rows]
+        ok = (g >= w - tol) | (torch.isinf(w) & torch.isinf(g))
+        assert bool(ok.all()), f"{int((~ok).any(dim=1).sum())} rows differ beyond near-ties"
+        for r in range(rows.numel()):
+            assert len(set(got[rows[r]].tolist())) == k, "duplicate ids in a top-k row"
+    return int(differ.sum())

@@ -1,0 +1,91 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol the header declares;
+the model mirrors keep the reference's API; host-side helpers."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(hnm_lib):
+    hdr = open(os.path.join(ROOT, "include", "hnm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hnm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 10
+    missing = [n for n in sorted(declared) if not hasattr(hnm_lib, n)]
+    assert not missing, f"declared in include/hnm_b200.h but not exported: {missing}"
+    from hnm_recommendation_b200 import _lib
+    assert declared == set(_lib._SIGNATURES), "ctypes signature table out of sync with the header"
+
+
+def test_abi_version_and_strerror(hnm_lib):
+    assert hnm_lib.hnm_abi_version() == 1
+    assert hnm_lib.hnm_strerror(0) == b"ok"
+    assert b"NULL" in hnm_lib.hnm_strerror(-1)
+    assert hnm_lib.hnm_strerror(-3) != hnm_lib.hnm_strerror(-2)
+    assert hnm_lib.hnm_graph_build_workspace_bytes(0, 0, 0) == 0
+
+
+def test_lightgcn_constructor_contract():
+    # tests/test_models.py:162-171 of the reference
+    from hnm_recommendation_b200 import LightGCN
+    m = LightGCN(num_users=100, num_items=50, embedding_dim=16, top_k=5, num_layers=3)
+    assert (m.num_users, m.num_items, m.num_layers, m.embedding_dim, m.top_k) == (100, 50, 3, 16, 5)
+    assert len(m.alpha) == 4 and m.alpha == [0.25] * 4
+    assert m.graph is None
+    assert list(m.state_dict().keys()) == ["embeddings.weight"]
+    assert tuple(m.embeddings.weight.shape) == (150, 16)
+    bound = (6.0 / (150 + 16)) ** 0.5
+    assert float(m.embeddings.weight.abs().max()) <= bound
+    m2 = LightGCN(10, 5, alpha=0.5, num_layers=2)
+    assert m2.alpha == pytest.approx([4 / 7, 2 / 7, 1 / 7])
+    assert vars(m2.hparams)["alpha"] == 0.5 and vars(m2.hparams)["num_users"] == 10
+
+
+def test_forward_before_set_graph_raises():
+    from hnm_recommendation_b200 import LightGCN
+    m = LightGCN(4, 3, embedding_dim=8)
+    with pytest.raises(RuntimeError, match="Graph not set"):
+        m.forward()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(hnm_lib):
+    from hnm_recommendation_b200 import LightGCN
+    m = LightGCN(4, 3, embedding_dim=8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.set_graph(torch.tensor([[0, 4], [4, 0]]))
+
+
+def test_exclusion_csr_host_logic():
+    from hnm_recommendation_b200 import engine
+    uids = torch.tensor([5, 2, 5, 9])
+    ptr, items = engine.exclusion_csr(uids, {5: {7, 3}, 9: set(), 1: {4}}, "cpu")
+    assert ptr.tolist() == [0, 2, 2, 4, 4] and items.tolist() == [3, 7, 3, 7]
+    assert engine.exclusion_csr(uids, None, "cpu") == (None, None)
+    assert engine.exclusion_csr(uids, {1: {2}}, "cpu") == (None, None)
+
+
+def test_synth_is_deterministic_and_shaped():
+    from hnm_recommendation_b200 import synth
+    a = synth.interactions(1000, 300, 20000, seed=7)
+    b = synth.interactions(1000, 300, 20000, seed=7)
+    assert np.array_equal(a.users, b.users) and np.array_equal(a.items, b.items)
+    assert a.users.shape == (20000,) and np.bincount(a.users, minlength=1000).min() >= 1
+    assert a.items.min() >= 0 and a.items.max() < 300
+    ei = a.edge_index()
+    assert tuple(ei.shape) == (2, 40000) and int(ei[1, :20000].min()) >= 1000
+    assert torch.equal(ei[0, :20000], ei[1, 20000:])
+
+
+def test_metrics_standin():
+    from hnm_recommendation_b200.metrics import RecommendationMetrics
+    m = RecommendationMetrics(top_k=3)
+    m.update(torch.tensor([[1, 2, 3], [4, 5, 6]]), [[1, 3], [9]])
+    out = m.compute()
+    assert set(out) == {"map_at_k", "recall_at_k", "precision_at_k", "ndcg_at_k"}
+    assert out["recall_at_k"] == pytest.approx(0.5) and out["precision_at_k"] == pytest.approx(1 / 3)
+    assert out["map_at_k"] == pytest.approx((1 + 2 / 3) / 2 / 2)

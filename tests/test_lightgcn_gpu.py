@@ -1,0 +1,186 @@
+"""Parity of the CUDA LightGCN path (through the C ABI) against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from conftest import (assert_close, assert_topk_matches_scores, filter_dict, golden_files, load_golden)
+
+pytestmark = pytest.mark.gpu
+LG = golden_files("lightgcn")
+
+
+def _model_from_golden(g):
+    from hnm_recommendation_b200 import LightGCN
+    alpha = None if np.isnan(g["alpha"]) else float(g["alpha"])
+    m = LightGCN(int(g["num_users"]), int(g["num_items"]), embedding_dim=int(g["embedding_dim"]),
+                 num_layers=int(g["num_layers"]), top_k=int(g["top_k"]), alpha=alpha)
+    m.load_state_dict({"embeddings.weight": torch.from_numpy(g["weight"])})
+    m = m.to("cuda")
+    ew = torch.from_numpy(g["edge_weight"]) if g["edge_weight"].size else None
+    m.set_graph(torch.from_numpy(g["edge_index"]), ew)
+    return m
+
+
+@pytest.mark.parametrize("path", LG, ids=lambda p: p.split("lightgcn_")[-1][:-4])
+def test_golden_forward_and_scores(hnm_lib, path):
+    g = load_golden(path)
+    m = _model_from_golden(g)
+    ue, ie = m.forward()
+    assert ue.shape == (m.num_users, m.embedding_dim) and ie.shape == (m.num_items, m.embedding_dim)
+    assert_close(ue, g["user_emb"], what="user_emb")          # P1: rtol 1e-5 (BASELINE.json north_star)
+    assert_close(ie, g["item_emb"], what="item_emb")
+    uids = torch.from_numpy(g["user_ids"])
+    assert_close(m.predict_all_items(uids), g["scores"], what="scores")
+    assert_close(m.predict(uids, torch.from_numpy(g["item_ids"])), g["pair_scores"], what="pair")
+
+
+@pytest.mark.parametrize("path", LG, ids=lambda p: p.split("lightgcn_")[-1][:-4])
+def test_golden_recommend(hnm_lib, path):
+    g = load_golden(path)
+    m = _model_from_golden(g)
+    k = int(g["top_k"])
+    uids = torch.from_numpy(g["user_ids"])
+    # end to end (own embeddings): equal to the reference's list up to near-ties (P3)
+    got = m.recommend(uids)
+    assert got.dtype == torch.int64 and tuple(got.shape) == (uids.numel(), k)
+    s64 = O.exact_scores_fp64(torch.from_numpy(g["user_emb"]), torch.from_numpy(g["item_emb"]), uids)
+    assert_topk_matches_scores(got, s64, k)
+    fd = filter_dict(g)
+    got_f = m.recommend(uids, filter_items=fd)
+    s64f = O.apply_filter(s64.clone(), uids, fd)
+    assert_topk_matches_scores(got_f, s64f, k)
+
+
+@pytest.mark.parametrize("path", LG, ids=lambda p: p.split("lightgcn_")[-1][:-4])
+def test_golden_topk_stagewise_bit_exact(hnm_lib, path):
+    """P2: fed with the reference's own embedding tensors, ids and fp64 scores are bit-identical to the oracle."""
+    from hnm_recommendation_b200 import engine
+    g = load_golden(path)
+    k = int(g["top_k"])
+    ue, ie = torch.from_numpy(g["user_emb"]), torch.from_numpy(g["item_emb"])
+    uids = torch.from_numpy(g["user_ids"])
+    want_ids, want_s = O.recommend_exact(ue, ie, uids, k)
+    ids, sc = engine.topk_exact(ue.cuda(), ie.cuda(), uids, k)
+    assert torch.equal(ids.cpu(), want_ids)
+    assert torch.equal(sc.cpu(), want_s)
+    fd = filter_dict(g)
+    want_ids, want_s = O.recommend_exact(ue, ie, uids, k, fd)
+    ids, sc = engine.topk_exact(ue.cuda(), ie.cuda(), uids, k, engine.exclusion_csr(uids, fd, "cuda"))
+    assert torch.equal(ids.cpu(), want_ids) and torch.equal(sc.cpu(), want_s)
+    # and they agree with the reference's fp32 list wherever that list is not a near-tie
+    assert_topk_matches_scores(torch.from_numpy(g["topk_canonical"]), O.exact_scores_fp64(ue, ie, uids), k)
+
+
+def _config1():
+    from hnm_recommendation_b200 import synth
+    data = synth.interactions(*synth.CONFIG1, seed=42)
+    n = data.num_users + data.num_items
+    return data, synth.xavier_embeddings(n, 64, seed=42)
+
+
+def test_config1_forward_matches_oracle(hnm_lib):
+    """BASELINE.json configs[0]: 10k users x 5k items x 200k interactions, d=64, L=3."""
+    from hnm_recommendation_b200 import LightGCN
+    data, w = _config1()
+    ei = data.edge_index()
+    orc = O.LightGCNOracle(data.num_users, data.num_items, 64, 3, 12, weight=w)
+    orc.set_graph(ei)
+    ou, oi = orc.forward()
+    m = LightGCN(data.num_users, data.num_items).to("cuda")
+    m.load_state_dict({"embeddings.weight": w})
+    m.set_graph(ei)
+    assert int(m.graph.nnz) == 2 * 200_000 + 15_000
+    assert torch.equal(m.graph.rowptr.cpu().long(), orc.graph[0])
+    assert torch.equal(m.graph.col.cpu().long(), orc.graph[1])
+    assert_close(m.graph.dis, orc.graph[3], rtol=2e-7, atol_scale=0, what="dis")
+    gu, gi = m.forward()
+    assert_close(gu, ou, what="users")
+    assert_close(gi, oi, what="items")
+    # cached forward returns the same buffer until the weights change
+    assert m.forward()[0].data_ptr() == gu.data_ptr()
+    with torch.no_grad():
+        m.embeddings.weight.mul_(2.0)
+    gu2, _ = m.forward()
+    assert_close(gu2, 2 * ou, what="users after in-place weight update")
+
+
+def test_config1_topk_all_users_bit_exact(hnm_lib):
+    from hnm_recommendation_b200 import engine
+    data, w = _config1()
+    orc = O.LightGCNOracle(data.num_users, data.num_items, 64, 3, 12, weight=w)
+    orc.set_graph(data.edge_index())
+    ou, oi = orc.forward()
+    uids = torch.arange(data.num_users)
+    want_ids, want_s = O.recommend_exact(ou, oi, uids, 12)
+    ids, sc = engine.topk_exact(ou.cuda(), oi.cuda(), None, 12)
+    assert torch.equal(ids.cpu(), want_ids) and torch.equal(sc.cpu(), want_s)
+    # reference-faithful fp32 sgemm + stable sort agrees except at near-ties; count them
+    ref32 = O.recommend(ou, oi, uids, 12)
+    n_diff = int((ref32 != want_ids).any(dim=1).sum())
+    assert n_diff <= 20, f"{n_diff} users differ between fp32-sgemm and exact ordering"
+    # item-sharded: two shards merged == unsharded
+    half = data.num_items // 2
+    a = engine.topk_exact(ou.cuda(), oi[:half].cuda().contiguous(), None, 12, item_begin=0)
+    b = engine.topk_exact(ou.cuda(), oi[half:].cuda().contiguous(), None, 12, item_begin=half)
+    mi, ms = engine.merge_topk(torch.stack([a[0], b[0]]), torch.stack([a[1], b[1]]))
+    assert torch.equal(mi.cpu(), want_ids) and torch.equal(ms.cpu(), want_s)
+
+
+def test_ties_and_filter_edge_cases(hnm_lib):
+    from hnm_recommendation_b200 import engine
+    # identical item rows -> exact ties -> id ascending
+    ue = torch.tensor([[1.0, 0.0, 2.0, 0.5]] * 3)
+    ie = torch.tensor([[1.0, 1.0, 1.0, 1.0]] * 6 + [[2.0, 2.0, 2.0, 2.0]] * 2 + [[-1.0, 0, 0, 0]] * 2)
+    ids, sc = engine.topk_exact(ue.cuda(), ie.cuda(), None, 5)
+    assert ids.cpu().tolist() == [[6, 7, 0, 1, 2]] * 3
+    # k == num_items, all items returned once
+    ids, _ = engine.topk_exact(ue.cuda(), ie.cuda(), None, 10)
+    assert sorted(ids[0].cpu().tolist()) == list(range(10))
+    # filtering leaves fewer than k finite scores: -inf tail, smallest excluded ids first
+    uids = torch.tensor([0, 1])
+    excl = engine.exclusion_csr(uids, {0: {6, 7, 0, 1, 2, 3, 4, 5, 9}, 1: set()}, "cuda")
+    ids, sc = engine.topk_exact(ue.cuda(), ie.cuda(), uids, 4, excl)
+    assert ids.cpu().tolist() == [[8, 0, 1, 2], [6, 7, 0, 1]]
+    assert sc[0, 1:].cpu().tolist() == [float("-inf")] * 3
+    want_ids, _ = O.recommend_exact(ue, ie, uids, 4, {0: {6, 7, 0, 1, 2, 3, 4, 5, 9}})
+    assert torch.equal(ids.cpu(), want_ids)
+    # empty batch
+    ids, sc = engine.topk_exact(ue.cuda(), ie.cuda(), torch.zeros(0, dtype=torch.int64), 3)
+    assert tuple(ids.shape) == (0, 3)
+
+
+def test_api_errors_and_dims(hnm_lib):
+    from hnm_recommendation_b200 import LightGCN
+    m = LightGCN(20, 10, embedding_dim=12, num_layers=2, top_k=3).to("cuda")   # dim 12 -> generic kernel
+    with pytest.raises(RuntimeError, match="Graph not set"):
+        m.recommend(torch.tensor([0]))
+    u = torch.randint(0, 20, (60,))
+    i = torch.randint(0, 10, (60,)) + 20
+    ei = torch.stack([torch.cat([u, i]), torch.cat([i, u])])
+    m.set_graph(ei)
+    orc = O.LightGCNOracle(20, 10, 12, 2, 3, weight=m.embeddings.weight.detach().cpu())
+    orc.set_graph(ei)
+    assert_close(m.forward()[0], orc.forward()[0], what="dim12 users")
+    assert_close(m.forward()[1], orc.forward()[1], what="dim12 items")
+    with pytest.raises(RuntimeError, match="out of range"):
+        m.recommend(torch.tensor([0]), k=11)
+    with pytest.raises(IndexError):
+        m.predict_all_items(torch.tensor([20]))
+    with pytest.raises(IndexError):
+        m.predict(torch.tensor([0]), torch.tensor([10]))
+    assert m.recommend(torch.tensor([3, 4]), k=10).shape == (2, 10)
+    assert not m.training                                        # recommend() leaves the module in eval mode
+    with pytest.raises(Exception):
+        m.set_graph(torch.tensor([[0, 99], [99, 0]]))            # node id out of range
+
+
+def test_large_k_falls_back_to_device_sort(hnm_lib):
+    from hnm_recommendation_b200 import LightGCN
+    m = LightGCN(16, 400, embedding_dim=16, top_k=300).to("cuda")
+    u = torch.randint(0, 16, (500,)); i = torch.randint(0, 400, (500,)) + 16
+    m.set_graph(torch.stack([torch.cat([u, i]), torch.cat([i, u])]))
+    got = m.recommend(torch.arange(16))
+    ue, ie = m.forward()
+    s = O.exact_scores_fp64(ue.cpu(), ie.cpu(), torch.arange(16))
+    assert_topk_matches_scores(got, s, 300, rel_tol=1e-5)
