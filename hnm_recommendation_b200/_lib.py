@@ -21,6 +21,7 @@ P = C.c_void_p
 I64 = C.c_int64
 I32 = C.c_int32
 F32 = C.c_float
+F64 = C.c_double
 SZ = C.c_size_t
 
 _SIGNATURES = {
@@ -36,17 +37,15 @@ _SIGNATURES = {
     "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, P, P, P]),
     "hnm_score_pack": (C.c_int, [P, P, I64, I64, I32, F32, P, P, P]),
     "hnm_absmax": (C.c_int, [P, I64, P, P]),
-    "hnm_score_topk_fused_workspace_bytes": (SZ, [I64, I64]),
-    "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, P, P, P, SZ, P]),
-    "hnm_rescore_topk": (C.c_int, [P, P, P, I64, I32, I64, I64, P, I32, P, F32, F32, P, P, I32, P, P, P, P]),
+    "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, P, I32, P, P, P]),
+    "hnm_rescore_topk": (C.c_int, [P, P, P, I64, I32, I64, P, I32, P, P, F64, F64, P, P, I32, P, P, P, P]),
     "hnm_merge_topk": (C.c_int, [P, P, I32, I64, I32, P, P, P]),
-    "hnm_ncf_precompute": (C.c_int, [P, I64, I32, P, I32, I32, P, P, P]),
-    "hnm_ncf_score_pairs": (C.c_int, [P, P, P, P, P, P, P, F32, P, P, I64, I32, I32, I32, P, P]),
-    "hnm_ncf_score_candidates": (C.c_int, [P, P, P, P, P, P, P, F32, P, I64, P, I32, I32, I32, I32, P, P]),
+    "hnm_ncf_precompute": (C.c_int, [P, I64, I32, P, I32, I32, I32, P, P, P]),
+    "hnm_ncf_score_pairs": (C.c_int, [P, P, P, P, P, P, I32, P, F32, P, P, I64, I32, P, P]),
+    "hnm_ncf_score_candidates": (C.c_int, [P, P, P, P, P, P, I32, P, F32, P, I64, P, I32, I32, P, P]),
 }
 
-_PENDING = {"hnm_score_pack", "hnm_absmax", "hnm_score_topk_fused_workspace_bytes", "hnm_score_topk_fused",
-            "hnm_rescore_topk", "hnm_ncf_precompute", "hnm_ncf_score_pairs", "hnm_ncf_score_candidates"}
+_PENDING = set()
 EXPORTED = tuple(n for n in _SIGNATURES if n not in _PENDING)
 
 

@@ -1,0 +1,250 @@
+// NeuralCF scoring: fused embedding gather + GMF + MLP + prediction layer.
+// Replaces src/models/neural_cf.py:125-139 (forward) and :167-206 (predict_all_items), eval mode.
+//
+// Layer 1 of the MLP is separable over the concatenated input,
+//     W1 [mu ; mi] + b1 = (W1[:, :h] mu) + (W1[:, h:] mi + b1) = P[u] + Q[i],
+// so hnm_ncf_precompute builds P (users) and Q (items, bias folded in) once per weight
+// update and a pair costs one 2*h1-float gather plus the small tail of the MLP.
+// One thread per (user, item) pair; the tail weights sit in shared memory and are read
+// as warp-wide broadcasts.
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxLayers = 8;
+constexpr int kMaxWidth = 256;
+
+struct NcfDims {
+  int num_layers;              // Linear layers in the MLP, first one included
+  int width[kMaxLayers];       // output width of each layer
+  int tail_floats;             // floats in the packed tail (W2, b2, W3, b3, ...)
+};
+
+// out[r, o] = sum_c w1[o, col_offset + c] * emb[r, c] (+ bias[o]); one warp per row.
+__global__ void __launch_bounds__(256)
+ncf_precompute_kernel(const float* __restrict__ emb, int64_t rows, int h, const float* __restrict__ w1, int h1,
+                      int ld, int col_offset, const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ float wt[];   // [h][h1 + 1] transposed slice of W1
+  for (int t = threadIdx.x; t < h * h1; t += blockDim.x) {
+    const int o = t / h, c = t % h;
+    wt[c * (h1 + 1) + o] = w1[(size_t)o * ld + col_offset + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpc) {
+    const float* x = emb + (size_t)r * h;
+    for (int o = lane; o < h1; o += 32) {
+      float s = 0.f;
+      for (int c = 0; c < h; ++c) s = fmaf(wt[c * (h1 + 1) + o], __ldg(x + c), s);
+      if (bias) s += bias[o];
+      out[(size_t)r * h1 + o] = s;
+    }
+  }
+}
+
+// Fast path: mf_dim 64, MLP [128 -> 64 -> 32] (the reference default, configs/model/neural_cf.yaml).
+__global__ void __launch_bounds__(256)
+ncf_score_default_kernel(const float* __restrict__ gu, const float* __restrict__ gi, const float* __restrict__ pu,
+                         const float* __restrict__ qi, const float* __restrict__ tail, const float* __restrict__ wp,
+                         float bp, const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids,
+                         const int32_t* __restrict__ cand_items, int cand_per_user, int64_t total,
+                         float* __restrict__ out) {
+  constexpr int MF = 64, H1 = 64, H2 = 32;
+  __shared__ __align__(16) float s_w2[H2 * H1];
+  __shared__ float s_b2[H2];
+  __shared__ float s_wp[MF + H2];
+  for (int t = threadIdx.x; t < H2 * H1; t += blockDim.x) s_w2[t] = tail[t];
+  for (int t = threadIdx.x; t < H2; t += blockDim.x) s_b2[t] = tail[H2 * H1 + t];
+  for (int t = threadIdx.x; t < MF + H2; t += blockDim.x) s_wp[t] = wp[t];
+  __syncthreads();
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t u, i;
+    if (cand_per_user > 0) {
+      const int64_t r = t / cand_per_user;
+      u = user_ids ? user_ids[r] : r;
+      i = cand_items ? (int64_t)cand_items[t] : t - r * cand_per_user;
+    } else {
+      u = user_ids[t];
+      i = item_ids[t];
+    }
+    const float* p = pu + (size_t)u * H1;
+    const float* q = qi + (size_t)i * H1;
+    float h1[H1];
+#pragma unroll
+    for (int c = 0; c < H1; c += 4) {
+      const float4 a = ldg_f4(p + c), b = ldg_f4(q + c);
+      h1[c] = fmaxf(a.x + b.x, 0.f);
+      h1[c + 1] = fmaxf(a.y + b.y, 0.f);
+      h1[c + 2] = fmaxf(a.z + b.z, 0.f);
+      h1[c + 3] = fmaxf(a.w + b.w, 0.f);
+    }
+    // GMF term: (gu * gi) . wp[:MF]   (neural_cf.py:127,136-139)
+    float y = 0.f;
+    const float* a = gu + (size_t)u * MF;
+    const float* b = gi + (size_t)i * MF;
+#pragma unroll
+    for (int c = 0; c < MF; c += 4) {
+      const float4 x = ldg_f4(a + c), z = ldg_f4(b + c);
+      y = fmaf(s_wp[c], __fmul_rn(x.x, z.x), y);
+      y = fmaf(s_wp[c + 1], __fmul_rn(x.y, z.y), y);
+      y = fmaf(s_wp[c + 2], __fmul_rn(x.z, z.z), y);
+      y = fmaf(s_wp[c + 3], __fmul_rn(x.w, z.w), y);
+    }
+#pragma unroll 4
+    for (int j = 0; j < H2; ++j) {
+      float s = 0.f;
+      const float4* w = reinterpret_cast<const float4*>(s_w2 + j * H1);
+#pragma unroll
+      for (int c = 0; c < H1 / 4; ++c) {
+        const float4 ww = w[c];
+        s = fmaf(ww.x, h1[4 * c], s);
+        s = fmaf(ww.y, h1[4 * c + 1], s);
+        s = fmaf(ww.z, h1[4 * c + 2], s);
+        s = fmaf(ww.w, h1[4 * c + 3], s);
+      }
+      s = fmaxf(s + s_b2[j], 0.f);
+      y = fmaf(s_wp[MF + j], s, y);
+    }
+    out[t] = y + bp;
+  }
+}
+
+// Any depth / width up to kMaxWidth: activations ping-pong through local memory.
+__global__ void __launch_bounds__(128)
+ncf_score_generic_kernel(const float* __restrict__ gu, const float* __restrict__ gi, const float* __restrict__ pu,
+                         const float* __restrict__ qi, const float* __restrict__ tail, NcfDims dims,
+                         const float* __restrict__ wp, float bp, int mf, const int64_t* __restrict__ user_ids,
+                         const int64_t* __restrict__ item_ids, const int32_t* __restrict__ cand_items,
+                         int cand_per_user, int64_t total, float* __restrict__ out) {
+  extern __shared__ float s_tail[];
+  for (int t = threadIdx.x; t < dims.tail_floats; t += blockDim.x) s_tail[t] = tail[t];
+  __syncthreads();
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t u, i;
+    if (cand_per_user > 0) {
+      const int64_t r = t / cand_per_user;
+      u = user_ids ? user_ids[r] : r;
+      i = cand_items ? (int64_t)cand_items[t] : t - r * cand_per_user;
+    } else {
+      u = user_ids[t];
+      i = item_ids[t];
+    }
+    float xa[kMaxWidth], xb[kMaxWidth];
+    const int h1 = dims.width[0];
+    for (int c = 0; c < h1; ++c) xa[c] = fmaxf(pu[(size_t)u * h1 + c] + qi[(size_t)i * h1 + c], 0.f);
+    float* cur = xa;
+    float* nxt = xb;
+    int in = h1, off = 0;
+    for (int l = 1; l < dims.num_layers; ++l) {
+      const int o = dims.width[l];
+      const float* w = s_tail + off;
+      const float* bb = w + o * in;
+      for (int j = 0; j < o; ++j) {
+        float s = 0.f;
+        for (int c = 0; c < in; ++c) s = fmaf(w[j * in + c], cur[c], s);
+        nxt[j] = fmaxf(s + bb[j], 0.f);
+      }
+      off += o * in + o;
+      in = o;
+      float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    float y = 0.f;
+    for (int c = 0; c < mf; ++c) y = fmaf(wp[c], __fmul_rn(gu[(size_t)u * mf + c], gi[(size_t)i * mf + c]), y);
+    for (int j = 0; j < in; ++j) y = fmaf(wp[mf + j], cur[j], y);
+    out[t] = y + bp;
+  }
+}
+
+int fill_dims(NcfDims& d, const int32_t* widths_host, int num_layers) {
+  if (!widths_host) return HNM_E_NULL;
+  if (num_layers < 1 || num_layers > kMaxLayers) return HNM_E_DIM;
+  d.num_layers = num_layers;
+  d.tail_floats = 0;
+  for (int l = 0; l < num_layers; ++l) {
+    d.width[l] = widths_host[l];
+    if (d.width[l] < 1 || d.width[l] > kMaxWidth) return HNM_E_DIM;
+    if (l > 0) d.tail_floats += d.width[l] * d.width[l - 1] + d.width[l];
+  }
+  return HNM_OK;
+}
+
+int launch_score(const float* gu, const float* gi, const float* pu, const float* qi, const float* tail,
+                 const int32_t* widths_host, int num_layers, const float* wp, float bp, int mf,
+                 const int64_t* user_ids, const int64_t* item_ids, const int32_t* cand_items, int cand_per_user,
+                 int64_t total, float* out, cudaStream_t stream) {
+  if (total == 0) return HNM_OK;
+  if (!gu || !gi || !pu || !qi || !wp || !out) return HNM_E_NULL;
+  NcfDims d{};
+  int rc = fill_dims(d, widths_host, num_layers);
+  if (rc != HNM_OK) return rc;
+  if (num_layers > 1 && !tail) return HNM_E_NULL;
+  if (mf < 1 || total < 0) return HNM_E_RANGE;
+  const bool is_default = num_layers == 2 && mf == 64 && d.width[0] == 64 && d.width[1] == 32 &&
+                          hnm_aligned16(gu) && hnm_aligned16(gi) && hnm_aligned16(pu) && hnm_aligned16(qi);
+  if (is_default) {
+    const int T = 256;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + T - 1) / T, (int64_t)hnm_num_sms() * 8);
+    ncf_score_default_kernel<<<grid, T, 0, stream>>>(gu, gi, pu, qi, tail, wp, bp, user_ids, item_ids, cand_items,
+                                                    cand_per_user, total, out);
+  } else {
+    const size_t smem = sizeof(float) * (size_t)d.tail_floats;
+    if (smem > 200 * 1024) return HNM_E_DIM;
+    static bool attr_set = false;
+    if (!attr_set) {
+      HNM_CUDA_TRY(cudaFuncSetAttribute(ncf_score_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+      attr_set = true;
+    }
+    const int T = 128;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + T - 1) / T, (int64_t)hnm_num_sms() * 8);
+    ncf_score_generic_kernel<<<grid, T, smem, stream>>>(gu, gi, pu, qi, tail, d, wp, bp, mf, user_ids, item_ids,
+                                                       cand_items, cand_per_user, total, out);
+  }
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
+}
+
+}  // namespace
+
+extern "C" int hnm_ncf_precompute(const float* mlp_emb, int64_t rows, int32_t h, const float* w1, int32_t h1,
+                                  int32_t w1_cols, int32_t col_offset, const float* bias, float* out,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows == 0) return HNM_OK;
+  if (!mlp_emb || !w1 || !out) return HNM_E_NULL;
+  if (rows < 0 || h < 1 || h1 < 1 || col_offset < 0 || col_offset + h > w1_cols) return HNM_E_RANGE;
+  const size_t smem = sizeof(float) * (size_t)h * (h1 + 1);
+  if (smem > 200 * 1024) return HNM_E_DIM;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HNM_CUDA_TRY(cudaFuncSetAttribute(ncf_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)hnm_num_sms() * 8);
+  ncf_precompute_kernel<<<grid, 256, smem, stream>>>(mlp_emb, rows, h, w1, h1, w1_cols, col_offset, bias, out);
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
+}
+
+extern "C" int hnm_ncf_score_pairs(const float* gmf_user, const float* gmf_item, const float* pu, const float* qi,
+                                   const float* mlp_tail, const int32_t* widths_host, int32_t num_layers,
+                                   const float* wp, float bp, const int64_t* user_ids, const int64_t* item_ids,
+                                   int64_t num_pairs, int32_t mf_dim, float* out, void* stream_) {
+  if (num_pairs > 0 && (!user_ids || !item_ids)) return HNM_E_NULL;
+  return launch_score(gmf_user, gmf_item, pu, qi, mlp_tail, widths_host, num_layers, wp, bp, mf_dim, user_ids,
+                      item_ids, nullptr, 0, num_pairs, out, (cudaStream_t)stream_);
+}
+
+extern "C" int hnm_ncf_score_candidates(const float* gmf_user, const float* gmf_item, const float* pu,
+                                        const float* qi, const float* mlp_tail, const int32_t* widths_host,
+                                        int32_t num_layers, const float* wp, float bp, const int64_t* user_ids,
+                                        int64_t num_rows, const int32_t* cand_items, int32_t cand_per_user,
+                                        int32_t mf_dim, float* out, void* stream_) {
+  if (cand_per_user < 1 || num_rows < 0) return HNM_E_RANGE;
+  return launch_score(gmf_user, gmf_item, pu, qi, mlp_tail, widths_host, num_layers, wp, bp, mf_dim, user_ids,
+                      nullptr, cand_items, cand_per_user, num_rows * cand_per_user, out, (cudaStream_t)stream_);
+}

@@ -1,7 +1,124 @@
-"""Tensor-core full-catalog scorer (placeholder until csrc/score_fused.cu lands)."""
+"""Full-catalog scorer on the tensor cores: pack -> fused score/select -> exact rescore -> fallback.
+
+Replaces ``torch.matmul(user_embeds, item_embeddings.t())`` + ``torch.topk`` of
+src/models/lightgcn.py:202,356.  Exactness does not rest on the fp16 tensor-core
+scores: they only nominate candidates; every returned list is ranked by exact
+fp64 scores and carries a certificate, and users that cannot be certified are
+recomputed by the exact SIMT kernel (hnm_topk_exact).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib, engine
+from ._lib import call, ptr, stream
+
+USER_BLOCK = 512
+ITEM_TILE = 128
+CAND_CAP = 128
+K_MAX = 16
+SEL_MARGIN = 4                 # tau tracks the (k + margin)-th best bucket maximum
+MAX_USERS_PER_LAUNCH = 1 << 21
+
+
+def _pow2_scale(absmax: float) -> float:
+    """Power of two s with absmax * s in [2^14, 2^15): fp16 keeps 11 significant bits, no overflow."""
+    if not (absmax > 0.0) or math.isinf(absmax) or math.isnan(absmax):
+        return 1.0
+    e = 14 - math.floor(math.log2(absmax))
+    return 2.0 ** max(-100, min(100, e))
 
 
 class FusedScorer:
+    """Holds the packed item shard; scores any list of users against it."""
+
     @staticmethod
     def supports(dim: int, k: int, num_items: int) -> bool:
-        return False
+        return dim == 64 and 1 <= k <= K_MAX and num_items >= 2 * ITEM_TILE
+
+    def __init__(self, user_emb: torch.Tensor, item_emb: torch.Tensor, item_begin: int = 0):
+        _lib.require_device()
+        self.user_emb = user_emb.contiguous()
+        self.item_emb = item_emb.contiguous()
+        self.item_begin = item_begin
+        dev = self.item_emb.device
+        self.num_items = int(self.item_emb.size(0))
+        self.items_padded = (self.num_items + ITEM_TILE - 1) // ITEM_TILE * ITEM_TILE
+        with torch.cuda.device(dev):
+            amax = torch.zeros(2, dtype=torch.float32, device=dev)
+            call("hnm_absmax", ptr(self.user_emb), self.user_emb.numel(), amax[0:1].data_ptr(), stream())
+            call("hnm_absmax", ptr(self.item_emb), self.item_emb.numel(), amax[1:2].data_ptr(), stream())
+            au, ai = amax.tolist()
+            self.user_scale, self.item_scale = _pow2_scale(au), _pow2_scale(ai)
+            self.items_f16 = torch.empty(self.items_padded, 64, dtype=torch.float16, device=dev)
+            sumsq = torch.empty(self.num_items, dtype=torch.float32, device=dev)
+            call("hnm_score_pack", ptr(self.item_emb), None, self.num_items, self.items_padded, 64,
+                 self.item_scale, ptr(self.items_f16), ptr(sumsq), stream())
+            # a hair above the fp32 value so the bound stays an upper bound
+            self.max_item_norm = math.sqrt(float(sumsq.max())) * (1.0 + 1e-6)
+        self.inv_scale = 1.0 / (self.user_scale * self.item_scale)
+        self.last_stats: Dict[str, int] = {}
+
+    def topk(self, user_ids: Optional[torch.Tensor], k: int, filter_items: Optional[Dict[int, set]] = None,
+             fallback: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """ids [B,k] int64 (global item indices), scores [B,k] fp64; canonical (score desc, id asc)."""
+        dev = self.item_emb.device
+        uids = engine._norm_ids(user_ids, self.user_emb.size(0), dev)
+        total = uids.numel() if uids is not None else int(self.user_emb.size(0))
+        ids = torch.empty(total, k, dtype=torch.int64, device=dev)
+        sc = torch.empty(total, k, dtype=torch.float64, device=dev)
+        cert = torch.empty(total, dtype=torch.int32, device=dev)
+        excl = (None, None)
+        if filter_items is not None:
+            if uids is None:
+                uids = torch.arange(total, device=dev)
+            excl = engine.exclusion_csr(uids, filter_items, dev)
+        for b0 in range(0, total, MAX_USERS_PER_LAUNCH):
+            b1 = min(total, b0 + MAX_USERS_PER_LAUNCH)
+            self._launch(uids, b0, b1, k, excl, ids, sc, cert)
+        self.last_stats = {"users": total, "uncertified": 0}
+        if fallback and total:
+            bad = (cert == 0).nonzero().view(-1)
+            n_bad = int(bad.numel())
+            self.last_stats["uncertified"] = n_bad
+            if n_bad:
+                bad_uids = bad if uids is None else uids[bad]
+                sub_excl = (None, None)
+                if excl[0] is not None:
+                    sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev)
+                e_ids, e_sc = engine.topk_exact(self.user_emb, self.item_emb, bad_uids, k, sub_excl,
+                                                item_begin=self.item_begin)
+                ids[bad] = e_ids
+                sc[bad] = e_sc
+        return ids, sc
+
+    def _launch(self, uids, b0, b1, k, excl, ids, sc, cert) -> None:
+        dev = self.item_emb.device
+        n = b1 - b0
+        padded = (n + USER_BLOCK - 1) // USER_BLOCK * USER_BLOCK
+        with torch.cuda.device(dev):
+            s = stream()
+            users_f16 = torch.empty(padded, 64, dtype=torch.float16, device=dev)
+            if uids is None:
+                src = self.user_emb[b0:b1]
+                call("hnm_score_pack", ptr(src), None, n, padded, 64, self.user_scale, ptr(users_f16), None, s)
+                rid = None
+                user_base = src
+            else:
+                rid = uids[b0:b1]
+                call("hnm_score_pack", ptr(self.user_emb), ptr(rid), n, padded, 64, self.user_scale, ptr(users_f16),
+                     None, s)
+                user_base = self.user_emb
+            cand = torch.empty(n, CAND_CAP, 2, dtype=torch.int32, device=dev)
+            count = torch.empty(n, dtype=torch.int32, device=dev)
+            thresh = torch.empty(n, dtype=torch.float32, device=dev)
+            call("hnm_score_topk_fused", ptr(users_f16), n, padded, ptr(self.items_f16), self.num_items,
+                 self.items_padded, min(32, k + SEL_MARGIN), ptr(cand), CAND_CAP, ptr(count), ptr(thresh), s)
+            ex_ptr = excl[0][b0:b1 + 1] if excl[0] is not None else None
+            call("hnm_rescore_topk", ptr(user_base), ptr(self.item_emb), ptr(rid), n, 64, self.item_begin,
+                 ptr(cand), CAND_CAP, ptr(count), ptr(thresh), self.inv_scale, self.max_item_norm,
+                 ptr(ex_ptr), ptr(excl[1]), k, ptr(ids[b0:b1]), ptr(sc[b0:b1]), ptr(cert[b0:b1]), s)
+        self._debug = (count, thresh)

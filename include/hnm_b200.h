@@ -131,41 +131,47 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
 /* ------------------------------------------------------------------------
  * Fused full-catalog score + top-k (tensor cores)   replaces lightgcn.py:202 + :356
  *
- * Stage 1  hnm_score_pack:      fp32 rows -> fp16 rows scaled by a power of two
- *          (row-major [rows_padded, dim], zero padded), also sum-of-squares per row.
- * Stage 2  hnm_score_topk_fused: TMA-fed tcgen05.mma (fp16 x fp16 -> fp32 in TMEM),
- *          epilogue keeps, per user, every item whose approximate score beats a
- *          running threshold; emits `cand_per_user` candidate ids + the final
- *          threshold.  The [users, items] score matrix never exists in memory.
- * Stage 3  hnm_rescore_topk:    exact fp64 scores of the candidates, canonical
- *          (score desc, id asc) top-k, and a per-user certificate that no
- *          non-candidate can belong to the top-k given the fp16 error bound.
+ * Stage 1  hnm_absmax + hnm_score_pack: fp32 rows -> fp16 rows scaled by a power of
+ *          two (row-major [rows_padded, 64], zero padded), plus sum of squares per row.
+ * Stage 2  hnm_score_topk_fused: TMA-fed tcgen05.mma (fp16 x fp16 -> fp32 in TMEM);
+ *          the epilogue keeps, per user, every item whose approximate score beats a
+ *          running threshold tau (the kth_sel-th largest of 32 disjoint bucket
+ *          maxima, a lower bound on the kth_sel-th best score).  The [users, items]
+ *          score matrix never exists in memory.  Per user it emits cand_count
+ *          entries {fp32 approx score bits, LOCAL item index} (cand_count may
+ *          exceed cand_cap: overflow, the user is then not certifiable) and the
+ *          final tau: every item that is not a stored candidate scored <= tau.
+ * Stage 3  hnm_rescore_topk: exact fp64 scores (k = 0..dim-1 fma chain) of the
+ *          candidates above tau, optional exclusion (lightgcn.py:349-353), canonical
+ *          (score desc, id asc) top-k, and a per-user certificate
+ *              exact_kth > tau / (su*si) + eps,
+ *              eps = 1.1 * 2^-10 * ||u|| * max_item_norm + dim * 2^-8 / (su*si)
+ *          that no non-candidate can belong to the top-k given the fp16 rounding bound.
  * Users whose certificate fails are re-run through hnm_topk_exact by the caller.
  * ---------------------------------------------------------------------- */
 #define HNM_FUSED_DIM 64            /* embedding dimension of the tensor-core path */
-#define HNM_FUSED_USER_TILE 128     /* users per CTA tile (UMMA M) */
-#define HNM_FUSED_ITEM_TILE 256     /* items per MMA tile (UMMA N) */
-#define HNM_FUSED_CAND 32           /* candidates emitted per user */
+#define HNM_FUSED_USER_TILE 128     /* users per accumulator (UMMA M) */
+#define HNM_FUSED_USER_BLOCK 512    /* users per CTA pass; users_padded must be a multiple */
+#define HNM_FUSED_ITEM_TILE 128     /* items per MMA tile (UMMA N); items_padded must be a multiple */
+#define HNM_FUSED_CAND_MAX 128      /* largest cand_cap */
 
+/* max |x| over `count` floats -> *out_absmax (device float, zeroed by the caller). */
+HNM_API int hnm_absmax(const float* emb, int64_t count, float* out_absmax, void* stream);
 HNM_API int hnm_score_pack(const float* emb, const int64_t* row_ids /* NULL = identity */, int64_t num_rows,
                    int64_t rows_padded, int32_t dim, float scale /* power of two */,
                    void* out_f16 /* [rows_padded, dim] __half */, float* out_sumsq /* [num_rows] or NULL */,
                    void* stream);
-/* max |x| over a [rows, dim] fp32 table -> *out_absmax (device float, must be zeroed by the caller). */
-HNM_API int hnm_absmax(const float* emb, int64_t count, float* out_absmax, void* stream);
-
-HNM_API size_t hnm_score_topk_fused_workspace_bytes(int64_t users_padded, int64_t items_padded);
 HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */, int64_t num_users, int64_t users_padded,
                          const void* items_f16 /* [items_padded, 64] */, int64_t num_items, int64_t items_padded,
-                         int32_t* cand_ids /* [num_users, HNM_FUSED_CAND], -1 = empty, LOCAL item index */,
-                         float* cand_thresh /* [num_users] largest approx score any non-candidate may have */,
-                         void* workspace, size_t workspace_bytes, void* stream);
-
-HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb, const int64_t* user_ids /* NULL = identity */,
-                     int64_t batch, int32_t dim, int64_t item_begin, int64_t num_items_local,
-                     const int32_t* cand_ids, int32_t cand_per_user, const float* cand_thresh,
-                     float inv_scale_product /* 1/(user_scale*item_scale) */, float max_item_norm,
-                     const int64_t* excl_ptr, const int64_t* excl_items,
+                         int32_t kth_sel /* 1..32 */,
+                         void* cand /* [num_users, cand_cap] x {uint32 score bits, uint32 local item} */,
+                         int32_t cand_cap, int32_t* cand_count /* [num_users] */,
+                         float* cand_thresh /* [num_users] final tau (scaled units) */, void* stream);
+HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb /* local shard rows */,
+                     const int64_t* user_ids /* NULL = identity */, int64_t batch, int32_t dim, int64_t item_begin,
+                     const void* cand, int32_t cand_cap, const int32_t* cand_count, const float* cand_thresh,
+                     double inv_scale_product /* 1/(user_scale*item_scale) */, double max_item_norm,
+                     const int64_t* excl_ptr, const int64_t* excl_items /* GLOBAL ids, sorted per user */,
                      int32_t k, int64_t* out_ids /* [batch,k] GLOBAL item ids */, double* out_scores /* [batch,k] */,
                      int32_t* out_certified /* [batch] 1 = provably exact */, void* stream);
 
@@ -181,26 +187,29 @@ HNM_API int hnm_merge_topk(const int64_t* in_ids, const double* in_scores, int32
 /* ------------------------------------------------------------------------
  * NeuralCF.forward / predict_all_items          src/models/neural_cf.py:125-139,167-206
  *
- * Architecture handled by the fused kernels: GMF(mf_dim) + MLP with exactly
- * two Linear layers [2h -> h1 -> h2] + Linear(mf_dim + h2 -> 1), the reference
- * default (mf_dim 64, mlp_dims [128, 64, 32]; configs/model/neural_cf.yaml).
- * Layer 1 is separable:  W1 [mu; mi] + b1 = (W1[:, :h] mu) + (W1[:, h:] mi + b1);
- * hnm_ncf_precompute builds those two tables once per weight update.
+ * Eval-mode logits  y = wp . [gu[u] * gi[i] ; MLP([mu[u] ; mi[i]])] + bp  for any MLP depth
+ * (Linear+ReLU stack, neural_cf.py:85-90).  Layer 1 is separable over the concatenated input:
+ *     W1 [mu ; mi] + b1 = P[u] + Q[i],   P = mu W1[:, :h]^T,   Q = mi W1[:, h:]^T + b1,
+ * hnm_ncf_precompute builds P / Q once per weight update (call it twice).  The remaining
+ * layers are passed packed as `mlp_tail` = W2 (row-major [w2, w1]), b2, W3, b3, ...;
+ * `widths_host` (HOST array, num_layers entries) lists the output width of every MLP
+ * layer, first one included (reference default: {64, 32}).  wp = prediction_layer.weight
+ * ([mf_dim + last width]), bp its bias.
  * ---------------------------------------------------------------------- */
 HNM_API int hnm_ncf_precompute(const float* mlp_emb /* [rows, h] */, int64_t rows, int32_t h,
-                       const float* w1 /* [h1, 2h] row-major */, int32_t h1, int32_t col_offset /* 0 users, h items */,
+                       const float* w1 /* [h1, w1_cols] row-major */, int32_t h1, int32_t w1_cols,
+                       int32_t col_offset /* 0 for users, h for items */,
                        const float* bias /* [h1] or NULL */, float* out /* [rows, h1] */, void* stream);
 HNM_API int hnm_ncf_score_pairs(const float* gmf_user, const float* gmf_item, const float* pu /* [U,h1] */,
-                        const float* qi /* [I,h1] */, const float* w2 /* [h2,h1] */, const float* b2,
-                        const float* wp /* [mf_dim + h2] */, float bp, const int64_t* user_ids,
-                        const int64_t* item_ids, int64_t num_pairs, int32_t mf_dim, int32_t h1, int32_t h2,
-                        float* out, void* stream);
-/* candidates laid out [num_users_listed, cand_per_user]; user_ids has one id per row. */
+                        const float* qi /* [I,h1] */, const float* mlp_tail, const int32_t* widths_host,
+                        int32_t num_layers, const float* wp, float bp, const int64_t* user_ids,
+                        const int64_t* item_ids, int64_t num_pairs, int32_t mf_dim, float* out, void* stream);
+/* out[r, c] for row r = user user_ids[r] (NULL = r) and candidate cand_items[r, c]
+ * (NULL = item c, i.e. predict_all_items when cand_per_user == num_items). */
 HNM_API int hnm_ncf_score_candidates(const float* gmf_user, const float* gmf_item, const float* pu, const float* qi,
-                             const float* w2, const float* b2, const float* wp, float bp,
-                             const int64_t* user_ids /* NULL = identity */, int64_t num_rows,
-                             const int32_t* cand_items /* [num_rows, cand_per_user] or NULL = items 0..cand_per_user-1 */,
-                             int32_t cand_per_user, int32_t mf_dim, int32_t h1, int32_t h2,
+                             const float* mlp_tail, const int32_t* widths_host, int32_t num_layers,
+                             const float* wp, float bp, const int64_t* user_ids, int64_t num_rows,
+                             const int32_t* cand_items, int32_t cand_per_user, int32_t mf_dim,
                              float* out /* [num_rows, cand_per_user] */, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,144 @@
+"""GPU parity: tensor-core score+select path (bit-exact top-k through certificate/fallback) and NeuralCF."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from conftest import assert_close, golden_files, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _emb(u, i, seed, kind="randn"):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "randn":
+        return torch.randn(u, 64, generator=g) * 0.1, torch.randn(i, 64, generator=g) * 0.1
+    # tiny magnitudes like a Xavier-initialised 1.5M-row table, with a common mean (propagated embeddings)
+    base = torch.randn(1, 64, generator=g) * 2e-3
+    return (torch.randn(u, 64, generator=g) * 1e-3 + base), (torch.randn(i, 64, generator=g) * 1e-3 + base)
+
+
+@pytest.mark.parametrize("u,i,kind", [(700, 1000, "randn"), (1537, 5000, "small"), (512, 256, "randn"),
+                                      (130, 4100, "small")])
+def test_fused_topk_bit_exact(hnm_lib, u, i, kind):
+    from hnm_recommendation_b200.scorer import FusedScorer
+    ue, ie = _emb(u, i, seed=u + i, kind=kind)
+    want_ids, want_s = O.recommend_exact(ue, ie, torch.arange(u), 12)
+    sc = FusedScorer(ue.cuda(), ie.cuda())
+    ids, s = sc.topk(None, 12)
+    assert torch.equal(ids.cpu(), want_ids)
+    assert torch.equal(s.cpu(), want_s)
+    # the tensor-core path alone must already certify nearly everyone on generic data
+    assert sc.last_stats["uncertified"] <= max(2, u // 100), sc.last_stats
+    # without the fallback, certified rows are exact and uncertified rows are flagged, never silently wrong
+    ids2, _ = sc.topk(None, 12, fallback=False)
+    same = (ids2.cpu() == want_ids).all(dim=1)
+    assert int((~same).sum()) <= sc.last_stats["uncertified"] or sc.last_stats["uncertified"] == 0
+
+
+def test_fused_subset_filter_and_shard(hnm_lib):
+    from hnm_recommendation_b200.scorer import FusedScorer
+    ue, ie = _emb(900, 3000, seed=5)
+    uids = torch.randperm(900)[:333]
+    filt = {int(x): set(torch.randint(0, 3000, (40,)).tolist()) for x in uids[::2].tolist()}
+    # make sure some filtered items are the user's true best ones
+    top = O.recommend_exact(ue, ie, uids, 12)[0]
+    for r, x in enumerate(uids.tolist()):
+        if x in filt:
+            filt[x].update(top[r, :5].tolist())
+    want_ids, want_s = O.recommend_exact(ue, ie, uids, 12, filt)
+    sc = FusedScorer(ue.cuda(), ie.cuda())
+    ids, s = sc.topk(uids, 12, filt)
+    assert torch.equal(ids.cpu(), want_ids) and torch.equal(s.cpu(), want_s)
+    # item shard [1000, 3000): ids are global
+    shard = FusedScorer(ue.cuda(), ie[1000:].cuda().contiguous(), item_begin=1000)
+    ids, s = shard.topk(uids, 7)
+    w_ids, w_s = O.recommend_exact(ue, ie[1000:], uids, 7)
+    assert torch.equal(ids.cpu(), w_ids + 1000) and torch.equal(s.cpu(), w_s)
+
+
+def test_fused_exact_ties_fall_back(hnm_lib):
+    """Duplicate item rows make exact ties at the cut: the certificate must refuse and the fallback decide by id."""
+    from hnm_recommendation_b200.scorer import FusedScorer
+    ue, ie = _emb(600, 2000, seed=9)
+    ie[1000:] = ie[:1000]                      # every item has a twin 1000 ids later
+    want_ids, want_s = O.recommend_exact(ue, ie, torch.arange(600), 12)
+    sc = FusedScorer(ue.cuda(), ie.cuda())
+    ids, s = sc.topk(None, 12)
+    assert torch.equal(ids.cpu(), want_ids) and torch.equal(s.cpu(), want_s)
+    # top-12 = 6 twins pairs -> the 12th and 13th never tie, but 11th/12th style ties inside are ordered by id
+    assert (ids[:, 0] + 1000 == ids[:, 1]).all()
+
+
+def test_lightgcn_recommend_uses_fused_path(hnm_lib):
+    from hnm_recommendation_b200 import LightGCN, synth
+    data = synth.interactions(3000, 1500, 40000, seed=3)
+    m = LightGCN(data.num_users, data.num_items).to("cuda")
+    with torch.no_grad():
+        m.embeddings.weight.copy_(synth.trained_like_embeddings(4500, 64, seed=3))
+    m.set_graph(data.edge_index())
+    ue, ie = m.forward()
+    uids = torch.arange(0, 3000, 7)
+    got = m.recommend(uids)
+    assert m._scorer is not None
+    want, _ = O.recommend_exact(ue.cpu(), ie.cpu(), uids, 12)
+    assert torch.equal(got.cpu(), want)
+    allu = m.recommend_all()
+    assert torch.equal(allu[uids.cuda()].cpu(), want)
+    # filter = the user's own purchases (serve.py:350-352 semantics)
+    hist = {}
+    for u_, i_ in zip(data.users[:5000].tolist(), data.items[:5000].tolist()):
+        hist.setdefault(u_, set()).add(i_)
+    got_f = m.recommend(uids, filter_items=hist)
+    want_f, _ = O.recommend_exact(ue.cpu(), ie.cpu(), uids, 12, hist)
+    assert torch.equal(got_f.cpu(), want_f)
+
+
+# ------------------------------------------------------------------------------- NeuralCF
+NCF = golden_files("ncf")
+
+
+@pytest.mark.parametrize("path", NCF, ids=lambda p: p.split("ncf_")[-1][:-4])
+def test_ncf_golden(hnm_lib, path):
+    from hnm_recommendation_b200 import NeuralCF
+    g = load_golden(path)
+    m = NeuralCF(int(g["num_users"]), int(g["num_items"]), mf_dim=int(g["mf_dim"]),
+                 mlp_dims=[int(x) for x in g["mlp_dims"]], top_k=int(g["top_k"]))
+    state = {k[len("state."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state.")}
+    assert set(state) == set(m.state_dict().keys())            # checkpoint-key compatibility
+    m.load_state_dict(state)
+    m = m.to("cuda").eval()
+    logits = m(torch.from_numpy(g["user_ids"]), torch.from_numpy(g["item_ids"]))
+    assert_close(logits, g["logits"], rtol=1e-5, atol_scale=1e-6, what="logits")     # P4
+    one = m(torch.from_numpy(g["user_ids"][:1]), torch.from_numpy(g["item_ids"][:1]))
+    assert one.dim() == 0
+    alls = m.predict_all_items(torch.from_numpy(g["all_user_ids"]))
+    assert_close(alls, g["all_scores"], rtol=1e-5, atol_scale=1e-6, what="all scores")
+    rec = m.recommend(torch.from_numpy(g["all_user_ids"]))
+    s = torch.from_numpy(g["all_scores"]).double()
+    got_s = torch.gather(s, 1, rec.cpu())
+    want_s = torch.gather(s, 1, torch.from_numpy(g["topk_canonical"]))
+    assert_close(got_s, want_s, rtol=1e-5, atol_scale=1e-5, what="recommended scores")
+
+
+def test_ncf_candidates_default_arch(hnm_lib):
+    from hnm_recommendation_b200 import NeuralCF
+    torch.manual_seed(0)
+    m = NeuralCF(2000, 900).to("cuda").eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("bias"):
+                p.normal_(0, 0.05)
+    cand = torch.randint(0, 900, (2000, 50), dtype=torch.int32)
+    out = m.score_candidates(None, cand)
+    orc = O.NeuralCFOracle(2000, 900, state={k: v.cpu() for k, v in m.state_dict().items()})
+    uu = torch.arange(2000).repeat_interleave(50)
+    want = orc.forward(uu, cand.view(-1).long()).view(2000, 50)
+    assert_close(out, want, rtol=1e-5, atol_scale=1e-6, what="candidate logits")
+    # weight update invalidates the cached layer-1 tables
+    with torch.no_grad():
+        m.mlp_layers[0].bias.add_(0.1)
+    out2 = m.score_candidates(None, cand)
+    assert not torch.allclose(out, out2)
+    with pytest.raises(IndexError):
+        m(torch.tensor([2000]), torch.tensor([0]))
