@@ -35,10 +35,10 @@ _SIGNATURES = {
     "hnm_pair_scores": (C.c_int, [P, P, P, P, I64, I32, I64, I64, P, P]),
     "hnm_score_all_items": (C.c_int, [P, P, P, I64, I64, I32, P, P]),
     "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, P, P, P]),
-    "hnm_score_pack": (C.c_int, [P, P, I64, I64, I32, F32, P, P, P]),
-    "hnm_absmax": (C.c_int, [P, I64, P, P]),
+    "hnm_score_pack": (C.c_int, [P, P, I64, I64, I32, P, F32, P, P, P]),
+    "hnm_absmax": (C.c_int, [P, I64, P, I32, P, P]),
     "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, P, I32, P, P, P]),
-    "hnm_rescore_topk": (C.c_int, [P, P, P, I64, I32, I64, P, I32, P, P, F64, F64, P, P, I32, P, P, P, P]),
+    "hnm_rescore_topk": (C.c_int, [P, P, P, I64, I32, I64, I64, P, I32, P, P, F64, F64, P, P, P, I32, P, P, P, P]),
     "hnm_merge_topk": (C.c_int, [P, P, I32, I64, I32, P, P, P]),
     "hnm_ncf_precompute": (C.c_int, [P, I64, I32, P, I32, I32, I32, P, P, P]),
     "hnm_ncf_score_pairs": (C.c_int, [P, P, P, P, P, P, I32, P, F32, P, P, I64, I32, P, P]),
@@ -84,9 +84,18 @@ def check(fn: str, code: int) -> None:
         raise HnmError(fn, code, strerror(code))
 
 
+LAUNCHES = 0          # kernels launched through call() since the counter was last reset (bench.py reads it)
+_LAUNCHES_PER_CALL = {"hnm_graph_build": 3}
+
+
 def call(fn: str, *args) -> None:
     """Call an int-returning entry point and raise HnmError on a non-zero status."""
+    global LAUNCHES
     check(fn, getattr(load(), fn)(*args))
+    n = _LAUNCHES_PER_CALL.get(fn, 1)
+    if fn == "hnm_lightgcn_layer" and args[13]:
+        n = 2                                     # whole-CTA pass over the long rows + warp-per-row pass
+    LAUNCHES += n
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

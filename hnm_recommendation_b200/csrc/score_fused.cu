@@ -8,50 +8,54 @@
 //                                 every item whose approximate score beats a running threshold
 //   hnm_rescore_topk            : exact fp64 scores of the survivors, canonical top-k, certificate
 //
-// Kernel shape (DESIGN.md "score_topk"): one persistent CTA per SM, 20 warps:
-//   warp 0   TMA producer      A: 4 user tiles x [128 x 64] fp16 per "super tile" (double buffered),
-//                              B: item tiles [128 x 64] fp16 through a 4-stage ring
-//   warp 1   MMA issuer        for every item tile, 4 accumulators (one per user tile), each
-//                              4 x tcgen05.mma M128 N128 K16; accumulator m lives in TMEM columns
-//                              [128 m, 128 m + 128)
+// Kernel shape (DESIGN.md "score_topk"): one persistent CTA per SM, 16 warps:
+//   warp 0   TMA producer      A: 3 user tiles x [128 x 64] fp16 per "super tile" (double buffered),
+//                              B: item tiles [128 x 64] fp16 through a 6-stage ring
+//   warp 1   MMA issuer        work item w = (item tile, user tile m), accumulator slot = w mod 4:
+//                              4 x tcgen05.mma M128 N128 K16 into TMEM columns [128 slot, 128 slot + 128)
 //   warp 2   TMEM allocator
-//   warps 4..19  epilogue, 4 warpgroups; warpgroup m drains accumulator m, thread = one user row.
-// Holding 4 user tiles per CTA makes every 16 KB item tile feed 4 MMAs: the L2 -> smem stream
-// drops to ~30 GB/s per SM, which the L2 can supply to all 148 SMs at tensor-core speed.
+//   warps 4..15  epilogue, 3 warpgroups; warpgroup m drains every accumulator of user tile m,
+//                thread = one user row (TMEM lane).
+// Three user tiles share each 16 KB item tile (L2 -> smem stream ~40 GB/s per SM at full rate) and the
+// fourth accumulator slot lets the MMA of (tile t+1, m) start while warpgroup m still drains (tile t, m).
 //
-// Select (per user row, all in registers): 32 bucket maxima (bucket = position of the 8-column
-// group inside a pair of item tiles); tau = the `kth_sel`-th largest bucket maximum is a lower
-// bound on the kth_sel-th best score seen so far, because bucket maxima belong to distinct items.
-// A column group is inspected element-wise only if its maximum exceeds tau; survivors are appended
-// to the user's candidate list in global memory.  tau is refreshed on a geometric schedule.
-// The first two item tiles are run twice: once to seed the buckets, once to collect.
+// Select (per user row, all in registers): 32 bucket maxima (bucket = position of the 4-column
+// group inside an item tile).  Bucket maxima belong to distinct items, so the kth_sel-th
+// largest of them, tau, is a lower bound on the kth_sel-th best score seen so far.  A column group
+// is inspected element-wise only if its maximum exceeds tau; survivors are appended to the user's
+// candidate list in global memory.  tau is refreshed (in-place sorting network over the bucket
+// registers) every time the number of item tiles seen has grown by 1/8.  The first kBootTiles item
+// tiles are run twice: once to seed the buckets, once to collect.
 #include <algorithm>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
 
 constexpr int kDim = HNM_FUSED_DIM;         // 64 fp16 = one 128-byte swizzle row
 constexpr int kUserTile = 128;              // UMMA M
-constexpr int kMU = 4;                      // user tiles per CTA (accumulators in flight)
-constexpr int kSuper = kUserTile * kMU;     // 512 users per CTA pass
+constexpr int kMU = 3;                      // user tiles per CTA
+constexpr int kSlots = 4;                   // TMEM accumulator slots (4 x 128 columns = all of TMEM)
+constexpr int kSuper = kUserTile * kMU;     // 384 users per CTA pass
 constexpr int kItemTile = 128;              // UMMA N
-constexpr int kStagesB = 4;
-constexpr int kBootTiles = 2;               // 2 x 128 items = 32 buckets x 8 columns
+constexpr int kStagesB = 6;
+constexpr int kBootTiles = 32;              // item tiles used to seed the bucket maxima (run twice)
 constexpr int kEpiWarps = 4 * kMU;
-constexpr int kThreads = (4 + kEpiWarps) * 32;   // 640
+constexpr int kThreads = (4 + kEpiWarps) * 32;   // 512
 constexpr int kTileBytes = kItemTile * kDim * 2; // 16384 (A tile and B tile have the same shape)
 constexpr int kNumBuckets = 32;
 
-static_assert(kUserTile == HNM_FUSED_USER_TILE && kItemTile == HNM_FUSED_ITEM_TILE && kSuper == HNM_FUSED_USER_BLOCK, "header mismatch");
+static_assert(kUserTile == HNM_FUSED_USER_TILE && kItemTile == HNM_FUSED_ITEM_TILE && kSuper == HNM_FUSED_USER_BLOCK,
+              "header mismatch");
 
 struct __align__(8) Barriers {
   uint64_t a_full[2], a_empty[2];
   uint64_t b_full[kStagesB], b_empty[kStagesB];
-  uint64_t t_full[kMU], t_empty[kMU];
+  uint64_t t_full[kSlots], t_empty[kSlots];
   uint32_t tmem_base;
 };
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + 2 * kMU * kTileBytes + kStagesB * kTileBytes + sizeof(Barriers);
@@ -124,23 +128,30 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 // The registers written by tcgen05.ld are only valid after tcgen05.wait::ld; passing them through the
 // wait as in/out operands keeps the compiler from scheduling their uses above it.
-__device__ __forceinline__ void tmem_ld_wait(float (&v)[16]) {
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
-                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                 "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]),
+                 "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]),
+                 "+f"(v[30]), "+f"(v[31])
                :
                : "memory");
 }
@@ -149,80 +160,101 @@ __device__ __forceinline__ void tmem_ld_wait(float (&v)[16]) {
 struct RowState {
   float tau;                  // collect threshold (+inf while seeding)
   int cnt;                    // candidates appended so far (may exceed the capacity: overflow)
-  float bm[kNumBuckets];      // bucket maxima
+  float bm[kNumBuckets];      // bucket maxima (an unordered multiset: see refresh_tau)
 };
 
-__device__ __forceinline__ float kth_largest(const float (&bm)[kNumBuckets], int kth) {
-  float prev = INFINITY, cur = -INFINITY;
-  for (int r = 0; r < kth; ++r) {
-    cur = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < kNumBuckets; ++i) cur = (bm[i] < prev) ? fmaxf(cur, bm[i]) : cur;
-    prev = cur;
-  }
-  return cur;
+__device__ __forceinline__ void cmpx(float& a, float& b) {   // a <- max, b <- min
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  a = hi;
+  b = lo;
 }
 
-// 16 accumulator columns of one user row: 2 groups of 8.  PAR selects the bucket half.
-template <int PAR>
-__device__ __forceinline__ void select16(const float (&v)[16], int chunk, int col0, RowState& st,
-                                         uint2* __restrict__ cand, int cap) {
+// Bitonic sorting network (descending, 240 comparators) over the 32 bucket registers, then
+// tau = bm[kth-1].  Sorting in place is legal: after any permutation register r still holds the
+// maximum of some item set S_r, the S_r stay pairwise disjoint, and later updates add each new item
+// to exactly one S_r.
+__device__ __forceinline__ float refresh_tau(float (&bm)[kNumBuckets], int kth) {
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const float* x = v + 8 * g;
-    const float m8 = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
-    float& b = st.bm[PAR * 16 + chunk * 2 + g];
-    b = fmaxf(b, m8);
-    if (m8 > st.tau) {
+  for (int k = 2; k <= kNumBuckets; k <<= 1) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (x[j] > st.tau) {
-          if (st.cnt < cap) cand[st.cnt] = make_uint2(__float_as_uint(x[j]), (uint32_t)(col0 + 8 * g + j));
-          ++st.cnt;
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < kNumBuckets; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          if ((i & k) == 0) cmpx(bm[i], bm[l]);
+          else cmpx(bm[l], bm[i]);
         }
+      }
+    }
+  }
+  float t = bm[0];
+#pragma unroll
+  for (int i = 1; i < kNumBuckets; ++i) t = (i < kth) ? bm[i] : t;
+  return t;
+}
+
+// 32 accumulator columns of one user row = 8 groups of 4 columns.  A group is both a bucket of the
+// threshold estimator and the unit that gets nominated: when its maximum beats tau the pair
+// {maximum, first column} is appended and hnm_rescore_topk rescores its four items exactly.
+// The common case (nothing in the chunk beats tau) is ~30 straight-line instructions and one
+// branch; the rare case is 8 predicated stores.  Earlier versions branched per group and inlined a
+// per-element scan: the kernel then spent most of its time stalled on instruction fetch
+// (profiles/r1_fused_notes.md).
+// UPDATE = false on the second visit of the seed tiles: their items already sit in the buckets and an
+// item must never be counted in two buckets (tau would stop being a lower bound).
+template <bool UPDATE>
+__device__ __forceinline__ void select32(const float (&v)[32], int chunk, int col0, RowState& st,
+                                         uint2* __restrict__ cand, int cap) {
+  float q[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    const float* x = v + 4 * h;
+    q[h] = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+    if (UPDATE) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
+  }
+  const float m32 = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7])));
+  if (m32 > st.tau) {
+    if (st.cnt > cap - 8) {              // no room for a full chunk: stop collecting, flag the row
+      st.tau = INFINITY;
+      st.cnt = cap + 1;
+    } else {
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (q[h] > st.tau) cand[st.cnt++] = make_uint2(__float_as_uint(q[h]), (uint32_t)(col0 + 4 * h));
       }
     }
   }
 }
 
-template <int PAR>
-__device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, int valid_cols, RowState& st,
-                                           uint2* __restrict__ cand, int cap, uint64_t* t_empty, int lane) {
-  float va[16], vb[16];
-  tmem_ld16(taddr, va);
+template <bool UPDATE>
+__device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& st, uint2* __restrict__ cand,
+                                           int cap, uint64_t* t_empty, int lane) {
+  float va[32], vb[32];
+  tmem_ld32(taddr, va);
   tmem_ld_wait(va);
-#pragma unroll
-  for (int c = 0; c < 8; c += 2) {
-    tmem_ld16(taddr + (c + 1) * 16, vb);
-    if (valid_cols < kItemTile) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) va[j] = (c * 16 + j < valid_cols) ? va[j] : -INFINITY;
-    }
-    select16<PAR>(va, c, item0 + c * 16, st, cand, cap);
-    tmem_ld_wait(vb);
-    if (c + 2 < 8) {
-      tmem_ld16(taddr + (c + 2) * 16, va);
-    } else {
-      // every column of this accumulator is in registers: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty);
-    }
-    if (valid_cols < kItemTile) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) vb[j] = ((c + 1) * 16 + j < valid_cols) ? vb[j] : -INFINITY;
-    }
-    select16<PAR>(vb, c + 1, item0 + (c + 1) * 16, st, cand, cap);
-    if (c + 2 < 8) tmem_ld_wait(va);
-  }
+  tmem_ld32(taddr + 32, vb);
+  select32<UPDATE>(va, 0, item0, st, cand, cap);
+  tmem_ld_wait(vb);
+  tmem_ld32(taddr + 64, va);
+  select32<UPDATE>(vb, 1, item0 + 32, st, cand, cap);
+  tmem_ld_wait(va);
+  tmem_ld32(taddr + 96, vb);
+  select32<UPDATE>(va, 2, item0 + 64, st, cand, cap);
+  tmem_ld_wait(vb);
+  // every column of this accumulator is in registers: hand the slot back to the MMA warp
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(t_empty);
+  select32<UPDATE>(vb, 3, item0 + 96, st, cand, cap);
 }
 
 // ----------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
-                        int num_users, int num_super, int num_items, int num_item_tiles, int kth_sel,
+                        int num_users, int num_super, int num_item_tiles, int kth_sel,
                         uint2* __restrict__ cand, int cap, int32_t* __restrict__ cand_count,
-                        float* __restrict__ cand_thresh) {
+                        float* __restrict__ cand_thresh, int mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                   // [2][kMU][kTileBytes]
@@ -239,7 +271,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     tma_prefetch_desc(&map_items);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
     for (int i = 0; i < kStagesB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
-    for (int i = 0; i < kMU; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
+    for (int i = 0; i < kSlots; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -252,6 +284,10 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  if (warp < 4) {
+  // The 4 control warps give registers back so the 12 epilogue warps can hold a whole 64-column
+  // double buffer plus the 32 bucket maxima without spilling (40 * 128 + 152 * 384 <= 64 K).
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
@@ -275,41 +311,46 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    uint32_t g = 0;
-    int n = 0;
-    for (int st = blockIdx.x; st < num_super; st += gridDim.x, ++n) {
-      const int abuf = n & 1;
-      mbar_wait(&bars->a_full[abuf], (n >> 1) & 1);
-      for (int it = 0; it < num_iters; ++it, ++g) {
-        const int stage = g % kStagesB;
-        mbar_wait(&bars->b_full[stage], (g / kStagesB) & 1);
-        const uint32_t b_addr = smem_u32(smem_b + stage * kTileBytes);
-#pragma unroll 1
-        for (int m = 0; m < kMU; ++m) {
-          mbar_wait(&bars->t_empty[m], (g & 1) ^ 1);
+    // One thread runs the whole loop: tcgen05.mma / commit are single-thread instructions, and keeping
+    // the other 31 lanes out of it avoids the per-instruction elect loops the compiler otherwise emits
+    // (they made this warp, not the tensor pipe, the bottleneck: profiles/r1_fused_v1.md).
+    if (lane == 0) {
+      uint32_t g = 0, w = 0;
+      int n = 0;
+      const uint64_t desc_hi = umma_desc_sw128(0) & ~uint64_t(0x3FFF);
+      for (int st = blockIdx.x; st < num_super; st += gridDim.x, ++n) {
+        const int abuf = n & 1;
+        mbar_wait(&bars->a_full[abuf], (n >> 1) & 1);
+        const uint32_t a_base = smem_u32(smem_a + abuf * kMU * kTileBytes);
+        for (int it = 0; it < num_iters; ++it, ++g) {
+          const int stage = g % kStagesB;
+          mbar_wait(&bars->b_full[stage], (g / kStagesB) & 1);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(smem_a + (abuf * kMU + m) * kTileBytes);
+          const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(smem_b + stage * kTileBytes) >> 4) & 0x3FFF);
 #pragma unroll
-            for (int k = 0; k < kDim / 16; ++k) {
-              umma_f16(tmem_base + m * kItemTile, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
-                       k > 0 ? 1u : 0u);
-            }
-            umma_commit(&bars->t_full[m]);
+          for (int m = 0; m < kMU; ++m, ++w) {
+            const uint32_t slot = w % kSlots;
+            mbar_wait(&bars->t_empty[slot], ((w / kSlots) & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t a_desc = desc_hi | (uint64_t)(((a_base + m * kTileBytes) >> 4) & 0x3FFF);
+            const uint32_t d_tmem = tmem_base + slot * kItemTile;
+#pragma unroll
+            for (int k = 0; k < kDim / 16; ++k)      // +32 bytes along K = +2 in the 16-byte address field
+              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, k > 0 ? 1u : 0u);
+            umma_commit(&bars->t_full[slot]);
           }
-          __syncwarp();
+          umma_commit(&bars->b_empty[stage]);
         }
-        if (lane == 0) umma_commit(&bars->b_empty[stage]);
-        __syncwarp();
+        umma_commit(&bars->a_empty[abuf]);
       }
-      if (lane == 0) umma_commit(&bars->a_empty[abuf]);
-      __syncwarp();
     }
-  } else if (warp >= 4) {
-    // ===================================================== epilogue: warpgroup m drains accumulator m
+  }
+  } else {
+    // ===================================================== epilogue: warpgroup m drains user tile m
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int m = (warp - 4) >> 2;
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + m * kItemTile;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t g = 0;
     for (int st = blockIdx.x; st < num_super; st += gridDim.x) {
       const int row = st * kSuper + m * kUserTile + q * 32 + lane;
@@ -320,23 +361,40 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       rs.cnt = 0;
 #pragma unroll
       for (int i = 0; i < kNumBuckets; ++i) rs.bm[i] = -INFINITY;
-      int next_refresh = boot + 2;
+      int next_refresh = boot;
       for (int it = 0; it < num_iters; ++it, ++g) {
         const int tile = it < boot ? it : it - boot;
-        if (it == boot) rs.tau = kth_largest(rs.bm, kth_sel);          // buckets seeded: start collecting
-        if (it == next_refresh) {
-          rs.tau = kth_largest(rs.bm, kth_sel);
-          next_refresh = boot + 2 * (it - boot);
+        if (it == next_refresh && mode == 0) {
+          // it == boot: the seed pass is over, collecting starts (again from tile 0)
+          rs.tau = refresh_tau(rs.bm, kth_sel);
+          const int seen = max(boot, it - boot);         // item tiles behind the current bucket maxima
+          next_refresh = it + max(2, seen / 8);
         }
-        const int valid = min(kItemTile, num_items - tile * kItemTile);
-        mbar_wait(&bars->t_full[m], g & 1);
+        const uint32_t w = g * kMU + m;
+        const uint32_t slot = w % kSlots;
+        mbar_wait(&bars->t_full[slot], (w / kSlots) & 1);
         tc_fence_after();
-        if (tile & 1) drain_tile<1>(taddr, tile * kItemTile, valid, rs, my_cand, my_cap, &bars->t_empty[m], lane);
-        else drain_tile<0>(taddr, tile * kItemTile, valid, rs, my_cand, my_cap, &bars->t_empty[m], lane);
+        const uint32_t taddr = lane_base + slot * kItemTile;
+        uint64_t* t_empty = &bars->t_empty[slot];
+        if (mode == 1 || mode == 3 || mode == 4) {   // debug: drain only / handshake only / one load
+          float va[32];
+          float acc = 0.f;
+          const int nld = mode == 1 ? 4 : (mode == 4 ? 1 : 0);
+          for (int c = 0; c < nld; ++c) { tmem_ld32(taddr + c * 32, va); tmem_ld_wait(va); acc += va[c]; }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty);
+          rs.bm[0] += acc;
+        } else if (it >= boot && it < 2 * boot) {      // second visit of a seed tile: collect only
+          drain_tile<false>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
+        } else {
+          drain_tile<true>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
+        }
       }
+      if (mode == 0) rs.tau = refresh_tau(rs.bm, kth_sel);
       if (row < num_users) {
         cand_count[row] = rs.cnt;
-        cand_thresh[row] = kth_largest(rs.bm, kth_sel);
+        cand_thresh[row] = rs.tau;
       }
     }
   }
@@ -350,10 +408,11 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
 }
 
 // ----------------------------------------------------------------------------- pack / absmax
-__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ center, int dim,
+                              float* __restrict__ out) {
   float m = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(x[i]));
+    m = fmaxf(m, fabsf(center ? __fsub_rn(x[i], center[i % dim]) : x[i]));
 #pragma unroll
   for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // m >= 0
@@ -361,7 +420,8 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __r
 
 // one 8-lane group per row of 64: lane handles 8 consecutive floats -> one 16-byte store
 __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __restrict__ row_ids, int64_t num_rows,
-                            int64_t rows_padded, float scale, __half* __restrict__ out, float* __restrict__ sumsq) {
+                            int64_t rows_padded, const float* __restrict__ center, float scale,
+                            __half* __restrict__ out, float* __restrict__ sumsq) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t r = t >> 3;
   const int sub = (int)(t & 7);
@@ -372,6 +432,11 @@ __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __rest
     const float* p = emb + (size_t)src * kDim + sub * 8;
     a = ldg_f4(p);
     b = ldg_f4(p + 4);
+    if (center) {     // w = fl(x - c): ranking of u.x and u.(x - c) is the same for a fixed user
+      const float4 ca = ldg_f4(center + sub * 8), cb = ldg_f4(center + sub * 8 + 4);
+      a = make_float4(__fsub_rn(a.x, ca.x), __fsub_rn(a.y, ca.y), __fsub_rn(a.z, ca.z), __fsub_rn(a.w, ca.w));
+      b = make_float4(__fsub_rn(b.x, cb.x), __fsub_rn(b.y, cb.y), __fsub_rn(b.z, cb.z), __fsub_rn(b.w, cb.w));
+    }
   }
   __half2 h[4];
   h[0] = __floats2half2_rn(a.x * scale, a.y * scale);
@@ -389,7 +454,8 @@ __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __rest
 }
 
 // ----------------------------------------------------------------------------- rescoring
-constexpr int kMaxPerLane = 4;   // candidate capacity handled = 32 * kMaxPerLane
+constexpr int kMaxPerLane = 8;   // candidate capacity handled = 32 * kMaxPerLane
+constexpr int kGroup = 4;        // items per nominated group (select32)
 
 __device__ __forceinline__ bool in_sorted(const int64_t* __restrict__ a, int64_t lo, int64_t hi, int64_t x) {
   while (lo < hi) {
@@ -403,13 +469,16 @@ __device__ __forceinline__ bool in_sorted(const int64_t* __restrict__ a, int64_t
 
 __global__ void __launch_bounds__(256)
 rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
-               const int64_t* __restrict__ user_ids, int64_t batch, int dim, int64_t item_begin,
+               const int64_t* __restrict__ user_ids, int64_t batch, int dim, int64_t item_begin, int num_items_local,
                const uint2* __restrict__ cand, int cap, const int32_t* __restrict__ cand_count,
                const float* __restrict__ cand_thresh, double inv_scale, double max_item_norm,
-               const int64_t* __restrict__ excl_ptr, const int64_t* __restrict__ excl_items, int k,
-               int64_t* __restrict__ out_ids, double* __restrict__ out_scores, int32_t* __restrict__ certified) {
+               const float* __restrict__ center, const int64_t* __restrict__ excl_ptr,
+               const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
+               double* __restrict__ out_scores, int32_t* __restrict__ certified) {
+  __shared__ uint32_t s_col[8][32];
   const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int wib = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (b >= batch) return;
   const int64_t uid = user_ids ? user_ids[b] : b;
   const float* urow = user_emb + (size_t)uid * dim;
@@ -420,54 +489,78 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
   int64_t ex_lo = 0, ex_hi = 0;
   if (excl_ptr) { ex_lo = excl_ptr[b]; ex_hi = excl_ptr[b + 1]; }
 
-  double s[kMaxPerLane];
-  int64_t id[kMaxPerLane];
-  int kept = 0;
+  // 1. keep the groups whose maximum ended above the final threshold (the others are covered by
+  //    the certificate bound) and compact them: lane j takes kept group j
+  int groups = 0;
 #pragma unroll
   for (int e = 0; e < kMaxPerLane; ++e) {
+    const int idx = lane + 32 * e;
+    uint2 c = make_uint2(0u, 0u);
+    bool keep = false;
+    if (idx < n) {
+      c = mine[idx];
+      keep = __uint_as_float(c.x) > thr;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    const int pos = groups + __popc(mask & ((1u << lane) - 1u));
+    if (keep && pos < 32) s_col[wib][pos] = c.y;
+    groups += __popc(mask);
+  }
+  __syncwarp();
+  const bool too_many = groups > 32;
+  const int col0 = lane < min(groups, 32) ? (int)s_col[wib][lane] : -1;
+
+  // 2. exact fp64 score (k = 0..dim-1 fma chain) of the four items of my group
+  double s[kGroup];
+  int64_t id[kGroup];
+  int kept = 0;
+#pragma unroll
+  for (int e = 0; e < kGroup; ++e) {
     s[e] = -INFINITY;
     id[e] = INT64_MAX;
-    const int idx = lane + 32 * e;
-    if (idx < n) {
-      const uint2 c = mine[idx];
-      // entries at or below the final threshold are covered by the certificate bound
-      if (__uint_as_float(c.x) > thr) {
-        const int64_t gid = item_begin + (int64_t)c.y;
-        if (!(ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, gid))) {
-          const float* irow = item_emb + (size_t)c.y * dim;
-          double acc = 0.0;
-          for (int kk = 0; kk < dim; kk += 4) {
-            const float4 u = ldg_f4(urow + kk), v = ldg_f4(irow + kk);
-            acc = fma((double)u.x, (double)v.x, acc);
-            acc = fma((double)u.y, (double)v.y, acc);
-            acc = fma((double)u.z, (double)v.z, acc);
-            acc = fma((double)u.w, (double)v.w, acc);
-          }
-          s[e] = acc;
-          id[e] = gid;
-          ++kept;
+    const int item = col0 + e;
+    if (col0 >= 0 && item < num_items_local) {          // columns past the catalog are zero padding
+      const int64_t gid = item_begin + (int64_t)item;
+      if (!(ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, gid))) {
+        const float* irow = item_emb + (size_t)item * dim;
+        double acc = 0.0;
+        for (int kk = 0; kk < dim; kk += 4) {
+          const float4 u = ldg_f4(urow + kk), v = ldg_f4(irow + kk);
+          acc = fma((double)u.x, (double)v.x, acc);
+          acc = fma((double)u.y, (double)v.y, acc);
+          acc = fma((double)u.z, (double)v.z, acc);
+          acc = fma((double)u.w, (double)v.w, acc);
         }
+        s[e] = acc;
+        id[e] = gid;
+        ++kept;
       }
     }
   }
-  // ||u||_2 for the error bound
-  double un = 0.0;
-  for (int kk = lane; kk < dim; kk += 32) { const double u = (double)urow[kk]; un = fma(u, u, un); }
+  // ||u||_2 for the error bound, u.c to translate centred scores back
+  double un = 0.0, uc = 0.0, uc_abs = 0.0;
+  for (int kk = lane; kk < dim; kk += 32) {
+    const double u = (double)urow[kk];
+    un = fma(u, u, un);
+    if (center) { const double c = (double)center[kk]; uc = fma(u, c, uc); uc_abs += fabs(u * c); }
+  }
 #pragma unroll
   for (int off = 16; off; off >>= 1) {
     un += __shfl_xor_sync(0xffffffffu, un, off);
+    uc += __shfl_xor_sync(0xffffffffu, uc, off);
+    uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
     kept += __shfl_xor_sync(0xffffffffu, kept, off);
   }
   un = sqrt(un);
 
+  // 3. canonical top-k of the exact scores: k rounds of warp argmax by (score desc, id asc)
   double kth_score = -INFINITY;
   for (int t = 0; t < k; ++t) {
-    // lane-local best, then warp argmax by (score desc, id asc)
     double bs = s[0];
     int64_t bi = id[0];
     int be = 0;
 #pragma unroll
-    for (int e = 1; e < kMaxPerLane; ++e)
+    for (int e = 1; e < kGroup; ++e)
       if (hnm_before(s[e], id[e], bs, bi)) { bs = s[e]; bi = id[e]; be = e; }
     double ws = bs;
     int64_t wi = bi;
@@ -479,7 +572,7 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
     }
     if (wi == bi && ws == bs && bi != INT64_MAX) {   // ids are unique, so exactly one lane matches
 #pragma unroll
-      for (int e = 0; e < kMaxPerLane; ++e)
+      for (int e = 0; e < kGroup; ++e)
         if (e == be) { s[e] = -INFINITY; id[e] = INT64_MAX; }
     }
     if (lane == 0) {
@@ -489,9 +582,10 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
     kth_score = ws;
   }
   if (lane == 0) {
-    // |approx - exact| <= eps for every pair of this user (DESIGN.md "certificate")
-    const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale;
-    const bool ok = raw <= cap && kept >= k && kth_score > (double)thr * inv_scale + eps;
+    // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c
+    const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale +
+                       1e-12 * uc_abs;
+    const bool ok = raw <= cap && !too_many && kept >= k && kth_score > (double)thr * inv_scale + eps + uc;
     certified[b] = ok ? 1 : 0;
   }
 }
@@ -517,27 +611,29 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows) {
 
 }  // namespace
 
-extern "C" int hnm_absmax(const float* emb, int64_t count, float* out_absmax, void* stream_) {
+extern "C" int hnm_absmax(const float* emb, int64_t count, const float* center, int32_t dim, float* out_absmax,
+                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!emb || !out_absmax) return HNM_E_NULL;
-  if (count <= 0) return HNM_E_RANGE;
+  if (count <= 0 || (center && dim <= 0)) return HNM_E_RANGE;
   const int T = 256;
   const unsigned grid = (unsigned)std::min<int64_t>((count + T - 1) / T, (int64_t)hnm_num_sms() * 8);
-  absmax_kernel<<<grid, T, 0, stream>>>(emb, count, out_absmax);
+  absmax_kernel<<<grid, T, 0, stream>>>(emb, count, center, dim, out_absmax);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
 
 extern "C" int hnm_score_pack(const float* emb, const int64_t* row_ids, int64_t num_rows, int64_t rows_padded,
-                              int32_t dim, float scale, void* out_f16, float* out_sumsq, void* stream_) {
+                              int32_t dim, const float* center, float scale, void* out_f16, float* out_sumsq,
+                              void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!emb || !out_f16) return HNM_E_NULL;
   if (dim != kDim) return HNM_E_DIM;
   if (num_rows < 0 || rows_padded < num_rows || rows_padded <= 0) return HNM_E_RANGE;
-  if (!hnm_aligned16(emb) || !hnm_aligned16(out_f16)) return HNM_E_ALIGN;
+  if (!hnm_aligned16(emb) || !hnm_aligned16(out_f16) || (center && !hnm_aligned16(center))) return HNM_E_ALIGN;
   const int T = 256;
   const int64_t threads = rows_padded * 8;
-  pack_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(emb, row_ids, num_rows, rows_padded, scale,
+  pack_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(emb, row_ids, num_rows, rows_padded, center, scale,
                                                                   (__half*)out_f16, out_sumsq);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
@@ -565,32 +661,37 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
                                       (int)kSmemBytes));
     attr_set = true;
   }
+  static const int debug_mode = getenv("HNM_FUSED_DEBUG") ? atoi(getenv("HNM_FUSED_DEBUG")) : 0;
   const int num_super = (int)(users_padded / kSuper);
   const int num_tiles = (int)(items_padded / kItemTile);
   const int grid = std::min(num_super, hnm_num_sms());
   score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_u, map_i, (int)num_users, num_super,
-                                                                  (int)num_items, num_tiles, kth_sel, (uint2*)cand,
-                                                                  cand_cap, cand_count, cand_thresh);
+                                                                  num_tiles, kth_sel, (uint2*)cand,
+                                                                  cand_cap, cand_count, cand_thresh, debug_mode);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
 
 extern "C" int hnm_rescore_topk(const float* user_emb, const float* item_emb, const int64_t* user_ids, int64_t batch,
-                                int32_t dim, int64_t item_begin, const void* cand, int32_t cand_cap,
+                                int32_t dim, int64_t item_begin, int64_t num_items_local, const void* cand,
+                                int32_t cand_cap,
                                 const int32_t* cand_count, const float* cand_thresh, double inv_scale_product,
-                                double max_item_norm, const int64_t* excl_ptr, const int64_t* excl_items, int32_t k,
-                                int64_t* out_ids, double* out_scores, int32_t* out_certified, void* stream_) {
+                                double max_item_norm, const float* center, const int64_t* excl_ptr,
+                                const int64_t* excl_items, int32_t k, int64_t* out_ids, double* out_scores,
+                                int32_t* out_certified, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (batch == 0) return HNM_OK;
   if (!user_emb || !item_emb || !cand || !cand_count || !cand_thresh || !out_ids || !out_scores || !out_certified)
     return HNM_E_NULL;
   if ((excl_ptr != nullptr) != (excl_items != nullptr)) return HNM_E_NULL;
-  if (batch < 0 || dim <= 0 || dim % 4 != 0 || k < 1 || k > 32 || cand_cap < 1 || cand_cap > 32 * kMaxPerLane)
+  if (batch < 0 || dim <= 0 || dim % 4 != 0 || k < 1 || k > 32 || cand_cap < 1 || cand_cap > 32 * kMaxPerLane ||
+      num_items_local < 1 || num_items_local > INT32_MAX)
     return HNM_E_RANGE;
   const int wpc = 8;
   rescore_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
-      user_emb, item_emb, user_ids, batch, dim, item_begin, (const uint2*)cand, cand_cap, cand_count, cand_thresh,
-      inv_scale_product, max_item_norm, excl_ptr, excl_items, k, out_ids, out_scores, out_certified);
+      user_emb, item_emb, user_ids, batch, dim, item_begin, (int)num_items_local, (const uint2*)cand, cand_cap,
+      cand_count, cand_thresh,
+      inv_scale_product, max_item_norm, center, excl_ptr, excl_items, k, out_ids, out_scores, out_certified);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }

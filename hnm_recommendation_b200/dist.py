@@ -1,0 +1,234 @@
+"""Multi-GPU form of the hot path: one process per GPU, torch.distributed for the plumbing.
+
+No counterpart in the reference (single device, scripts/train.py:233-234); the partitioning is the
+one BASELINE.json's north_star prescribes:
+
+  * propagation: rows of A_hat are sharded (each rank owns one equal slice of the user rows and one
+    of the item rows, so every rank gets the same mix of short user rows and long item rows); after
+    every layer the freshly written row slices are all-gathered so the next layer can gather from
+    all rows;
+  * scoring: the item catalog is sharded; each rank runs the fused score/select + exact rescoring
+    against its item shard for ALL users, the per-shard exact top-k lists are exchanged (all-to-all
+    by user slice), merged by (score desc, item id asc), and the merged slices are all-gathered.
+
+The compute steps are injected (``Backend``) so the host logic -- partitioning, exchanges, merge
+order -- can be exercised on CPU with gloo and the oracle standing in for the kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def even_ranges(n: int, parts: int) -> List[Tuple[int, int]]:
+    """Split [0, n) into `parts` contiguous ranges whose sizes differ by at most one."""
+    base, rem = divmod(n, parts)
+    out, start = [], 0
+    for p in range(parts):
+        size = base + (1 if p < rem else 0)
+        out.append((start, start + size))
+        start += size
+    return out
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    rank: int
+    user_rows: List[Tuple[int, int]]      # per rank, node-id range inside [0, U)
+    item_rows: List[Tuple[int, int]]      # per rank, node-id range inside [U, U+I)
+    item_shards: List[Tuple[int, int]]    # per rank, item-index range inside [0, I)
+    user_slices: List[Tuple[int, int]]    # per rank, the users whose lists this rank merges
+
+    @staticmethod
+    def make(num_users: int, num_items: int, world: int, rank: int) -> "ShardPlan":
+        ur = even_ranges(num_users, world)
+        ir = even_ranges(num_items, world)
+        return ShardPlan(world, rank, ur, [(num_users + a, num_users + b) for a, b in ir], ir, ur)
+
+
+class Collectives:
+    """The three exchanges, with NCCL fast paths and a plain fallback that also runs on gloo."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nccl = dist.get_backend(group) == "nccl"
+
+    def allgather_rows(self, buf: torch.Tensor, ranges: Sequence[Tuple[int, int]]) -> None:
+        """Every rank has written buf[ranges[rank]]; make all ranges valid on all ranks (in place)."""
+        views = [buf[a:b] for a, b in ranges]
+        if self.nccl:
+            dist.all_gather(views, views[self.rank], group=self.group)      # uneven sizes are supported on NCCL
+        else:
+            for src, v in enumerate(views):
+                if v.numel():
+                    dist.broadcast(v, src=dist.get_global_rank(self.group, src) if self.group else src,
+                                   group=self.group)
+
+    def exchange_by_user_slice(self, t: torch.Tensor, slices: Sequence[Tuple[int, int]]) -> torch.Tensor:
+        """t: [U, k] computed against this rank's item shard.  Returns [world, n_mine, k]: every rank's
+        rows for the users of my slice."""
+        a, b = slices[self.rank]
+        n_mine = b - a
+        out = torch.empty((self.world, n_mine) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        if self.nccl:
+            in_splits = [y - x for x, y in slices]
+            dist.all_to_all_single(out.view(self.world * n_mine, *t.shape[1:]), t.contiguous(),
+                                   output_split_sizes=[n_mine] * self.world, input_split_sizes=in_splits,
+                                   group=self.group)
+        else:
+            full = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(full, t.contiguous(), group=self.group)
+            for r in range(self.world):
+                out[r] = full[r][a:b]
+        return out
+
+    def allgather_slices(self, mine: torch.Tensor, slices: Sequence[Tuple[int, int]], total: int) -> torch.Tensor:
+        out = torch.empty((total,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        a, b = slices[self.rank]
+        out[a:b] = mine
+        self.allgather_rows(out, slices)
+        return out
+
+
+class ShardedLightGCN:
+    """Wraps a LightGCN whose parameters and graph are replicated on every rank."""
+
+    def __init__(self, model, group=None, backend=None):
+        self.model = model
+        self.coll = Collectives(group)
+        self.plan = ShardPlan.make(model.num_users, model.num_items, self.coll.world, self.coll.rank)
+        self.backend = backend or CudaBackend()
+        self._scorer = None
+        self.stage_ms: Dict[str, float] = {}
+
+    # ---------------------------------------------------------------- propagate
+    def forward(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        m, p = self.model, self.plan
+        if m.graph is None:
+            raise RuntimeError("Graph not set. Call set_graph() first.")
+        my_ranges = [p.user_rows[p.rank], p.item_rows[p.rank]]
+
+        def exchange(buf):
+            self.coll.allgather_rows(buf, p.user_rows)
+            self.coll.allgather_rows(buf, p.item_rows)
+
+        final = self.backend.propagate(m, my_ranges, exchange)
+        self._scorer = None
+        return final[: m.num_users], final[m.num_users:]
+
+    # ---------------------------------------------------------------- recommend
+    def recommend_all(self, k: Optional[int] = None, return_scores: bool = False):
+        m, p = self.model, self.plan
+        k = m.top_k if k is None else int(k)
+        with torch.no_grad():
+            ue, ie = self.forward()
+            i0, i1 = p.item_shards[p.rank]
+            ids, sc = self.backend.local_topk(self, ue, ie[i0:i1], i0, k)           # [U, k] vs my item shard
+            ids_x = self.coll.exchange_by_user_slice(ids, p.user_slices)           # [G, n_mine, k]
+            sc_x = self.coll.exchange_by_user_slice(sc, p.user_slices)
+            m_ids, m_sc = self.backend.merge(ids_x, sc_x)                          # [n_mine, k]
+            out_ids = self.coll.allgather_slices(m_ids, p.user_slices, m.num_users)
+            if return_scores:
+                return out_ids, self.coll.allgather_slices(m_sc, p.user_slices, m.num_users)
+        return out_ids
+
+
+class CudaBackend:
+    """The B200 kernels (default)."""
+
+    def propagate(self, model, my_ranges, exchange):
+        from . import engine
+        return engine.propagate(model.graph, model.embeddings.weight, model.alpha, model.num_layers,
+                                row_ranges=my_ranges, exchange=exchange)
+
+    def local_topk(self, sharded, ue, ie_shard, item_begin, k):
+        from . import engine
+        from .scorer import FusedScorer
+        ie_shard = ie_shard.contiguous()
+        if FusedScorer.supports(ue.size(1), k, ie_shard.size(0)):
+            sharded._scorer = FusedScorer(ue, ie_shard, item_begin=item_begin)
+            return sharded._scorer.topk(None, k)
+        return engine.topk_exact(ue, ie_shard, None, k, item_begin=item_begin)
+
+    def merge(self, ids, scores):
+        from . import engine
+        return engine.merge_topk(ids, scores)
+
+
+def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) -> Dict[str, float]:
+    """Per-stage device times (CUDA events on the launching stream) of one hot-path pass on this rank."""
+    from . import engine
+    from ._lib import call, ptr, stream
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    g = model.graph
+    w = model.embeddings.weight.detach()
+    n, d = w.shape
+    if sharded is not None:
+        p = sharded.plan
+        ranges = [p.user_rows[p.rank], p.item_rows[p.rank]]
+    else:
+        ranges = [(0, n)]
+    xs = torch.empty_like(w)
+    xo = torch.empty_like(w)
+    acc = torch.empty_like(w)
+    out: Dict[str, float] = {}
+    with torch.cuda.device(w.device):
+        call("hnm_lightgcn_prescale", ptr(w), ptr(g.dis), 0.25, ptr(xs), ptr(acc), n, d, stream())
+        heavy = ptr(g.heavy_rows) if g.num_heavy else None
+
+        def layer():
+            for r0, r1 in ranges:
+                call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
+                     0.25, n, d, r0, r1, heavy, g.num_heavy, g.heavy_threshold, stream())
+        layer()
+        a = ev()
+        for _ in range(steps):
+            layer()
+        b = ev()
+        torch.cuda.synchronize()
+        out["spmm_layer_ms"] = a.elapsed_time(b) / steps
+        a = ev()
+        for _ in range(steps):
+            call("hnm_lightgcn_prescale", ptr(w), ptr(g.dis), 0.25, ptr(xs), ptr(acc), n, d, stream())
+        b = ev()
+        torch.cuda.synchronize()
+        out["prescale_ms"] = a.elapsed_time(b) / steps
+    del xs, xo, acc
+    # propagate (all layers, exchanges included when sharded)
+    fwd = sharded.forward if sharded is not None else model.forward
+    fwd()
+    a = ev()
+    for _ in range(steps):
+        fwd()
+    b = ev()
+    torch.cuda.synchronize()
+    out["propagate_ms"] = a.elapsed_time(b) / steps
+    # scoring stages
+    rec = sharded.recommend_all if sharded is not None else model.recommend_all
+    rec()
+    scorer = sharded._scorer if sharded is not None else model._scorer
+    fused = {"fused": 0.0, "rescore": 0.0, "pack": 0.0, "fallback": 0.0}
+    uncert = 0
+    if scorer is not None:
+        for _ in range(steps):
+            rec()
+            scorer = sharded._scorer if sharded is not None else model._scorer
+            scorer.profile = True
+            scorer.topk(None, model.top_k)
+            for k2 in fused:
+                fused[k2] += scorer.stage_ms.get(k2, 0.0) / steps
+            uncert = scorer.last_stats.get("uncertified", 0)
+    out.update({"fused_ms": fused["fused"], "rescore_ms": fused["rescore"], "pack_users_ms": fused["pack"],
+                "fallback_ms": fused["fallback"], "uncertified_users": uncert})
+    return out

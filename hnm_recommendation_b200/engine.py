@@ -70,11 +70,11 @@ def build_graph(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n
 
 
 def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
-              row_range: Optional[Tuple[int, int]] = None, exchange=None) -> torch.Tensor:
+              row_ranges: Optional[Sequence[Tuple[int, int]]] = None, exchange=None) -> torch.Tensor:
     """LightGCN.forward (lightgcn.py:147-158): returns final [N, d] = sum_l alpha_l * A_hat^l E0.
 
-    row_range/exchange serve the row-sharded multi-GPU form: this rank computes rows
-    [r0, r1) of every layer and ``exchange(buf)`` makes all rows of ``buf`` visible
+    row_ranges/exchange serve the row-sharded multi-GPU form: this rank computes the listed
+    row ranges of every layer and ``exchange(buf)`` makes all rows of ``buf`` visible
     (an allgather of row slices) before the next layer gathers from it.
     """
     _lib.require_device()
@@ -84,7 +84,7 @@ def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layer
     n, d = e0.shape
     if n != graph.num_nodes:
         raise ValueError("embedding rows != graph nodes")
-    r0, r1 = row_range if row_range is not None else (0, n)
+    ranges = list(row_ranges) if row_ranges is not None else [(0, n)]
     acc = torch.empty_like(e0)
     xs_a = torch.empty_like(e0)
     xs_b = torch.empty_like(e0) if num_layers > 1 else None
@@ -94,9 +94,10 @@ def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layer
         cur, nxt = xs_a, xs_b
         for layer in range(1, num_layers + 1):
             last = layer == num_layers
-            call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
-                 None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, r0, r1,
-                 ptr(graph.heavy_rows) if graph.num_heavy else None, graph.num_heavy, graph.heavy_threshold, s)
+            for r0, r1 in ranges:
+                call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
+                     None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, r0, r1,
+                     ptr(graph.heavy_rows) if graph.num_heavy else None, graph.num_heavy, graph.heavy_threshold, s)
             if not last:
                 if exchange is not None:
                     exchange(nxt)

@@ -16,11 +16,11 @@ import torch
 from . import _lib, engine
 from ._lib import call, ptr, stream
 
-USER_BLOCK = 512
+USER_BLOCK = 384
 ITEM_TILE = 128
-CAND_CAP = 128
+CAND_CAP = 256
 K_MAX = 16
-SEL_MARGIN = 4                 # tau tracks the (k + margin)-th best bucket maximum
+SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maximum
 MAX_USERS_PER_LAUNCH = 1 << 21
 
 
@@ -39,28 +39,36 @@ class FusedScorer:
     def supports(dim: int, k: int, num_items: int) -> bool:
         return dim == 64 and 1 <= k <= K_MAX and num_items >= 2 * ITEM_TILE
 
-    def __init__(self, user_emb: torch.Tensor, item_emb: torch.Tensor, item_begin: int = 0):
+    def __init__(self, user_emb: torch.Tensor, item_emb: torch.Tensor, item_begin: int = 0,
+                 center: bool = True, sel_margin: int = SEL_MARGIN):
         _lib.require_device()
         self.user_emb = user_emb.contiguous()
         self.item_emb = item_emb.contiguous()
         self.item_begin = item_begin
+        self.sel_margin = sel_margin
         dev = self.item_emb.device
         self.num_items = int(self.item_emb.size(0))
         self.items_padded = (self.num_items + ITEM_TILE - 1) // ITEM_TILE * ITEM_TILE
         with torch.cuda.device(dev):
+            # any fp32 vector is a valid centre; the mean row is the one that shrinks the items most
+            self.center = self.item_emb.mean(dim=0, dtype=torch.float64).float().contiguous() if center else None
             amax = torch.zeros(2, dtype=torch.float32, device=dev)
-            call("hnm_absmax", ptr(self.user_emb), self.user_emb.numel(), amax[0:1].data_ptr(), stream())
-            call("hnm_absmax", ptr(self.item_emb), self.item_emb.numel(), amax[1:2].data_ptr(), stream())
+            call("hnm_absmax", ptr(self.user_emb), self.user_emb.numel(), None, 64, amax[0:1].data_ptr(), stream())
+            call("hnm_absmax", ptr(self.item_emb), self.item_emb.numel(), ptr(self.center), 64,
+                 amax[1:2].data_ptr(), stream())
             au, ai = amax.tolist()
             self.user_scale, self.item_scale = _pow2_scale(au), _pow2_scale(ai)
             self.items_f16 = torch.empty(self.items_padded, 64, dtype=torch.float16, device=dev)
             sumsq = torch.empty(self.num_items, dtype=torch.float32, device=dev)
             call("hnm_score_pack", ptr(self.item_emb), None, self.num_items, self.items_padded, 64,
-                 self.item_scale, ptr(self.items_f16), ptr(sumsq), stream())
+                 ptr(self.center), self.item_scale, ptr(self.items_f16), ptr(sumsq), stream())
             # a hair above the fp32 value so the bound stays an upper bound
             self.max_item_norm = math.sqrt(float(sumsq.max())) * (1.0 + 1e-6)
         self.inv_scale = 1.0 / (self.user_scale * self.item_scale)
         self.last_stats: Dict[str, int] = {}
+        self.profile = False                       # record CUDA events around each stage of topk()
+        self.stage_ms: Dict[str, float] = {}
+        self._events = []
 
     def topk(self, user_ids: Optional[torch.Tensor], k: int, filter_items: Optional[Dict[int, set]] = None,
              fallback: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -76,10 +84,12 @@ class FusedScorer:
             if uids is None:
                 uids = torch.arange(total, device=dev)
             excl = engine.exclusion_csr(uids, filter_items, dev)
+        self._events = []
         for b0 in range(0, total, MAX_USERS_PER_LAUNCH):
             b1 = min(total, b0 + MAX_USERS_PER_LAUNCH)
             self._launch(uids, b0, b1, k, excl, ids, sc, cert)
         self.last_stats = {"users": total, "uncertified": 0}
+        self._mark("fallback_begin")
         if fallback and total:
             bad = (cert == 0).nonzero().view(-1)
             n_bad = int(bad.numel())
@@ -93,7 +103,21 @@ class FusedScorer:
                                                 item_begin=self.item_begin)
                 ids[bad] = e_ids
                 sc[bad] = e_sc
+        self._mark("fallback_end")
+        if self.profile:
+            torch.cuda.synchronize(dev)
+            ms: Dict[str, float] = {}
+            for (n0, e0), (n1, e1) in zip(self._events[:-1], self._events[1:]):
+                if n0.endswith("_begin") and n1 == n0[:-6] + "_end":
+                    ms[n0[:-6]] = ms.get(n0[:-6], 0.0) + e0.elapsed_time(e1)
+            self.stage_ms = ms
         return ids, sc
+
+    def _mark(self, name: str) -> None:
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._events.append((name, ev))
 
     def _launch(self, uids, b0, b1, k, excl, ids, sc, cert) -> None:
         dev = self.item_emb.device
@@ -102,23 +126,29 @@ class FusedScorer:
         with torch.cuda.device(dev):
             s = stream()
             users_f16 = torch.empty(padded, 64, dtype=torch.float16, device=dev)
+            self._mark("pack_begin")
             if uids is None:
                 src = self.user_emb[b0:b1]
-                call("hnm_score_pack", ptr(src), None, n, padded, 64, self.user_scale, ptr(users_f16), None, s)
+                call("hnm_score_pack", ptr(src), None, n, padded, 64, None, self.user_scale, ptr(users_f16), None, s)
                 rid = None
                 user_base = src
             else:
                 rid = uids[b0:b1]
-                call("hnm_score_pack", ptr(self.user_emb), ptr(rid), n, padded, 64, self.user_scale, ptr(users_f16),
-                     None, s)
+                call("hnm_score_pack", ptr(self.user_emb), ptr(rid), n, padded, 64, None, self.user_scale,
+                     ptr(users_f16), None, s)
                 user_base = self.user_emb
             cand = torch.empty(n, CAND_CAP, 2, dtype=torch.int32, device=dev)
             count = torch.empty(n, dtype=torch.int32, device=dev)
             thresh = torch.empty(n, dtype=torch.float32, device=dev)
+            self._mark("pack_end")
+            self._mark("fused_begin")
             call("hnm_score_topk_fused", ptr(users_f16), n, padded, ptr(self.items_f16), self.num_items,
-                 self.items_padded, min(32, k + SEL_MARGIN), ptr(cand), CAND_CAP, ptr(count), ptr(thresh), s)
+                 self.items_padded, min(32, k + self.sel_margin), ptr(cand), CAND_CAP, ptr(count), ptr(thresh), s)
+            self._mark("fused_end")
             ex_ptr = excl[0][b0:b1 + 1] if excl[0] is not None else None
+            self._mark("rescore_begin")
             call("hnm_rescore_topk", ptr(user_base), ptr(self.item_emb), ptr(rid), n, 64, self.item_begin,
-                 ptr(cand), CAND_CAP, ptr(count), ptr(thresh), self.inv_scale, self.max_item_norm,
-                 ptr(ex_ptr), ptr(excl[1]), k, ptr(ids[b0:b1]), ptr(sc[b0:b1]), ptr(cert[b0:b1]), s)
+                 self.num_items, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), self.inv_scale, self.max_item_norm,
+                 ptr(self.center), ptr(ex_ptr), ptr(excl[1]), k, ptr(ids[b0:b1]), ptr(sc[b0:b1]), ptr(cert[b0:b1]), s)
+            self._mark("rescore_end")
         self._debug = (count, thresh)

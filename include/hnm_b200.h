@@ -137,28 +137,35 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
  *          the epilogue keeps, per user, every item whose approximate score beats a
  *          running threshold tau (the kth_sel-th largest of 32 disjoint bucket
  *          maxima, a lower bound on the kth_sel-th best score).  The [users, items]
- *          score matrix never exists in memory.  Per user it emits cand_count
- *          entries {fp32 approx score bits, LOCAL item index} (cand_count may
- *          exceed cand_cap: overflow, the user is then not certifiable) and the
- *          final tau: every item that is not a stored candidate scored <= tau.
- * Stage 3  hnm_rescore_topk: exact fp64 scores (k = 0..dim-1 fma chain) of the
- *          candidates above tau, optional exclusion (lightgcn.py:349-353), canonical
+ *          score matrix never exists in memory.  The unit of nomination is a group
+ *          of 4 adjacent items: per user the kernel emits cand_count entries
+ *          {fp32 bits of the group's best approx score, LOCAL index of its first
+ *          item} (cand_count may exceed cand_cap: overflow, the user is then not
+ *          certifiable) and the final tau: every item outside the stored groups
+ *          scored <= tau.
+ * Stage 3  hnm_rescore_topk: exact fp64 scores (k = 0..dim-1 fma chain) of the items
+ *          of the groups that ended above tau, optional exclusion (lightgcn.py:349-353), canonical
  *          (score desc, id asc) top-k, and a per-user certificate
- *              exact_kth > tau / (su*si) + eps,
- *              eps = 1.1 * 2^-10 * ||u|| * max_item_norm + dim * 2^-8 / (su*si)
+ *              exact_kth > tau / (su*si) + eps + u.c,
+ *              eps = 1.1 * 2^-10 * ||u|| * max_j ||x_j - c|| + dim * 2^-8 / (su*si)
  *          that no non-candidate can belong to the top-k given the fp16 rounding bound.
  * Users whose certificate fails are re-run through hnm_topk_exact by the caller.
  * ---------------------------------------------------------------------- */
 #define HNM_FUSED_DIM 64            /* embedding dimension of the tensor-core path */
 #define HNM_FUSED_USER_TILE 128     /* users per accumulator (UMMA M) */
-#define HNM_FUSED_USER_BLOCK 512    /* users per CTA pass; users_padded must be a multiple */
+#define HNM_FUSED_USER_BLOCK 384    /* users per CTA pass; users_padded must be a multiple */
 #define HNM_FUSED_ITEM_TILE 128     /* items per MMA tile (UMMA N); items_padded must be a multiple */
-#define HNM_FUSED_CAND_MAX 128      /* largest cand_cap */
+#define HNM_FUSED_CAND_MAX 256      /* largest cand_cap */
 
-/* max |x| over `count` floats -> *out_absmax (device float, zeroed by the caller). */
-HNM_API int hnm_absmax(const float* emb, int64_t count, float* out_absmax, void* stream);
+/* max |x - center[col]| over `count` floats of a [rows, dim] table -> *out_absmax (device float,
+ * zeroed by the caller).  center NULL = no centring. */
+HNM_API int hnm_absmax(const float* emb, int64_t count, const float* center, int32_t dim, float* out_absmax,
+               void* stream);
+/* out = fp16((emb[row] - center) * scale).  Item tables are centred on their mean row: for a fixed
+ * user, u.x and u.(x - c) rank items identically, and the smaller magnitudes tighten the bound. */
 HNM_API int hnm_score_pack(const float* emb, const int64_t* row_ids /* NULL = identity */, int64_t num_rows,
-                   int64_t rows_padded, int32_t dim, float scale /* power of two */,
+                   int64_t rows_padded, int32_t dim, const float* center /* [dim] or NULL */,
+                   float scale /* power of two */,
                    void* out_f16 /* [rows_padded, dim] __half */, float* out_sumsq /* [num_rows] or NULL */,
                    void* stream);
 HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */, int64_t num_users, int64_t users_padded,
@@ -169,8 +176,11 @@ HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */,
                          float* cand_thresh /* [num_users] final tau (scaled units) */, void* stream);
 HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb /* local shard rows */,
                      const int64_t* user_ids /* NULL = identity */, int64_t batch, int32_t dim, int64_t item_begin,
+                     int64_t num_items_local /* rows of item_emb; columns past it are zero padding */,
                      const void* cand, int32_t cand_cap, const int32_t* cand_count, const float* cand_thresh,
-                     double inv_scale_product /* 1/(user_scale*item_scale) */, double max_item_norm,
+                     double inv_scale_product /* 1/(user_scale*item_scale) */,
+                     double max_item_norm /* max ||x_j - center|| over the shard */,
+                     const float* center /* the item centre used by hnm_score_pack, or NULL */,
                      const int64_t* excl_ptr, const int64_t* excl_items /* GLOBAL ids, sorted per user */,
                      int32_t k, int64_t* out_ids /* [batch,k] GLOBAL item ids */, double* out_scores /* [batch,k] */,
                      int32_t* out_certified /* [batch] 1 = provably exact */, void* stream);

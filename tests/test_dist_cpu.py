@@ -1,0 +1,114 @@
+"""world_size-2 gloo test of the multi-GPU host logic (partitioning, the three exchanges, merge order).
+The kernels are replaced by the oracle through the Backend hook, so this runs without a GPU."""
+import os
+import socket
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class OracleBackend:
+    """Same contract as hnm_recommendation_b200.dist.CudaBackend, computed on CPU by the oracle."""
+
+    def propagate(self, model, my_ranges, exchange):
+        rowptr, col, val, _ = model.graph
+        w = model.embeddings.weight
+        acc = model.alpha[0] * w
+        cur = w
+        for layer in range(1, model.num_layers + 1):
+            full = O.lightgcn_oracle._spmm(rowptr, col, val, cur)
+            nxt = torch.full_like(w, float("nan"))            # rows this rank does not own stay garbage
+            for r0, r1 in my_ranges:
+                nxt[r0:r1] = full[r0:r1]
+                acc[r0:r1] += model.alpha[layer] * full[r0:r1]
+            if layer < model.num_layers:
+                exchange(nxt)
+                assert not torch.isnan(nxt).any(), "exchange left rows unfilled"
+            cur = nxt
+        exchange(acc)
+        return acc
+
+    def local_topk(self, sharded, ue, ie_shard, item_begin, k):
+        ids, sc = O.recommend_exact(ue, ie_shard.contiguous(), torch.arange(ue.size(0)), k)
+        return ids + item_begin, sc
+
+    def merge(self, ids, scores):
+        g, n, k = ids.shape
+        ids = ids.permute(1, 0, 2).reshape(n, g * k)
+        sc = scores.permute(1, 0, 2).reshape(n, g * k)
+        o1 = torch.sort(ids, dim=1, stable=True).indices                       # id ascending ...
+        sc1, ids1 = torch.gather(sc, 1, o1), torch.gather(ids, 1, o1)
+        o2 = torch.sort(sc1, dim=1, descending=True, stable=True).indices      # ... then score descending, stable
+        return torch.gather(ids1, 1, o2)[:, :k].contiguous(), torch.gather(sc1, 1, o2)[:, :k].contiguous()
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hnm_recommendation_b200 import dist as hdist
+        torch.manual_seed(0)
+        U, I, d, L, k = 203, 97, 16, 3, 12                     # sizes that do not divide by the world size
+        g = torch.Generator().manual_seed(1)
+        u = torch.randint(0, U, (1500,), generator=g)
+        i = torch.randint(0, I, (1500,), generator=g) + U
+        ei = torch.stack([torch.cat([u, i]), torch.cat([i, u])])
+        w = torch.randn(U + I, d, generator=g) * 0.1
+        model = SimpleNamespace(num_users=U, num_items=I, top_k=k, num_layers=L, alpha=O.layer_weights(L),
+                                graph=O.build_norm_adj(ei, None, U + I), embeddings=SimpleNamespace(weight=w))
+        sh = hdist.ShardedLightGCN(model, backend=OracleBackend())
+        plan = sh.plan
+        assert plan.user_rows[0][0] == 0 and plan.user_rows[-1][1] == U
+        assert plan.item_rows[0][0] == U and plan.item_rows[-1][1] == U + I
+        assert sum(b - a for a, b in plan.item_shards) == I
+        ue, ie = sh.forward()
+        rowptr, col, val, _ = model.graph
+        ou, oi = O.forward(w, rowptr, col, val, U, L, model.alpha)
+        assert torch.allclose(ue, ou, rtol=1e-6, atol=1e-8) and torch.allclose(ie, oi, rtol=1e-6, atol=1e-8)
+        ids, sc = sh.recommend_all(return_scores=True)
+        want_ids, want_sc = O.recommend_exact(ou, oi, torch.arange(U), k)
+        ok = torch.equal(ids, want_ids) and torch.allclose(sc, want_sc, rtol=1e-12, atol=0)
+        q.put((rank, bool(ok), ""))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_lightgcn_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, ok, err in results:
+        assert ok, f"rank {rank} failed:\n{err}"
+
+
+def test_even_ranges_and_plan():
+    from hnm_recommendation_b200.dist import ShardPlan, even_ranges
+    assert even_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert even_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    p = ShardPlan.make(1371980, 105542, 8, 3)
+    assert p.user_rows[7][1] == 1371980 and p.item_rows[0][0] == 1371980 and p.item_rows[7][1] == 1371980 + 105542
+    sizes = [b - a for a, b in p.item_shards]
+    assert max(sizes) - min(sizes) <= 1
