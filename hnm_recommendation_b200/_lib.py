@@ -34,7 +34,7 @@ _SIGNATURES = {
     "hnm_lightgcn_layer": (C.c_int, [P, P, P, P, P, P, P, F32, I64, I32, I64, I64, P, I32, I32, P]),
     "hnm_pair_scores": (C.c_int, [P, P, P, P, I64, I32, I64, I64, P, P]),
     "hnm_score_all_items": (C.c_int, [P, P, P, I64, I64, I32, P, P]),
-    "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, P, P, P]),
+    "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, I32, P, P, P]),
     "hnm_score_pack": (C.c_int, [P, P, I64, I64, I32, P, F32, P, P, P]),
     "hnm_absmax": (C.c_int, [P, I64, P, I32, P, P]),
     "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, P, I32, P, P, P]),

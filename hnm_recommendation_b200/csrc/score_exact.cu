@@ -6,6 +6,7 @@
 // hnm_topk_exact is the correctness anchor of the tensor-core path and its fallback for
 // users whose certificate fails; it never writes the [users, items] score matrix.
 #include <math.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace {
@@ -137,6 +138,15 @@ topk_exact_kernel(const float* __restrict__ ue, const float* __restrict__ ie, co
 
   const int64_t ub = (int64_t)blockIdx.x * XU;
   const int nu = (batch - ub < XU) ? (int)(batch - ub) : XU;
+  if (gridDim.y > 1) {     // item range split across blockIdx.y; partial lists are merged afterwards
+    const int64_t chunk = (item_end - item_begin + gridDim.y - 1) / gridDim.y;
+    const int64_t b0 = item_begin + chunk * blockIdx.y;
+    ie += (size_t)(b0 - item_begin) * dim;
+    item_end = (b0 + chunk < item_end) ? b0 + chunk : item_end;
+    item_begin = b0;
+    out_ids += (size_t)blockIdx.y * batch * k;
+    out_scores += (size_t)blockIdx.y * batch * k;
+  }
   for (int t = threadIdx.x; t < dim * XU; t += XT) {
     const int kk = t / XU, u = t % XU;
     double v = 0.0;
@@ -292,8 +302,8 @@ extern "C" int hnm_score_all_items(const float* user_emb, const float* item_emb,
 
 extern "C" int hnm_topk_exact(const float* user_emb, const float* item_emb, const int64_t* user_ids, int64_t batch,
                               int64_t item_begin, int64_t item_end, int32_t dim, int32_t k,
-                              const int64_t* excl_ptr, const int64_t* excl_items, int64_t* out_ids,
-                              double* out_scores, void* stream_) {
+                              const int64_t* excl_ptr, const int64_t* excl_items, int32_t item_splits,
+                              int64_t* out_ids, double* out_scores, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (batch == 0) return HNM_OK;
   if (!user_emb || !item_emb || !out_ids || !out_scores) return HNM_E_NULL;
@@ -308,8 +318,12 @@ extern "C" int hnm_topk_exact(const float* user_emb, const float* item_emb, cons
     attr_set = true;
   }
   const unsigned grid = (unsigned)((batch + XU - 1) / XU);
-  topk_exact_kernel<<<grid, XT, smem, stream>>>(user_emb, item_emb, user_ids, batch, item_begin, item_end, dim, k,
-                                               excl_ptr, excl_items, out_ids, out_scores);
+  const int64_t items = item_end - item_begin;
+  if (item_splits < 1 || item_splits > 64 || (item_splits > 1 && items / item_splits < std::max<int64_t>(k, 1)))
+    return HNM_E_RANGE;
+  topk_exact_kernel<<<dim3(grid, item_splits), XT, smem, stream>>>(user_emb, item_emb, user_ids, batch, item_begin,
+                                                                   item_end, dim, k, excl_ptr, excl_items, out_ids,
+                                                                   out_scores);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }

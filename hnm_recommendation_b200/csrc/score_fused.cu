@@ -49,8 +49,7 @@ constexpr int kThreads = (4 + kEpiWarps) * 32;   // 512
 constexpr int kTileBytes = kItemTile * kDim * 2; // 16384 (A tile and B tile have the same shape)
 constexpr int kNumBuckets = 32;
 
-static_assert(kUserTile == HNM_FUSED_USER_TILE && kItemTile == HNM_FUSED_ITEM_TILE && kSuper == HNM_FUSED_USER_BLOCK,
-              "header mismatch");
+static_assert(kUserTile == HNM_FUSED_USER_TILE && kItemTile == HNM_FUSED_ITEM_TILE, "header mismatch");
 
 struct __align__(8) Barriers {
   uint64_t a_full[2], a_empty[2];
@@ -252,7 +251,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& 
 // ----------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
-                        int num_users, int num_super, int num_item_tiles, int kth_sel,
+                        int num_users, int num_user_tiles, int num_item_tiles, int kth_sel,
                         uint2* __restrict__ cand, int cap, int32_t* __restrict__ cand_count,
                         float* __restrict__ cand_thresh, int mode) {
   extern __shared__ uint8_t smem_raw[];
@@ -265,6 +264,11 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
   const int lane = threadIdx.x & 31;
   const int boot = num_item_tiles < kBootTiles ? num_item_tiles : kBootTiles;
   const int num_iters = num_item_tiles + boot;
+  // user tiles are dealt out evenly: CTA b owns [t_begin, t_end) and walks it in passes of up to kMU
+  // tiles, so CTAs differ by at most one tile (a third of a pass), not by a whole pass
+  const int t_base = num_user_tiles / (int)gridDim.x, t_rem = num_user_tiles % (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * t_base + min((int)blockIdx.x, t_rem);
+  const int t_end = t_begin + t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_users);
@@ -293,13 +297,14 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     if (lane == 0) {
       uint32_t g = 0;
       int n = 0;
-      for (int st = blockIdx.x; st < num_super; st += gridDim.x, ++n) {
+      for (int t0 = t_begin; t0 < t_end; t0 += kMU, ++n) {
+        const int mc = min(kMU, t_end - t0);
         const int abuf = n & 1;
         mbar_wait(&bars->a_empty[abuf], ((n >> 1) & 1) ^ 1);
-        mbar_expect_tx(&bars->a_full[abuf], kMU * kTileBytes);
-        for (int m = 0; m < kMU; ++m)
+        mbar_expect_tx(&bars->a_full[abuf], mc * kTileBytes);
+        for (int m = 0; m < mc; ++m)
           tma_load_2d(smem_a + (abuf * kMU + m) * kTileBytes, &map_users, &bars->a_full[abuf], 0,
-                      st * kSuper + m * kUserTile);
+                      (t0 + m) * kUserTile);
         for (int it = 0; it < num_iters; ++it, ++g) {
           const int tile = it < boot ? it : it - boot;
           const int stage = g % kStagesB;
@@ -318,7 +323,8 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       uint32_t g = 0, w = 0;
       int n = 0;
       const uint64_t desc_hi = umma_desc_sw128(0) & ~uint64_t(0x3FFF);
-      for (int st = blockIdx.x; st < num_super; st += gridDim.x, ++n) {
+      for (int t0 = t_begin; t0 < t_end; t0 += kMU, ++n) {
+        const int mc = min(kMU, t_end - t0);
         const int abuf = n & 1;
         mbar_wait(&bars->a_full[abuf], (n >> 1) & 1);
         const uint32_t a_base = smem_u32(smem_a + abuf * kMU * kTileBytes);
@@ -328,7 +334,8 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
           tc_fence_after();
           const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(smem_b + stage * kTileBytes) >> 4) & 0x3FFF);
 #pragma unroll
-          for (int m = 0; m < kMU; ++m, ++w) {
+          for (int m = 0; m < kMU; ++m) {
+            if (m >= mc) break;
             const uint32_t slot = w % kSlots;
             mbar_wait(&bars->t_empty[slot], ((w / kSlots) & 1) ^ 1);
             tc_fence_after();
@@ -338,6 +345,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
             for (int k = 0; k < kDim / 16; ++k)      // +32 bytes along K = +2 in the 16-byte address field
               umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, k > 0 ? 1u : 0u);
             umma_commit(&bars->t_full[slot]);
+            ++w;
           }
           umma_commit(&bars->b_empty[stage]);
         }
@@ -351,9 +359,11 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     const int m = (warp - 4) >> 2;
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t g = 0;
-    for (int st = blockIdx.x; st < num_super; st += gridDim.x) {
-      const int row = st * kSuper + m * kUserTile + q * 32 + lane;
+    uint32_t w_base = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += kMU) {
+      const int mc = min(kMU, t_end - t0);
+      if (m >= mc) { w_base += (uint32_t)(num_iters * mc); continue; }     // short last pass: this warpgroup rests
+      const int row = (t0 + m) * kUserTile + q * 32 + lane;
       uint2* my_cand = cand + (size_t)(row < num_users ? row : 0) * cap;
       const int my_cap = row < num_users ? cap : 0;      // padded rows count but never store
       RowState rs;
@@ -362,7 +372,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
 #pragma unroll
       for (int i = 0; i < kNumBuckets; ++i) rs.bm[i] = -INFINITY;
       int next_refresh = boot;
-      for (int it = 0; it < num_iters; ++it, ++g) {
+      for (int it = 0; it < num_iters; ++it) {
         const int tile = it < boot ? it : it - boot;
         if (it == next_refresh && mode == 0) {
           // it == boot: the seed pass is over, collecting starts (again from tile 0)
@@ -370,7 +380,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
           const int seen = max(boot, it - boot);         // item tiles behind the current bucket maxima
           next_refresh = it + max(2, seen / 8);
         }
-        const uint32_t w = g * kMU + m;
+        const uint32_t w = w_base + (uint32_t)(it * mc + m);
         const uint32_t slot = w % kSlots;
         mbar_wait(&bars->t_full[slot], (w / kSlots) & 1);
         tc_fence_after();
@@ -391,6 +401,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
           drain_tile<true>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
         }
       }
+      w_base += (uint32_t)(num_iters * mc);
       if (mode == 0) rs.tau = refresh_tau(rs.bm, kth_sel);
       if (row < num_users) {
         cand_count[row] = rs.cnt;
@@ -467,6 +478,11 @@ __device__ __forceinline__ bool in_sorted(const int64_t* __restrict__ a, int64_t
   return false;
 }
 
+// (score desc, id asc) with 32-bit ids; used by the warp-wide sort below
+__device__ __forceinline__ bool before32(double sa, int ia, double sb, int ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+
 __global__ void __launch_bounds__(256)
 rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
                const int64_t* __restrict__ user_ids, int64_t batch, int dim, int64_t item_begin, int num_items_local,
@@ -476,6 +492,8 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
                const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
                double* __restrict__ out_scores, int32_t* __restrict__ certified) {
   __shared__ uint32_t s_col[8][32];
+  __shared__ double s_sc[8][32];
+  __shared__ int s_id[8][32];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -510,84 +528,87 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
   const bool too_many = groups > 32;
   const int col0 = lane < min(groups, 32) ? (int)s_col[wib][lane] : -1;
 
-  // 2. exact fp64 score (k = 0..dim-1 fma chain) of the four items of my group
-  double s[kGroup];
-  int64_t id[kGroup];
-  int kept = 0;
+  // 2. exact fp64 scores (k = 0..dim-1 fma chain per item) of the four items of my group; the four
+  //    chains advance together so eight row loads are in flight and u is converted once per step
+  bool live[kGroup];
+  const float* irow[kGroup];
+  double acc[kGroup];
 #pragma unroll
   for (int e = 0; e < kGroup; ++e) {
-    s[e] = -INFINITY;
-    id[e] = INT64_MAX;
     const int item = col0 + e;
-    if (col0 >= 0 && item < num_items_local) {          // columns past the catalog are zero padding
-      const int64_t gid = item_begin + (int64_t)item;
-      if (!(ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, gid))) {
-        const float* irow = item_emb + (size_t)item * dim;
-        double acc = 0.0;
-        for (int kk = 0; kk < dim; kk += 4) {
-          const float4 u = ldg_f4(urow + kk), v = ldg_f4(irow + kk);
-          acc = fma((double)u.x, (double)v.x, acc);
-          acc = fma((double)u.y, (double)v.y, acc);
-          acc = fma((double)u.z, (double)v.z, acc);
-          acc = fma((double)u.w, (double)v.w, acc);
-        }
-        s[e] = acc;
-        id[e] = gid;
-        ++kept;
+    live[e] = col0 >= 0 && item < num_items_local;          // columns past the catalog are zero padding
+    if (live[e] && ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)item)) live[e] = false;
+    irow[e] = item_emb + (size_t)(live[e] ? item : 0) * dim;
+    acc[e] = 0.0;
+  }
+  double un = 0.0, uc = 0.0, uc_abs = 0.0;                  // ||u||^2, u.c, sum |u_k c_k|
+  for (int kk = 0; kk < dim; kk += 4) {
+    const float4 uf = ldg_f4(urow + kk);
+    float4 vf[kGroup];
+#pragma unroll
+    for (int e = 0; e < kGroup; ++e) vf[e] = ldg_f4(irow[e] + kk);
+    const double u0 = (double)uf.x, u1 = (double)uf.y, u2 = (double)uf.z, u3 = (double)uf.w;
+#pragma unroll
+    for (int e = 0; e < kGroup; ++e) {
+      acc[e] = fma(u0, (double)vf[e].x, acc[e]);
+      acc[e] = fma(u1, (double)vf[e].y, acc[e]);
+      acc[e] = fma(u2, (double)vf[e].z, acc[e]);
+      acc[e] = fma(u3, (double)vf[e].w, acc[e]);
+    }
+    if (lane == ((kk >> 2) & 31)) {        // every lane sees the whole user row: count each k on one lane
+      un = fma(u0, u0, un); un = fma(u1, u1, un); un = fma(u2, u2, un); un = fma(u3, u3, un);
+      if (center) {
+        const float4 cf = ldg_f4(center + kk);
+        const double c0 = (double)cf.x, c1 = (double)cf.y, c2 = (double)cf.z, c3 = (double)cf.w;
+        uc = fma(u0, c0, uc); uc = fma(u1, c1, uc); uc = fma(u2, c2, uc); uc = fma(u3, c3, uc);
+        uc_abs += fabs(u0 * c0) + fabs(u1 * c1) + fabs(u2 * c2) + fabs(u3 * c3);
       }
     }
-  }
-  // ||u||_2 for the error bound, u.c to translate centred scores back
-  double un = 0.0, uc = 0.0, uc_abs = 0.0;
-  for (int kk = lane; kk < dim; kk += 32) {
-    const double u = (double)urow[kk];
-    un = fma(u, u, un);
-    if (center) { const double c = (double)center[kk]; uc = fma(u, c, uc); uc_abs += fabs(u * c); }
   }
 #pragma unroll
   for (int off = 16; off; off >>= 1) {
     un += __shfl_xor_sync(0xffffffffu, un, off);
     uc += __shfl_xor_sync(0xffffffffu, uc, off);
     uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
-    kept += __shfl_xor_sync(0xffffffffu, kept, off);
   }
   un = sqrt(un);
+  // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
+  const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
+  const double cut = (double)thr * inv_scale + eps + uc;
 
-  // 3. canonical top-k of the exact scores: k rounds of warp argmax by (score desc, id asc)
-  double kth_score = -INFINITY;
-  for (int t = 0; t < k; ++t) {
-    double bs = s[0];
-    int64_t bi = id[0];
-    int be = 0;
+  // 3. contenders = rescored items strictly above the cut.  With at least k of them the k best
+  //    contenders are provably the exact top-k; compact them one per lane and sort the warp.
+  int total = 0;
 #pragma unroll
-    for (int e = 1; e < kGroup; ++e)
-      if (hnm_before(s[e], id[e], bs, bi)) { bs = s[e]; bi = id[e]; be = e; }
-    double ws = bs;
-    int64_t wi = bi;
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      const double os = __shfl_xor_sync(0xffffffffu, ws, off);
-      const int64_t oi = __shfl_xor_sync(0xffffffffu, wi, off);
-      if (hnm_before(os, oi, ws, wi)) { ws = os; wi = oi; }
-    }
-    if (wi == bi && ws == bs && bi != INT64_MAX) {   // ids are unique, so exactly one lane matches
-#pragma unroll
-      for (int e = 0; e < kGroup; ++e)
-        if (e == be) { s[e] = -INFINITY; id[e] = INT64_MAX; }
-    }
-    if (lane == 0) {
-      out_ids[(size_t)b * k + t] = wi;
-      out_scores[(size_t)b * k + t] = ws;
-    }
-    kth_score = ws;
+  for (int e = 0; e < kGroup; ++e) {
+    const bool c = live[e] && acc[e] > cut;
+    const unsigned mask = __ballot_sync(0xffffffffu, c);
+    const int pos = total + __popc(mask & ((1u << lane) - 1u));
+    if (c && pos < 32) { s_sc[wib][pos] = acc[e]; s_id[wib][pos] = col0 + e; }
+    total += __popc(mask);
   }
-  if (lane == 0) {
-    // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c
-    const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale +
-                       1e-12 * uc_abs;
-    const bool ok = raw <= cap && !too_many && kept >= k && kth_score > (double)thr * inv_scale + eps + uc;
-    certified[b] = ok ? 1 : 0;
+  __syncwarp();
+  double ms = lane < min(total, 32) ? s_sc[wib][lane] : -INFINITY;
+  int mi = lane < min(total, 32) ? s_id[wib][lane] : INT32_MAX;
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const double os = __shfl_xor_sync(0xffffffffu, ms, stride);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, stride);
+      const bool lower = (lane & stride) == 0;                 // lower lane of the pair
+      const bool desc = (lane & size) == 0;                    // this block sorts best-first
+      const bool other_first = before32(os, oi, ms, mi);
+      // the lower lane keeps the better entry in a best-first block, the worse one otherwise
+      const bool take = (lower == desc) ? other_first : !other_first && !(os == ms && oi == mi);
+      if (take) { ms = os; mi = oi; }
+    }
   }
+  if (lane < k) {
+    out_ids[(size_t)b * k + lane] = mi == INT32_MAX ? INT64_MAX : item_begin + (int64_t)mi;
+    out_scores[(size_t)b * k + lane] = ms;
+  }
+  if (lane == 0) certified[b] = (raw <= cap && !too_many && total >= k && total <= 32) ? 1 : 0;
 }
 
 int make_map(CUtensorMap* map, const void* base, int64_t rows) {
@@ -646,7 +667,7 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!users_f16 || !items_f16 || !cand || !cand_count || !cand_thresh) return HNM_E_NULL;
   if (num_users <= 0 || num_items <= 0 || users_padded < num_users || items_padded < num_items) return HNM_E_RANGE;
-  if (users_padded % kSuper != 0 || items_padded % kItemTile != 0) return HNM_E_RANGE;
+  if (users_padded % kUserTile != 0 || items_padded % kItemTile != 0) return HNM_E_RANGE;
   if (users_padded > INT32_MAX || items_padded > INT32_MAX) return HNM_E_RANGE;
   if (kth_sel < 1 || kth_sel > kNumBuckets || cand_cap < 1 || cand_cap > 32 * kMaxPerLane) return HNM_E_RANGE;
   if ((reinterpret_cast<uintptr_t>(users_f16) & 127) || (reinterpret_cast<uintptr_t>(items_f16) & 127)) return HNM_E_ALIGN;
@@ -662,10 +683,10 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
     attr_set = true;
   }
   static const int debug_mode = getenv("HNM_FUSED_DEBUG") ? atoi(getenv("HNM_FUSED_DEBUG")) : 0;
-  const int num_super = (int)(users_padded / kSuper);
+  const int num_user_tiles = (int)(users_padded / kUserTile);
   const int num_tiles = (int)(items_padded / kItemTile);
-  const int grid = std::min(num_super, hnm_num_sms());
-  score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_u, map_i, (int)num_users, num_super,
+  const int grid = std::min((num_user_tiles + kMU - 1) / kMU, hnm_num_sms());
+  score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_u, map_i, (int)num_users, num_user_tiles,
                                                                   num_tiles, kth_sel, (uint2*)cand,
                                                                   cand_cap, cand_count, cand_thresh, debug_mode);
   HNM_LAUNCH_CHECK();

@@ -7,9 +7,15 @@ one BASELINE.json's north_star prescribes:
     of the item rows, so every rank gets the same mix of short user rows and long item rows); after
     every layer the freshly written row slices are all-gathered so the next layer can gather from
     all rows;
-  * scoring: the item catalog is sharded; each rank runs the fused score/select + exact rescoring
-    against its item shard for ALL users, the per-shard exact top-k lists are exchanged (all-to-all
-    by user slice), merged by (score desc, item id asc), and the merged slices are all-gathered.
+  * scoring, mode "items" (north_star): the item catalog is sharded; each rank runs the fused
+    score/select + exact rescoring against its item shard for ALL users, the per-shard exact top-k
+    lists are exchanged (all-to-all by user slice), merged by (score desc, item id asc), and the
+    merged slices are all-gathered;
+  * scoring, mode "users" (default): users are independent units, so each rank scores the users of
+    its own row slice against the whole catalog (27 MB, replicated) with no data-path collective;
+    only the [U/G, k] results are all-gathered, and the last propagation exchange shrinks to the
+    item rows.  Per-rank work (nomination, rescoring, fallback) then falls as 1/G, which the item
+    mode cannot do: every item shard nominates ~k candidates for every user.
 
 The compute steps are injected (``Backend``) so the host logic -- partitioning, exchanges, merge
 order -- can be exercised on CPU with gloo and the oracle standing in for the kernels.
@@ -99,8 +105,12 @@ class Collectives:
 class ShardedLightGCN:
     """Wraps a LightGCN whose parameters and graph are replicated on every rank."""
 
-    def __init__(self, model, group=None, backend=None):
+    def __init__(self, model, group=None, backend=None, mode: Optional[str] = None):
+        import os
         self.model = model
+        self.mode = mode or os.environ.get("HNM_SHARD_MODE", "users")
+        if self.mode not in ("users", "items"):
+            raise ValueError("mode must be 'users' or 'items'")
         self.coll = Collectives(group)
         self.plan = ShardPlan.make(model.num_users, model.num_items, self.coll.world, self.coll.rank)
         self.backend = backend or CudaBackend()
@@ -108,7 +118,9 @@ class ShardedLightGCN:
         self.stage_ms: Dict[str, float] = {}
 
     # ---------------------------------------------------------------- propagate
-    def forward(self) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward(self, all_rows: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(user_embeddings, item_embeddings).  With all_rows=False in "users" mode only this rank's
+        user rows (plan.user_rows[rank]) and all item rows are valid."""
         m, p = self.model, self.plan
         if m.graph is None:
             raise RuntimeError("Graph not set. Call set_graph() first.")
@@ -118,7 +130,11 @@ class ShardedLightGCN:
             self.coll.allgather_rows(buf, p.user_rows)
             self.coll.allgather_rows(buf, p.item_rows)
 
-        final = self.backend.propagate(m, my_ranges, exchange)
+        def exchange_items(buf):
+            self.coll.allgather_rows(buf, p.item_rows)
+
+        final = self.backend.propagate(m, my_ranges, exchange,
+                                       exchange_items if (self.mode == "users" and not all_rows) else exchange)
         self._scorer = None
         return final[: m.num_users], final[m.num_users:]
 
@@ -127,6 +143,14 @@ class ShardedLightGCN:
         m, p = self.model, self.plan
         k = m.top_k if k is None else int(k)
         with torch.no_grad():
+            if self.mode == "users":
+                ue, ie = self.forward(all_rows=False)
+                u0, u1 = p.user_slices[p.rank]
+                ids, sc = self.backend.local_topk(self, ue[u0:u1], ie, 0, k)           # my users vs all items
+                out_ids = self.coll.allgather_slices(ids, p.user_slices, m.num_users)
+                if return_scores:
+                    return out_ids, self.coll.allgather_slices(sc, p.user_slices, m.num_users)
+                return out_ids
             ue, ie = self.forward()
             i0, i1 = p.item_shards[p.rank]
             ids, sc = self.backend.local_topk(self, ue, ie[i0:i1], i0, k)           # [U, k] vs my item shard
@@ -142,15 +166,16 @@ class ShardedLightGCN:
 class CudaBackend:
     """The B200 kernels (default)."""
 
-    def propagate(self, model, my_ranges, exchange):
+    def propagate(self, model, my_ranges, exchange, exchange_final):
         from . import engine
         return engine.propagate(model.graph, model.embeddings.weight, model.alpha, model.num_layers,
-                                row_ranges=my_ranges, exchange=exchange)
+                                row_ranges=my_ranges, exchange=exchange, exchange_final=exchange_final)
 
     def local_topk(self, sharded, ue, ie_shard, item_begin, k):
         from . import engine
         from .scorer import FusedScorer
         ie_shard = ie_shard.contiguous()
+        ue = ue.contiguous()
         if FusedScorer.supports(ue.size(1), k, ie_shard.size(0)):
             sharded._scorer = FusedScorer(ue, ie_shard, item_begin=item_begin)
             return sharded._scorer.topk(None, k)

@@ -21,6 +21,7 @@ FUSED_USER_TILE = 128
 FUSED_ITEM_TILE = 256
 FUSED_CAND = 32
 FUSED_K_MAX = 16
+NUM_SMS = 148
 
 
 @dataclass
@@ -70,12 +71,15 @@ def build_graph(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n
 
 
 def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
-              row_ranges: Optional[Sequence[Tuple[int, int]]] = None, exchange=None) -> torch.Tensor:
+              row_ranges: Optional[Sequence[Tuple[int, int]]] = None, exchange=None,
+              exchange_final=None) -> torch.Tensor:
     """LightGCN.forward (lightgcn.py:147-158): returns final [N, d] = sum_l alpha_l * A_hat^l E0.
 
     row_ranges/exchange serve the row-sharded multi-GPU form: this rank computes the listed
     row ranges of every layer and ``exchange(buf)`` makes all rows of ``buf`` visible
-    (an allgather of row slices) before the next layer gathers from it.
+    (an allgather of row slices) before the next layer gathers from it; ``exchange_final`` does the
+    same for the returned layer sum (defaults to ``exchange``; a user-sharded scorer only needs the
+    item rows of it).
     """
     _lib.require_device()
     if not e0.is_cuda:
@@ -102,8 +106,9 @@ def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layer
                 if exchange is not None:
                     exchange(nxt)
                 cur, nxt = nxt, cur
-        if exchange is not None:
-            exchange(acc)
+        final_x = exchange_final if exchange_final is not None else exchange
+        if final_x is not None:
+            final_x(acc)
     return acc
 
 
@@ -179,12 +184,20 @@ def topk_exact(user_emb, item_emb, user_ids: Optional[torch.Tensor], k: int,
     dev = user_emb.device
     u = _norm_ids(user_ids, user_emb.size(0), dev)
     b = u.numel() if u is not None else (batch if batch is not None else user_emb.size(0))
-    ids = torch.empty(b, k, dtype=torch.int64, device=dev)
-    sc = torch.empty(b, k, dtype=torch.float64, device=dev)
+    # few users (the fallback of the tensor-core path): split the item range so the launch fills the GPU
+    n_items = int(item_emb.size(0))
+    ctas = max(1, (b + 7) // 8)
+    splits = max(1, min(16, (2 * NUM_SMS + ctas - 1) // ctas, n_items // max(1024, k)))
+    ids = torch.empty(splits, b, k, dtype=torch.int64, device=dev)
+    sc = torch.empty(splits, b, k, dtype=torch.float64, device=dev)
+    if b == 0:
+        return ids[0], sc[0]
     with torch.cuda.device(dev):
-        call("hnm_topk_exact", ptr(user_emb), ptr(item_emb), ptr(u), b, item_begin, item_begin + item_emb.size(0),
-             user_emb.size(1), k, ptr(excl[0]), ptr(excl[1]), ptr(ids), ptr(sc), stream())
-    return ids, sc
+        call("hnm_topk_exact", ptr(user_emb), ptr(item_emb), ptr(u), b, item_begin, item_begin + n_items,
+             user_emb.size(1), k, ptr(excl[0]), ptr(excl[1]), splits, ptr(ids), ptr(sc), stream())
+    if splits == 1:
+        return ids[0], sc[0]
+    return merge_topk(ids, sc)
 
 
 def merge_topk(ids: torch.Tensor, scores: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -16,7 +16,7 @@ import torch
 from . import _lib, engine
 from ._lib import call, ptr, stream
 
-USER_BLOCK = 384
+USER_BLOCK = 128
 ITEM_TILE = 128
 CAND_CAP = 256
 K_MAX = 16

@@ -122,11 +122,15 @@ HNM_API int hnm_score_all_items(const float* user_emb, const float* item_emb, co
  * GLOBAL item ids (NULL = none).  When fewer than k items remain, the tail is
  * filled with score -inf and the smallest excluded ids (ascending).
  * out_ids are GLOBAL item indices (item_begin is added).
+ * item_splits > 1 cuts the item range into that many equal parts handled by different
+ * thread blocks (so a launch with few users still fills the GPU); the outputs are then
+ * [item_splits, batch, k] partial lists to be combined with hnm_merge_topk.
  * ---------------------------------------------------------------------- */
 HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const int64_t* user_ids, int64_t batch,
                    int64_t item_begin, int64_t item_end, int32_t dim, int32_t k,
-                   const int64_t* excl_ptr, const int64_t* excl_items,
-                   int64_t* out_ids /* [batch, k] */, double* out_scores /* [batch, k] */, void* stream);
+                   const int64_t* excl_ptr, const int64_t* excl_items, int32_t item_splits,
+                   int64_t* out_ids /* [item_splits, batch, k] */, double* out_scores /* same shape */,
+                   void* stream);
 
 /* ------------------------------------------------------------------------
  * Fused full-catalog score + top-k (tensor cores)   replaces lightgcn.py:202 + :356
@@ -152,8 +156,7 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
  * Users whose certificate fails are re-run through hnm_topk_exact by the caller.
  * ---------------------------------------------------------------------- */
 #define HNM_FUSED_DIM 64            /* embedding dimension of the tensor-core path */
-#define HNM_FUSED_USER_TILE 128     /* users per accumulator (UMMA M) */
-#define HNM_FUSED_USER_BLOCK 384    /* users per CTA pass; users_padded must be a multiple */
+#define HNM_FUSED_USER_TILE 128     /* users per accumulator (UMMA M); users_padded must be a multiple */
 #define HNM_FUSED_ITEM_TILE 128     /* items per MMA tile (UMMA N); items_padded must be a multiple */
 #define HNM_FUSED_CAND_MAX 256      /* largest cand_cap */
 

@@ -23,7 +23,7 @@ def _free_port():
 class OracleBackend:
     """Same contract as hnm_recommendation_b200.dist.CudaBackend, computed on CPU by the oracle."""
 
-    def propagate(self, model, my_ranges, exchange):
+    def propagate(self, model, my_ranges, exchange, exchange_final):
         rowptr, col, val, _ = model.graph
         w = model.embeddings.weight
         acc = model.alpha[0] * w
@@ -38,7 +38,7 @@ class OracleBackend:
                 exchange(nxt)
                 assert not torch.isnan(nxt).any(), "exchange left rows unfilled"
             cur = nxt
-        exchange(acc)
+        exchange_final(acc)
         return acc
 
     def local_topk(self, sharded, ue, ie_shard, item_begin, k):
@@ -69,7 +69,7 @@ def _worker(rank, world, port, q):
         w = torch.randn(U + I, d, generator=g) * 0.1
         model = SimpleNamespace(num_users=U, num_items=I, top_k=k, num_layers=L, alpha=O.layer_weights(L),
                                 graph=O.build_norm_adj(ei, None, U + I), embeddings=SimpleNamespace(weight=w))
-        sh = hdist.ShardedLightGCN(model, backend=OracleBackend())
+        sh = hdist.ShardedLightGCN(model, backend=OracleBackend(), mode="items")
         plan = sh.plan
         assert plan.user_rows[0][0] == 0 and plan.user_rows[-1][1] == U
         assert plan.item_rows[0][0] == U and plan.item_rows[-1][1] == U + I
@@ -81,6 +81,13 @@ def _worker(rank, world, port, q):
         ids, sc = sh.recommend_all(return_scores=True)
         want_ids, want_sc = O.recommend_exact(ou, oi, torch.arange(U), k)
         ok = torch.equal(ids, want_ids) and torch.allclose(sc, want_sc, rtol=1e-12, atol=0)
+        # default mode: users are sharded, nothing but the results is exchanged
+        sh_u = hdist.ShardedLightGCN(model, backend=OracleBackend(), mode="users")
+        ids_u, sc_u = sh_u.recommend_all(return_scores=True)
+        ok = ok and torch.equal(ids_u, want_ids) and torch.allclose(sc_u, want_sc, rtol=1e-12, atol=0)
+        ue_u, ie_u = sh_u.forward(all_rows=False)
+        a, b = sh_u.plan.user_rows[rank]
+        ok = ok and torch.allclose(ue_u[a:b], ou[a:b], rtol=1e-6, atol=1e-8) and torch.allclose(ie_u, oi, rtol=1e-6, atol=1e-8)
         q.put((rank, bool(ok), ""))
     except Exception as exc:  # noqa: BLE001
         import traceback
