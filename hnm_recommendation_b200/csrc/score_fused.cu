@@ -467,6 +467,8 @@ __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __rest
 // ----------------------------------------------------------------------------- rescoring
 constexpr int kMaxPerLane = 8;   // candidate capacity handled = 32 * kMaxPerLane
 constexpr int kGroup = 4;        // items per nominated group (select32)
+constexpr int kMaxGroups = 64;   // surviving groups hnm_rescore_topk can take per user
+constexpr int kMaxContenders = 128;  // rescored items above the cut it can rank per user
 
 __device__ __forceinline__ bool in_sorted(const int64_t* __restrict__ a, int64_t lo, int64_t hi, int64_t x) {
   while (lo < hi) {
@@ -491,9 +493,9 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
                const float* __restrict__ center, const int64_t* __restrict__ excl_ptr,
                const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
                double* __restrict__ out_scores, int32_t* __restrict__ certified) {
-  __shared__ uint32_t s_col[8][32];
-  __shared__ double s_sc[8][32];
-  __shared__ int s_id[8][32];
+  __shared__ uint32_t s_col[8][kMaxGroups];
+  __shared__ double s_sc[8][kMaxContenders];
+  __shared__ int s_id[8][kMaxContenders];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -521,12 +523,17 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
     }
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     const int pos = groups + __popc(mask & ((1u << lane) - 1u));
-    if (keep && pos < 32) s_col[wib][pos] = c.y;
+    if (keep && pos < kMaxGroups) s_col[wib][pos] = c.y;
     groups += __popc(mask);
   }
   __syncwarp();
-  const bool too_many = groups > 32;
-  const int col0 = lane < min(groups, 32) ? (int)s_col[wib][lane] : -1;
+  const bool too_many = groups > kMaxGroups;
+  groups = min(groups, kMaxGroups);
+  int total = 0;                                            // contenders found so far
+  double un = 0.0, uc = 0.0, uc_abs = 0.0;                  // ||u||^2, u.c, sum |u_k c_k|
+  double cut = 0.0;
+  for (int gb = 0; gb < groups || gb == 0; gb += 32) {      // 32 groups per round; one round is the rule
+  const int col0 = gb + lane < groups ? (int)s_col[wib][gb + lane] : -1;
 
   // 2. exact fp64 scores (k = 0..dim-1 fma chain per item) of the four items of my group; the four
   //    chains advance together so eight row loads are in flight and u is converted once per step
@@ -541,7 +548,6 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
     irow[e] = item_emb + (size_t)(live[e] ? item : 0) * dim;
     acc[e] = 0.0;
   }
-  double un = 0.0, uc = 0.0, uc_abs = 0.0;                  // ||u||^2, u.c, sum |u_k c_k|
   for (int kk = 0; kk < dim; kk += 4) {
     const float4 uf = ldg_f4(urow + kk);
     float4 vf[kGroup];
@@ -555,7 +561,7 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
       acc[e] = fma(u2, (double)vf[e].z, acc[e]);
       acc[e] = fma(u3, (double)vf[e].w, acc[e]);
     }
-    if (lane == ((kk >> 2) & 31)) {        // every lane sees the whole user row: count each k on one lane
+    if (gb == 0 && lane == ((kk >> 2) & 31)) {   // every lane sees the whole user row: count each k on one lane
       un = fma(u0, u0, un); un = fma(u1, u1, un); un = fma(u2, u2, un); un = fma(u3, u3, un);
       if (center) {
         const float4 cf = ldg_f4(center + kk);
@@ -565,50 +571,84 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
       }
     }
   }
+  if (gb == 0) {
 #pragma unroll
-  for (int off = 16; off; off >>= 1) {
-    un += __shfl_xor_sync(0xffffffffu, un, off);
-    uc += __shfl_xor_sync(0xffffffffu, uc, off);
-    uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
+    for (int off = 16; off; off >>= 1) {
+      un += __shfl_xor_sync(0xffffffffu, un, off);
+      uc += __shfl_xor_sync(0xffffffffu, uc, off);
+      uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
+    }
+    un = sqrt(un);
+    // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
+    const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
+    cut = (double)thr * inv_scale + eps + uc;
   }
-  un = sqrt(un);
-  // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
-  const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
-  const double cut = (double)thr * inv_scale + eps + uc;
 
   // 3. contenders = rescored items strictly above the cut.  With at least k of them the k best
   //    contenders are provably the exact top-k; compact them one per lane and sort the warp.
-  int total = 0;
 #pragma unroll
   for (int e = 0; e < kGroup; ++e) {
     const bool c = live[e] && acc[e] > cut;
     const unsigned mask = __ballot_sync(0xffffffffu, c);
     const int pos = total + __popc(mask & ((1u << lane) - 1u));
-    if (c && pos < 32) { s_sc[wib][pos] = acc[e]; s_id[wib][pos] = col0 + e; }
+    if (c && pos < kMaxContenders) { s_sc[wib][pos] = acc[e]; s_id[wib][pos] = col0 + e; }
     total += __popc(mask);
   }
+  }   // rounds of 32 groups
   __syncwarp();
-  double ms = lane < min(total, 32) ? s_sc[wib][lane] : -INFINITY;
-  int mi = lane < min(total, 32) ? s_id[wib][lane] : INT32_MAX;
+  if (total <= 32) {
+    // the rule: one contender per lane, one warp-wide bitonic sort
+    double ms = lane < total ? s_sc[wib][lane] : -INFINITY;
+    int mi = lane < total ? s_id[wib][lane] : INT32_MAX;
 #pragma unroll
-  for (int size = 2; size <= 32; size <<= 1) {
+    for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const double os = __shfl_xor_sync(0xffffffffu, ms, stride);
-      const int oi = __shfl_xor_sync(0xffffffffu, mi, stride);
-      const bool lower = (lane & stride) == 0;                 // lower lane of the pair
-      const bool desc = (lane & size) == 0;                    // this block sorts best-first
-      const bool other_first = before32(os, oi, ms, mi);
-      // the lower lane keeps the better entry in a best-first block, the worse one otherwise
-      const bool take = (lower == desc) ? other_first : !other_first && !(os == ms && oi == mi);
-      if (take) { ms = os; mi = oi; }
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, ms, stride);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, stride);
+        const bool lower = (lane & stride) == 0;                 // lower lane of the pair
+        const bool desc = (lane & size) == 0;                    // this block sorts best-first
+        const bool other_first = before32(os, oi, ms, mi);
+        // the lower lane keeps the better entry in a best-first block, the worse one otherwise
+        const bool take = (lower == desc) ? other_first : !other_first && !(os == ms && oi == mi);
+        if (take) { ms = os; mi = oi; }
+      }
+    }
+    if (lane < k) {
+      out_ids[(size_t)b * k + lane] = mi == INT32_MAX ? INT64_MAX : item_begin + (int64_t)mi;
+      out_scores[(size_t)b * k + lane] = ms;
+    }
+  } else if (total <= kMaxContenders) {
+    // the exception (tau ended far below the k-th score): k rounds of warp argmax over the list
+    for (int t = 0; t < k; ++t) {
+      double bs = -INFINITY;
+      int bi = INT32_MAX, bp = -1;
+      for (int p = lane; p < total; p += 32) {
+        const double x = s_sc[wib][p];
+        const int xi = s_id[wib][p];
+        if (before32(x, xi, bs, bi)) { bs = x; bi = xi; bp = p; }
+      }
+      double ws = bs;
+      int wi = bi;
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, ws, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
+        if (before32(os, oi, ws, wi)) { ws = os; wi = oi; }
+      }
+      if (bp >= 0 && wi == bi && ws == bs) { s_sc[wib][bp] = -INFINITY; s_id[wib][bp] = INT32_MAX; }
+      __syncwarp();
+      if (lane == 0) {
+        out_ids[(size_t)b * k + t] = item_begin + (int64_t)wi;
+        out_scores[(size_t)b * k + t] = ws;
+      }
     }
   }
-  if (lane < k) {
-    out_ids[(size_t)b * k + lane] = mi == INT32_MAX ? INT64_MAX : item_begin + (int64_t)mi;
-    out_scores[(size_t)b * k + lane] = ms;
+  if (lane == 0) {
+    // bit 0: provably exact; bits 1.. say why not (list overflow, > 32 groups, < k contenders, > 32 contenders)
+    const int why = (raw > cap ? 2 : 0) | (too_many ? 4 : 0) | (total < k ? 8 : 0) | (total > kMaxContenders ? 16 : 0);
+    certified[b] = why == 0 ? 1 : why;
   }
-  if (lane == 0) certified[b] = (raw <= cap && !too_many && total >= k && total <= 32) ? 1 : 0;
 }
 
 int make_map(CUtensorMap* map, const void* base, int64_t rows) {

@@ -9,6 +9,7 @@
 // lane, column indices read coalesced and broadcast by shuffle.  Rows longer than
 // `heavy_threshold` are summed by a whole CTA in a fixed order (deterministic).
 #include <algorithm>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -102,8 +103,8 @@ __device__ __forceinline__ void row_epilogue(float4 s, float di, float alpha, fl
   *reinterpret_cast<float4*>(acc_p) = a;
 }
 
-template <int D, bool WEIGHTED>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+template <int D, bool WEIGHTED, int WPC, int RPW>
+__global__ void __launch_bounds__(WPC * 32)
 spmm_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
                  const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
                  float* __restrict__ accbuf, float alpha, int64_t row_begin, int64_t row_end,
@@ -111,9 +112,9 @@ spmm_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   using S = Shape<D>;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int64_t first = row_begin + ((int64_t)blockIdx.x * kWarpsPerCta + warp) * kRowsPerWarp;
+  const int64_t first = row_begin + ((int64_t)blockIdx.x * WPC + warp) * RPW;
 #pragma unroll 1
-  for (int r = 0; r < kRowsPerWarp; ++r) {
+  for (int r = 0; r < RPW; ++r) {
     const int64_t row = first + r;
     if (row >= row_end) return;
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
@@ -232,14 +233,26 @@ int launch_layer(const int32_t* rowptr, const int32_t* col, const float* w, cons
     HNM_LAUNCH_CHECK();
   }
   const int64_t rows = row_end - row_begin;
-  const int64_t per_cta = (int64_t)kWarpsPerCta * kRowsPerWarp;
-  const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);
-  if (grid > 0) {
-    spmm_rows_kernel<D, WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-        rowptr, col, w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
-        num_heavy > 0 ? heavy_threshold : INT32_MAX);
-    HNM_LAUNCH_CHECK();
+  static const int variant = getenv("HNM_SPMM_VARIANT") ? atoi(getenv("HNM_SPMM_VARIANT")) : 0;
+  const int32_t thr = num_heavy > 0 ? heavy_threshold : INT32_MAX;
+#define HNM_ROWS(WPC, RPW)                                                                                   \
+  {                                                                                                          \
+    const int64_t per_cta = (int64_t)(WPC) * (RPW);                                                          \
+    const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);                                        \
+    if (grid > 0)                                                                                            \
+      spmm_rows_kernel<D, WEIGHTED, WPC, RPW><<<grid, (WPC)*32, 0, stream>>>(rowptr, col, w, dis, xs_in, xs_out, acc, \
+                                                                             alpha, row_begin, row_end, thr); \
   }
+  switch (variant) {
+    // small CTAs retire (and free their warp slots) at a finer grain: 2 warps x 4 rows measured best
+    // at the H&M shape (6.28 ms / 3 layers vs 7.32 ms for 8 x 4; profiles/r1_spmm_notes.md)
+    case 1: HNM_ROWS(4, 4); break;
+    case 2: HNM_ROWS(8, 4); break;
+    case 3: HNM_ROWS(4, 1); break;
+    default: HNM_ROWS(2, 4); break;
+  }
+#undef HNM_ROWS
+  HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
 

@@ -68,8 +68,24 @@ class Collectives:
     def allgather_rows(self, buf: torch.Tensor, ranges: Sequence[Tuple[int, int]]) -> None:
         """Every rank has written buf[ranges[rank]]; make all ranges valid on all ranks (in place)."""
         views = [buf[a:b] for a, b in ranges]
-        if self.nccl:
-            dist.all_gather(views, views[self.rank], group=self.group)      # uneven sizes are supported on NCCL
+        sizes = {v.shape[0] for v in views}
+        contiguous = all(ranges[i][1] == ranges[i + 1][0] for i in range(len(ranges) - 1))
+        if len(sizes) == 1 and contiguous and self.world > 1:
+            # equal slices laid out back to back: one in-place all-gather, no staging copies
+            dist.all_gather_into_tensor(buf[ranges[0][0]:ranges[-1][1]], views[self.rank], group=self.group)
+        elif self.nccl:
+            # uneven slices: every rank sends its slice to every peer, coalesced into one NCCL group
+            ops = []
+            for peer in range(self.world):
+                if peer == self.rank:
+                    continue
+                gp = dist.get_global_rank(self.group, peer) if self.group else peer
+                if views[self.rank].numel():
+                    ops.append(dist.P2POp(dist.isend, views[self.rank], gp, group=self.group))
+                if views[peer].numel():
+                    ops.append(dist.P2POp(dist.irecv, views[peer], gp, group=self.group))
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
         else:
             for src, v in enumerate(views):
                 if v.numel():
@@ -253,7 +269,8 @@ def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) ->
             scorer.topk(None, model.top_k)
             for k2 in fused:
                 fused[k2] += scorer.stage_ms.get(k2, 0.0) / steps
-            uncert = scorer.last_stats.get("uncertified", 0)
+            uncert = dict(scorer.last_stats)
     out.update({"fused_ms": fused["fused"], "rescore_ms": fused["rescore"], "pack_users_ms": fused["pack"],
-                "fallback_ms": fused["fallback"], "uncertified_users": uncert})
+                "fallback_ms": fused["fallback"], "uncertified_users": uncert.get("uncertified", 0),
+                "scorer_stats": uncert})
     return out

@@ -72,7 +72,13 @@ class FusedScorer:
 
     def topk(self, user_ids: Optional[torch.Tensor], k: int, filter_items: Optional[Dict[int, set]] = None,
              fallback: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
-        """ids [B,k] int64 (global item indices), scores [B,k] fp64; canonical (score desc, id asc)."""
+        """ids [B,k] int64 (global item indices), scores [B,k] fp64; canonical (score desc, id asc).
+
+        Three tiers, each only for the users the previous one could not certify:
+        1. tensor-core nomination with tau tracking the (k + sel_margin)-th best score, exact rescoring;
+        2. the same with a wider margin (k + 12): near-ties between the k-th score and tau disappear;
+        3. exact fp64 brute force (hnm_topk_exact): exact ties, overflowing lists, anything else.
+        """
         dev = self.item_emb.device
         uids = engine._norm_ids(user_ids, self.user_emb.size(0), dev)
         total = uids.numel() if uids is not None else int(self.user_emb.size(0))
@@ -85,27 +91,48 @@ class FusedScorer:
                 uids = torch.arange(total, device=dev)
             excl = engine.exclusion_csr(uids, filter_items, dev)
         self._events = []
+        sel = min(32, k + self.sel_margin)
         for b0 in range(0, total, MAX_USERS_PER_LAUNCH):
             b1 = min(total, b0 + MAX_USERS_PER_LAUNCH)
-            self._launch(uids, b0, b1, k, excl, ids, sc, cert)
-        self.last_stats = {"users": total, "uncertified": 0}
+            self._launch(uids, b0, b1, k, sel, excl, ids, sc, cert)
+        self.last_stats = {"users": total, "uncertified": 0, "tier2": 0, "tier3": 0}
+        why = None
         self._mark("fallback_begin")
         if fallback and total:
-            bad = (cert == 0).nonzero().view(-1)
+            bad = (cert != 1).nonzero().view(-1)
             n_bad = int(bad.numel())
             self.last_stats["uncertified"] = n_bad
+            why = cert[bad] if (n_bad and self.profile) else None
             if n_bad:
                 bad_uids = bad if uids is None else uids[bad]
-                sub_excl = (None, None)
-                if excl[0] is not None:
-                    sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev)
-                e_ids, e_sc = engine.topk_exact(self.user_emb, self.item_emb, bad_uids, k, sub_excl,
-                                                item_begin=self.item_begin)
-                ids[bad] = e_ids
-                sc[bad] = e_sc
+                sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev) if excl[0] is not None else (None, None)
+                sel2 = min(32, k + 12)
+                if sel2 > sel:
+                    ids2 = torch.empty(n_bad, k, dtype=torch.int64, device=dev)
+                    sc2 = torch.empty(n_bad, k, dtype=torch.float64, device=dev)
+                    cert2 = torch.empty(n_bad, dtype=torch.int32, device=dev)
+                    self._launch(bad_uids, 0, n_bad, k, sel2, sub_excl, ids2, sc2, cert2, mark=False)
+                    ok2 = cert2 == 1
+                    ids[bad[ok2]] = ids2[ok2]
+                    sc[bad[ok2]] = sc2[ok2]
+                    self.last_stats["tier2"] = n_bad
+                    bad = bad[~ok2]
+                    bad_uids = bad_uids[~ok2]
+                    if bad.numel() and excl[0] is not None:
+                        sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev)
+                if bad.numel():
+                    self.last_stats["tier3"] = int(bad.numel())
+                    e_ids, e_sc = engine.topk_exact(self.user_emb, self.item_emb, bad_uids, k, sub_excl,
+                                                    item_begin=self.item_begin)
+                    ids[bad] = e_ids
+                    sc[bad] = e_sc
         self._mark("fallback_end")
         if self.profile:
             torch.cuda.synchronize(dev)
+            if fallback and total and why is not None:
+                self.last_stats.update({"overflow": int((why & 2).ne(0).sum()), "many_groups": int((why & 4).ne(0).sum()),
+                                        "few_contenders": int((why & 8).ne(0).sum()),
+                                        "many_contenders": int((why & 16).ne(0).sum())})
             ms: Dict[str, float] = {}
             for (n0, e0), (n1, e1) in zip(self._events[:-1], self._events[1:]):
                 if n0.endswith("_begin") and n1 == n0[:-6] + "_end":
@@ -119,14 +146,15 @@ class FusedScorer:
             ev.record()
             self._events.append((name, ev))
 
-    def _launch(self, uids, b0, b1, k, excl, ids, sc, cert) -> None:
+    def _launch(self, uids, b0, b1, k, sel, excl, ids, sc, cert, mark: bool = True) -> None:
         dev = self.item_emb.device
         n = b1 - b0
         padded = (n + USER_BLOCK - 1) // USER_BLOCK * USER_BLOCK
+        note = self._mark if mark else (lambda name: None)
         with torch.cuda.device(dev):
             s = stream()
             users_f16 = torch.empty(padded, 64, dtype=torch.float16, device=dev)
-            self._mark("pack_begin")
+            note("pack_begin")
             if uids is None:
                 src = self.user_emb[b0:b1]
                 call("hnm_score_pack", ptr(src), None, n, padded, 64, None, self.user_scale, ptr(users_f16), None, s)
@@ -140,15 +168,16 @@ class FusedScorer:
             cand = torch.empty(n, CAND_CAP, 2, dtype=torch.int32, device=dev)
             count = torch.empty(n, dtype=torch.int32, device=dev)
             thresh = torch.empty(n, dtype=torch.float32, device=dev)
-            self._mark("pack_end")
-            self._mark("fused_begin")
+            note("pack_end")
+            note("fused_begin")
             call("hnm_score_topk_fused", ptr(users_f16), n, padded, ptr(self.items_f16), self.num_items,
-                 self.items_padded, min(32, k + self.sel_margin), ptr(cand), CAND_CAP, ptr(count), ptr(thresh), s)
-            self._mark("fused_end")
+                 self.items_padded, sel, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), s)
+            note("fused_end")
             ex_ptr = excl[0][b0:b1 + 1] if excl[0] is not None else None
-            self._mark("rescore_begin")
+            note("rescore_begin")
             call("hnm_rescore_topk", ptr(user_base), ptr(self.item_emb), ptr(rid), n, 64, self.item_begin,
                  self.num_items, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), self.inv_scale, self.max_item_norm,
                  ptr(self.center), ptr(ex_ptr), ptr(excl[1]), k, ptr(ids[b0:b1]), ptr(sc[b0:b1]), ptr(cert[b0:b1]), s)
-            self._mark("rescore_end")
-        self._debug = (count, thresh)
+            note("rescore_end")
+        if mark:
+            self._debug = (count, thresh)

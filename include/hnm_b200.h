@@ -186,7 +186,9 @@ HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb /* loc
                      const float* center /* the item centre used by hnm_score_pack, or NULL */,
                      const int64_t* excl_ptr, const int64_t* excl_items /* GLOBAL ids, sorted per user */,
                      int32_t k, int64_t* out_ids /* [batch,k] GLOBAL item ids */, double* out_scores /* [batch,k] */,
-                     int32_t* out_certified /* [batch] 1 = provably exact */, void* stream);
+                     int32_t* out_certified /* [batch] 1 = provably exact; else reason bits: 2 list overflow,
+                                                4 too many groups, 8 fewer than k contenders, 16 too many */,
+                     void* stream);
 
 /* ------------------------------------------------------------------------
  * Multi-GPU merge of per-shard exact top-k lists (no reference counterpart;
