@@ -11,13 +11,14 @@
 // Kernel shape (DESIGN.md "score_topk"): one persistent CTA per SM, 16 warps:
 //   warp 0   TMA producer      A: 3 user tiles x [128 x 64] fp16 per "super tile" (double buffered),
 //                              B: item tiles [128 x 64] fp16 through a 6-stage ring
-//   warp 1   MMA issuer        work item w = (item tile, user tile m), accumulator slot = w mod 4:
-//                              4 x tcgen05.mma M128 N128 K16 into TMEM columns [128 slot, 128 slot + 128)
-//   warp 2   TMEM allocator
+//   warps 1-3 MMA issuers      warp 1+m issues user tile m; work item w = (item tile, user tile m),
+//                              accumulator slot = w mod 4: 4 x tcgen05.mma M128 N128 K16 into TMEM
+//                              columns [128 slot, 128 slot + 128); warp 2 also owns the TMEM allocation
 //   warps 4..15  epilogue, 3 warpgroups; warpgroup m drains every accumulator of user tile m,
 //                thread = one user row (TMEM lane).
-// Three user tiles share each 16 KB item tile (L2 -> smem stream ~40 GB/s per SM at full rate) and the
-// fourth accumulator slot lets the MMA of (tile t+1, m) start while warpgroup m still drains (tile t, m).
+// Three user tiles share each 16 KB item tile (L2 -> smem stream ~40 GB/s per SM at full rate).  Each
+// user tile owns one accumulator, its own issuer thread and its own epilogue warpgroup: while
+// warpgroup m drains its accumulator the tensor pipe works for the other two user tiles.
 //
 // Select (per user row, all in registers): 32 bucket maxima (bucket = position of the 4-column
 // group inside an item tile).  Bucket maxima belong to distinct items, so the kth_sel-th
@@ -39,7 +40,7 @@ namespace {
 constexpr int kDim = HNM_FUSED_DIM;         // 64 fp16 = one 128-byte swizzle row
 constexpr int kUserTile = 128;              // UMMA M
 constexpr int kMU = 3;                      // user tiles per CTA
-constexpr int kSlots = 4;                   // TMEM accumulator slots (4 x 128 columns = all of TMEM)
+constexpr int kSlots = kMU;                 // one TMEM accumulator (128 columns) per user tile
 constexpr int kSuper = kUserTile * kMU;     // 384 users per CTA pass
 constexpr int kItemTile = 128;              // UMMA N
 constexpr int kStagesB = 6;
@@ -142,18 +143,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-// The registers written by tcgen05.ld are only valid after tcgen05.wait::ld; passing them through the
-// wait as in/out operands keeps the compiler from scheduling their uses above it.
-__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+// tcgen05.wait::ld: the registers written by earlier tcgen05.ld become readable.  The loaded registers
+// are threaded through the statement as in/out operands so that the compiler cannot schedule a
+// consumer above it.
+#define HNM_F8(v, o) "+f"(v[o]), "+f"(v[o + 1]), "+f"(v[o + 2]), "+f"(v[o + 3]), "+f"(v[o + 4]), "+f"(v[o + 5]), "+f"(v[o + 6]), "+f"(v[o + 7])
+__device__ __forceinline__ void tmem_ld_wait(float (&a)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
-                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
-                 "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]),
-                 "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]),
-                 "+f"(v[30]), "+f"(v[31])
+               : HNM_F8(a, 0), HNM_F8(a, 8), HNM_F8(a, 16), HNM_F8(a, 24)
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait(float (&a)[32], float (&b)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : HNM_F8(a, 0), HNM_F8(a, 8), HNM_F8(a, 16), HNM_F8(a, 24), HNM_F8(b, 0), HNM_F8(b, 8), HNM_F8(b, 16),
+                 HNM_F8(b, 24)
+               :
+               : "memory");
+}
+#undef HNM_F8
 
 // ----------------------------------------------------------------------------- select state
 struct RowState {
@@ -200,17 +207,24 @@ __device__ __forceinline__ float refresh_tau(float (&bm)[kNumBuckets], int kth) 
 // branch; the rare case is 8 predicated stores.  Earlier versions branched per group and inlined a
 // per-element scan: the kernel then spent most of its time stalled on instruction fetch
 // (profiles/r1_fused_notes.md).
-// UPDATE = false on the second visit of the seed tiles: their items already sit in the buckets and an
-// item must never be counted in two buckets (tau would stop being a lower bound).
-template <bool UPDATE>
-__device__ __forceinline__ void select32(const float (&v)[32], int chunk, int col0, RowState& st,
-                                         uint2* __restrict__ cand, int cap) {
-  float q[8];
+// The four group maxima pairs of a 32-column chunk; after this the 32 accumulator values are dead,
+// so their registers can take the next tcgen05.ld while the rest of the chunk is processed.
+__device__ __forceinline__ void group_max(const float (&v)[32], float (&q)[8]) {
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
     const float* x = v + 4 * h;
     q[h] = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
-    if (UPDATE) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
+  }
+}
+
+// UPDATE = false on the second visit of the seed tiles: their items already sit in the buckets and an
+// item must never be counted in two buckets (tau would stop being a lower bound).
+template <bool UPDATE>
+__device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col0, RowState& st,
+                                         uint2* __restrict__ cand, int cap) {
+  if (UPDATE) {
+#pragma unroll
+    for (int h = 0; h < 8; ++h) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
   }
   const float m32 = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7])));
   if (m32 > st.tau) {
@@ -226,26 +240,30 @@ __device__ __forceinline__ void select32(const float (&v)[32], int chunk, int co
   }
 }
 
+// One 128-column accumulator of one user row.  Two 32-column loads are kept in flight: chunks 2 and 3
+// are fetched while chunks 0 and 1 are processed, so one TMEM round trip per tile is exposed, not four.
 template <bool UPDATE>
 __device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& st, uint2* __restrict__ cand,
                                            int cap, uint64_t* t_empty, int lane) {
-  float va[32], vb[32];
+  float va[32], vb[32], q0[8], q1[8];
   tmem_ld32(taddr, va);
-  tmem_ld_wait(va);
   tmem_ld32(taddr + 32, vb);
-  select32<UPDATE>(va, 0, item0, st, cand, cap);
-  tmem_ld_wait(vb);
+  tmem_ld_wait(va, vb);
+  group_max(va, q0);
   tmem_ld32(taddr + 64, va);
-  select32<UPDATE>(vb, 1, item0 + 32, st, cand, cap);
-  tmem_ld_wait(va);
+  group_max(vb, q1);
   tmem_ld32(taddr + 96, vb);
-  select32<UPDATE>(va, 2, item0 + 64, st, cand, cap);
-  tmem_ld_wait(vb);
-  // every column of this accumulator is in registers: hand the slot back to the MMA warp
+  finish32<UPDATE>(q0, 0, item0, st, cand, cap);
+  finish32<UPDATE>(q1, 1, item0 + 32, st, cand, cap);
+  tmem_ld_wait(va, vb);
+  // every column of this accumulator is in registers: hand it back to its MMA issuer
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(t_empty);
-  select32<UPDATE>(vb, 3, item0 + 96, st, cand, cap);
+  group_max(va, q0);
+  group_max(vb, q1);
+  finish32<UPDATE>(q0, 2, item0 + 64, st, cand, cap);
+  finish32<UPDATE>(q1, 3, item0 + 96, st, cand, cap);
 }
 
 // ----------------------------------------------------------------------------- the kernel
@@ -269,12 +287,15 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
   const int t_base = num_user_tiles / (int)gridDim.x, t_rem = num_user_tiles % (int)gridDim.x;
   const int t_begin = (int)blockIdx.x * t_base + min((int)blockIdx.x, t_rem);
   const int t_end = t_begin + t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
+  // every CTA sweeps the catalog from a different starting tile: otherwise all 148 SMs ask the L2 for
+  // the same 16 KB item tile at the same moment
+  const int rot = (int)(((long long)blockIdx.x * num_item_tiles) / (int)gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_users);
     tma_prefetch_desc(&map_items);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
-    for (int i = 0; i < kStagesB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], kMU); }
+    for (int i = 0; i < kStagesB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], kMU); }
     for (int i = 0; i < kSlots; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
     fence_barrier_init();
   }
@@ -306,7 +327,8 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
           tma_load_2d(smem_a + (abuf * kMU + m) * kTileBytes, &map_users, &bars->a_full[abuf], 0,
                       (t0 + m) * kUserTile);
         for (int it = 0; it < num_iters; ++it, ++g) {
-          const int tile = it < boot ? it : it - boot;
+          int tile = (it < boot ? it : it - boot) + rot;
+          if (tile >= num_item_tiles) tile -= num_item_tiles;
           const int stage = g % kStagesB;
           mbar_wait(&bars->b_empty[stage], ((g / kStagesB) & 1) ^ 1);
           mbar_expect_tx(&bars->b_full[stage], kTileBytes);
@@ -314,42 +336,46 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    // One thread runs the whole loop: tcgen05.mma / commit are single-thread instructions, and keeping
-    // the other 31 lanes out of it avoids the per-instruction elect loops the compiler otherwise emits
-    // (they made this warp, not the tensor pipe, the bottleneck: profiles/r1_fused_v1.md).
+  } else {
+    // ===================================================== MMA issuers: warp 1 + m serves user tile m
+    // tcgen05.mma holds its issuing thread for about the duration of the MMA (tools/bench_mma.cu:
+    // 73 cycles per M128 N128 K16), so with a single issuer every mbarrier wait / fence / commit adds
+    // to the tensor pipe's critical path (measured: 562 cycles per accumulator instead of 292).  Three
+    // issuing threads, one per user tile, overlap each other's bookkeeping with MMA issue.
+    const int m = warp - 1;
     if (lane == 0) {
-      uint32_t g = 0, w = 0;
+      uint32_t g = 0, uses = 0;
       int n = 0;
       const uint64_t desc_hi = umma_desc_sw128(0) & ~uint64_t(0x3FFF);
       for (int t0 = t_begin; t0 < t_end; t0 += kMU, ++n) {
         const int mc = min(kMU, t_end - t0);
+        const bool active = m < mc;
         const int abuf = n & 1;
         mbar_wait(&bars->a_full[abuf], (n >> 1) & 1);
-        const uint32_t a_base = smem_u32(smem_a + abuf * kMU * kTileBytes);
+        tc_fence_after();
+        const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(smem_a + (abuf * kMU + m) * kTileBytes) >> 4) & 0x3FFF);
         for (int it = 0; it < num_iters; ++it, ++g) {
           const int stage = g % kStagesB;
           mbar_wait(&bars->b_full[stage], (g / kStagesB) & 1);
-          tc_fence_after();
-          const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(smem_b + stage * kTileBytes) >> 4) & 0x3FFF);
-#pragma unroll
-          for (int m = 0; m < kMU; ++m) {
-            if (m >= mc) break;
-            const uint32_t slot = w % kSlots;
-            mbar_wait(&bars->t_empty[slot], ((w / kSlots) & 1) ^ 1);
+          if (active) {
+            // accumulator m belongs to user tile m alone (its use counter is `uses`), so no issuer ever
+            // has to order itself against another one
+            const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(smem_b + stage * kTileBytes) >> 4) & 0x3FFF);
+            mbar_wait(&bars->t_empty[m], (uses & 1) ^ 1);
             tc_fence_after();
-            const uint64_t a_desc = desc_hi | (uint64_t)(((a_base + m * kTileBytes) >> 4) & 0x3FFF);
-            const uint32_t d_tmem = tmem_base + slot * kItemTile;
+            const uint32_t d_tmem = tmem_base + m * kItemTile;
 #pragma unroll
             for (int k = 0; k < kDim / 16; ++k)      // +32 bytes along K = +2 in the 16-byte address field
               umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, k > 0 ? 1u : 0u);
-            umma_commit(&bars->t_full[slot]);
-            ++w;
+            umma_commit(&bars->t_full[m]);
+            umma_commit(&bars->b_empty[stage]);
+            ++uses;
+          } else {
+            mbar_arrive(&bars->b_empty[stage]);       // keep the stage's arrival count at kMU
           }
-          umma_commit(&bars->b_empty[stage]);
         }
-        umma_commit(&bars->a_empty[abuf]);
+        if (active) umma_commit(&bars->a_empty[abuf]);
+        else mbar_arrive(&bars->a_empty[abuf]);
       }
     }
   }
@@ -359,10 +385,12 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     const int m = (warp - 4) >> 2;
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t w_base = 0;
+    uint32_t uses = 0;
+    const uint32_t taddr = lane_base + m * kItemTile;
+    uint64_t* t_empty = &bars->t_empty[m];
     for (int t0 = t_begin; t0 < t_end; t0 += kMU) {
       const int mc = min(kMU, t_end - t0);
-      if (m >= mc) { w_base += (uint32_t)(num_iters * mc); continue; }     // short last pass: this warpgroup rests
+      if (m >= mc) continue;                                                // short last pass: this warpgroup rests
       const int row = (t0 + m) * kUserTile + q * 32 + lane;
       uint2* my_cand = cand + (size_t)(row < num_users ? row : 0) * cap;
       const int my_cap = row < num_users ? cap : 0;      // padded rows count but never store
@@ -373,19 +401,17 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       for (int i = 0; i < kNumBuckets; ++i) rs.bm[i] = -INFINITY;
       int next_refresh = boot;
       for (int it = 0; it < num_iters; ++it) {
-        const int tile = it < boot ? it : it - boot;
+        int tile = (it < boot ? it : it - boot) + rot;
+        if (tile >= num_item_tiles) tile -= num_item_tiles;
         if (it == next_refresh && mode == 0) {
           // it == boot: the seed pass is over, collecting starts (again from tile 0)
           rs.tau = refresh_tau(rs.bm, kth_sel);
           const int seen = max(boot, it - boot);         // item tiles behind the current bucket maxima
           next_refresh = it + max(2, seen / 8);
         }
-        const uint32_t w = w_base + (uint32_t)(it * mc + m);
-        const uint32_t slot = w % kSlots;
-        mbar_wait(&bars->t_full[slot], (w / kSlots) & 1);
+        mbar_wait(&bars->t_full[m], uses & 1);
+        ++uses;
         tc_fence_after();
-        const uint32_t taddr = lane_base + slot * kItemTile;
-        uint64_t* t_empty = &bars->t_empty[slot];
         if (mode == 1 || mode == 3 || mode == 4) {   // debug: drain only / handshake only / one load
           float va[32];
           float acc = 0.f;
@@ -401,7 +427,6 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
           drain_tile<true>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
         }
       }
-      w_base += (uint32_t)(num_iters * mc);
       if (mode == 0) rs.tau = refresh_tau(rs.bm, kth_sel);
       if (row < num_users) {
         cand_count[row] = rs.cnt;
