@@ -22,6 +22,7 @@ CAND_CAP = 256
 K_MAX = 16
 SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maximum
 MAX_USERS_PER_LAUNCH = 1 << 21
+TIER2_MIN_USERS = 384
 
 
 def _pow2_scale(absmax: float) -> float:
@@ -107,7 +108,9 @@ class FusedScorer:
                 bad_uids = bad if uids is None else uids[bad]
                 sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev) if excl[0] is not None else (None, None)
                 sel2 = min(32, k + 12)
-                if sel2 > sel:
+                # a second tensor-core pass pays off only when it fills a good part of the machine;
+                # a handful of users go straight to the exact kernel (which splits the catalog over CTAs)
+                if sel2 > sel and n_bad >= TIER2_MIN_USERS:
                     ids2 = torch.empty(n_bad, k, dtype=torch.int64, device=dev)
                     sc2 = torch.empty(n_bad, k, dtype=torch.float64, device=dev)
                     cert2 = torch.empty(n_bad, dtype=torch.int32, device=dev)
