@@ -31,7 +31,7 @@ _SIGNATURES = {
     "hnm_graph_build_workspace_bytes": (SZ, [I64, I64, C.c_int]),
     "hnm_graph_build": (C.c_int, [P, P, P, I64, I64, P, P, P, P, I32, P, P, P, SZ, P]),
     "hnm_lightgcn_prescale": (C.c_int, [P, P, F32, P, P, I64, I32, P]),
-    "hnm_lightgcn_layer": (C.c_int, [P, P, P, P, P, P, P, F32, I64, I32, I64, I64, P, I32, I32, P]),
+    "hnm_lightgcn_layer": (C.c_int, [P, P, P, P, P, P, P, F32, I64, I32, I64, I64, P, I32, I32, I32, P]),
     "hnm_pair_scores": (C.c_int, [P, P, P, P, I64, I32, I64, I64, P, P]),
     "hnm_score_all_items": (C.c_int, [P, P, P, I64, I64, I32, P, P]),
     "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, I32, P, P, P]),
@@ -94,7 +94,7 @@ def call(fn: str, *args) -> None:
     check(fn, getattr(load(), fn)(*args))
     n = _LAUNCHES_PER_CALL.get(fn, 1)
     if fn == "hnm_lightgcn_layer" and args[13]:
-        n = 2                                     # whole-CTA pass over the long rows + warp-per-row pass
+        n = 2 + (1 if args[14] else 0)            # cluster pass + whole-CTA pass over the long rows + warp-per-row pass
     LAUNCHES += n
 
 

@@ -7,9 +7,10 @@
 // given edge_weight=None) nor a per-edge dis[col] gather.  HBM-bound integer/gather work:
 // one warp per row, D/4 lanes x 128-bit loads per embedding row, several rows in flight per
 // lane, column indices read coalesced and broadcast by shuffle.  Rows longer than
-// `heavy_threshold` are summed by a whole CTA in a fixed order (deterministic).
+// `heavy_threshold` are summed by a cluster of 8 CTAs in a fixed order (deterministic).
 #include <algorithm>
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace {
@@ -17,6 +18,8 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 constexpr int kRowsPerWarp = 4;
 constexpr int kHeavyThreads = 512;
+constexpr int kHugeThreads = 256;
+constexpr int kHeavyCluster = 8;
 
 template <int D>
 struct Shape {
@@ -132,6 +135,8 @@ spmm_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   }
 }
 
+// Long rows (more than heavy_threshold entries): one 512-thread CTA per row, warps take contiguous
+// 32-aligned chunks (coalesced col[] reads) and the partial sums are added in warp order.
 template <int D, bool WEIGHTED>
 __global__ void __launch_bounds__(kHeavyThreads)
 spmm_heavy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
@@ -146,7 +151,6 @@ spmm_heavy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-  // contiguous 32-aligned chunk per warp keeps the col[] reads coalesced
   const int per = ((end - beg + NW - 1) / NW + 31) & ~31;
   const int b = min(end, beg + warp * per), e = min(end, b + per);
   float4 acc[S::VEC];
@@ -163,6 +167,58 @@ spmm_heavy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     const size_t off = (size_t)row * D + (size_t)threadIdx.x * 4;
     row_epilogue(s, __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off);
   }
+}
+
+// Very long rows (more than HNM_HUGE_ROW entries; popular items reach ~45 k at the H&M shape): one
+// thread-block CLUSTER of kHeavyCluster CTAs per row.  Every CTA sums a contiguous slice, CTA 0 then adds
+// the slices in rank order through distributed shared memory (fixed order: deterministic).  Without it
+// the single longest row is the critical path of a layer once the work is split over 8 GPUs.
+template <int D, bool WEIGHTED>
+__global__ void __cluster_dims__(kHeavyCluster, 1, 1) __launch_bounds__(kHugeThreads)
+spmm_huge_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+                  const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
+                  float* __restrict__ accbuf, float alpha, const int32_t* __restrict__ heavy_rows,
+                  int64_t row_begin, int64_t row_end) {
+  using S = Shape<D>;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int NW = kHugeThreads / 32;
+  __shared__ float4 part[NW][D / 4];
+  __shared__ float4 cta_sum[D / 4];
+  const unsigned crank = cluster.block_rank();
+  const int64_t row = heavy_rows[blockIdx.x / kHeavyCluster];
+  if (row < row_begin || row >= row_end) return;          // uniform over the whole cluster
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  constexpr int NWT = NW * kHeavyCluster;                  // warps working on this row
+  const int per = ((end - beg + NWT - 1) / NWT + 31) & ~31;
+  const int gw = (int)crank * NW + warp;
+  const int b = min(end, beg + gw * per), e = min(end, b + per);
+  float4 acc[S::VEC];
+  warp_gather<D, WEIGHTED>(col, w, xs_in, b, e, lane, acc);
+  if (lane < S::LPR) {
+#pragma unroll
+    for (int t = 0; t < S::VEC; ++t) part[warp][t * S::LPR + lane] = acc[t];
+  }
+  __syncthreads();
+  if (threadIdx.x < D / 4) {
+    float4 s = part[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < NW; ++k) add4(s, part[k][threadIdx.x]);
+    cta_sum[threadIdx.x] = s;
+  }
+  cluster.sync();
+  if (crank == 0 && threadIdx.x < D / 4) {
+    float4 s = cta_sum[threadIdx.x];
+    for (unsigned r = 1; r < kHeavyCluster; ++r) {
+      const float4* remote = cluster.map_shared_rank(cta_sum, r);
+      add4(s, remote[threadIdx.x]);
+    }
+    const size_t off = (size_t)row * D + (size_t)threadIdx.x * 4;
+    row_epilogue(s, __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off);
+  }
+  cluster.sync();                                          // keep every CTA's shared memory alive until read
 }
 
 // Any dimension: one warp per row, lanes stride over the columns, edges in order.
@@ -226,10 +282,17 @@ __global__ void prescale_kernel_v4(const float4* __restrict__ e0, const float* _
 template <int D, bool WEIGHTED>
 int launch_layer(const int32_t* rowptr, const int32_t* col, const float* w, const float* dis, const float* xs_in,
                  float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
-                 const int32_t* heavy_rows, int32_t num_heavy, int32_t heavy_threshold, cudaStream_t stream) {
-  if (num_heavy > 0) {
-    spmm_heavy_kernel<D, WEIGHTED><<<num_heavy, kHeavyThreads, 0, stream>>>(rowptr, col, w, dis, xs_in, xs_out, acc,
-                                                                         alpha, heavy_rows, row_begin, row_end);
+                 const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge, int32_t heavy_threshold,
+                 cudaStream_t stream) {
+  if (num_huge > 0) {
+    spmm_huge_kernel<D, WEIGHTED><<<num_huge * kHeavyCluster, kHugeThreads, 0, stream>>>(rowptr, col, w, dis, xs_in, xs_out,
+                                                                                      acc, alpha, heavy_rows, row_begin,
+                                                                                      row_end);
+    HNM_LAUNCH_CHECK();
+  }
+  if (num_heavy > num_huge) {
+    spmm_heavy_kernel<D, WEIGHTED><<<num_heavy - num_huge, kHeavyThreads, 0, stream>>>(
+        rowptr, col, w, dis, xs_in, xs_out, acc, alpha, heavy_rows + num_huge, row_begin, row_end);
     HNM_LAUNCH_CHECK();
   }
   const int64_t rows = row_end - row_begin;
@@ -259,11 +322,12 @@ int launch_layer(const int32_t* rowptr, const int32_t* col, const float* w, cons
 template <bool WEIGHTED>
 int dispatch_layer(int dim, const int32_t* rowptr, const int32_t* col, const float* w, const float* dis,
                    const float* xs_in, float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
-                   const int32_t* heavy_rows, int32_t num_heavy, int32_t heavy_threshold, cudaStream_t stream) {
+                   const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge, int32_t heavy_threshold,
+                   cudaStream_t stream) {
 #define HNM_CASE(DD)                                                                                          \
   case DD:                                                                                                    \
     return launch_layer<DD, WEIGHTED>(rowptr, col, w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,   \
-                                      heavy_rows, num_heavy, heavy_threshold, stream)
+                                      heavy_rows, num_heavy, num_huge, heavy_threshold, stream)
   switch (dim) {
     HNM_CASE(8);
     HNM_CASE(16);
@@ -310,11 +374,12 @@ extern "C" int hnm_lightgcn_prescale(const float* e0, const float* dis, float al
 extern "C" int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_col, const float* csr_w,
                                   const float* dis, const float* xs_in, float* xs_out, float* acc, float alpha,
                                   int64_t num_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
-                                  const int32_t* heavy_rows, int32_t num_heavy, int32_t heavy_threshold,
-                                  void* stream_) {
+                                  const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge,
+                                  int32_t heavy_threshold, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!csr_rowptr || !csr_col || !dis || !xs_in || !acc) return HNM_E_NULL;
   if (num_heavy > 0 && !heavy_rows) return HNM_E_NULL;
+  if (num_huge < 0 || num_huge > num_heavy) return HNM_E_RANGE;
   if (num_nodes <= 0 || dim <= 0 || row_begin < 0 || row_end > num_nodes || row_begin > row_end) return HNM_E_RANGE;
   if (xs_in == xs_out) return HNM_E_RANGE;  // rows are gathered while others are written
   if (dim % 4 == 0 && !(hnm_aligned16(xs_in) && hnm_aligned16(acc) && (!xs_out || hnm_aligned16(xs_out))))
@@ -322,7 +387,7 @@ extern "C" int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_
   if (row_begin == row_end) return HNM_OK;
   if (csr_w)
     return dispatch_layer<true>(dim, csr_rowptr, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
-                                heavy_rows, num_heavy, heavy_threshold, stream);
+                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
   return dispatch_layer<false>(dim, csr_rowptr, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
-                               heavy_rows, num_heavy, heavy_threshold, stream);
+                               heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
 }

@@ -149,6 +149,8 @@ class ShardedLightGCN:
         def exchange_items(buf):
             self.coll.allgather_rows(buf, p.item_rows)
 
+        if hasattr(self.backend, "propagate_padded"):
+            return self.backend.propagate_padded(self, all_rows or self.mode != "users")
         final = self.backend.propagate(m, my_ranges, exchange,
                                        exchange_items if (self.mode == "users" and not all_rows) else exchange)
         self._scorer = None
@@ -181,6 +183,40 @@ class ShardedLightGCN:
 
 class CudaBackend:
     """The B200 kernels (default)."""
+
+    def __init__(self):
+        self._padded_key = None
+        self._padded = None
+
+    def propagate_padded(self, sharded, final_users: bool):
+        """Row-sharded propagation in the padded node layout: equal slices, in-place all-gathers."""
+        from . import engine
+        m, coll = sharded.model, sharded.coll
+        layout = engine.PaddedLayout(m.num_users, m.num_items, coll.world)
+        key = (id(m.graph), coll.world)
+        if self._padded_key != key:
+            if m.edge_index is None:
+                raise RuntimeError("Graph not set. Call set_graph() first.")
+            dev = m.embeddings.weight.device
+            ei = layout.remap_edges(m.edge_index.to(dev))
+            self._padded = engine.build_graph(ei, m.edge_weight, layout.num_nodes, dev)
+            self._padded_key = key
+        up = layout.users_padded
+
+        def xu(buf):
+            a, b = layout.user_slice(coll.rank)
+            dist.all_gather_into_tensor(buf[:up], buf[a:b], group=coll.group)
+
+        def xi(buf):
+            a, b = layout.item_slice(coll.rank)
+            dist.all_gather_into_tensor(buf[up:], buf[a:b], group=coll.group)
+
+        acc = engine.propagate_padded(self._padded, layout, m.embeddings.weight, m.alpha, m.num_layers, coll.rank,
+                                      xu, xi, final_users=final_users)
+        sharded._scorer = None
+        sharded.plan.user_slices = [layout.user_rows(r) for r in range(coll.world)]
+        sharded.plan.user_rows = sharded.plan.user_slices
+        return acc[: m.num_users], acc[up:up + m.num_items]
 
     def propagate(self, model, my_ranges, exchange, exchange_final):
         from . import engine
@@ -231,7 +267,7 @@ def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) ->
         def layer():
             for r0, r1 in ranges:
                 call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
-                     0.25, n, d, r0, r1, heavy, g.num_heavy, g.heavy_threshold, stream())
+                     0.25, n, d, r0, r1, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
         layer()
         a = ev()
         for _ in range(steps):

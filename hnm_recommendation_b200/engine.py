@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 HEAVY_THRESHOLD = 1024          # CSR rows longer than this are summed by a whole CTA
+HUGE_ROW = 8192                 # ... and rows longer than this by a cluster of 8 CTAs (HNM_HUGE_ROW)
 EXACT_K_MAX = 256               # hnm_topk_exact limit (XCAP - XT in score_exact.cu)
 FUSED_DIM = 64
 FUSED_USER_TILE = 128
@@ -33,8 +34,9 @@ class Graph:
     col: torch.Tensor             # int32 [nnz]
     w: Optional[torch.Tensor]     # fp32 [nnz] raw edge weights in CSR order, None when all ones
     dis: torch.Tensor             # fp32 [N]  deg^-1/2
-    heavy_rows: torch.Tensor      # int32 [H]
+    heavy_rows: torch.Tensor      # int32 [H], the num_huge very long rows first
     heavy_threshold: int = HEAVY_THRESHOLD
+    num_huge: int = 0             # rows with more than HUGE_ROW entries (summed by a CTA cluster)
 
     @property
     def num_heavy(self) -> int:
@@ -66,8 +68,14 @@ def build_graph(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n
     with torch.cuda.device(device):
         call("hnm_graph_build", ptr(ei[0]), ptr(ei[1]), ptr(ew), m, num_nodes, ptr(rowptr), ptr(col), ptr(w),
              ptr(dis), heavy_threshold, ptr(heavy), C.addressof(n_heavy), ptr(ws), ws_bytes, stream())
-    heavy_rows = torch.sort(heavy[: n_heavy.value]).values.contiguous()
-    return Graph(num_nodes, nnz, rowptr, col, w, dis, heavy_rows, heavy_threshold)
+    heavy_rows = torch.sort(heavy[: n_heavy.value]).values
+    num_huge = 0
+    if heavy_rows.numel():
+        idx = heavy_rows.long()
+        huge = (rowptr[idx + 1] - rowptr[idx]) > HUGE_ROW
+        num_huge = int(huge.sum())
+        heavy_rows = torch.cat([heavy_rows[huge], heavy_rows[~huge]])
+    return Graph(num_nodes, nnz, rowptr, col, w, dis, heavy_rows.contiguous(), heavy_threshold, num_huge)
 
 
 def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
@@ -101,7 +109,8 @@ def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layer
             for r0, r1 in ranges:
                 call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
                      None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, r0, r1,
-                     ptr(graph.heavy_rows) if graph.num_heavy else None, graph.num_heavy, graph.heavy_threshold, s)
+                     ptr(graph.heavy_rows) if graph.num_heavy else None, graph.num_heavy, graph.num_huge,
+                     graph.heavy_threshold, s)
             if not last:
                 if exchange is not None:
                     exchange(nxt)
@@ -210,3 +219,98 @@ def merge_topk(ids: torch.Tensor, scores: torch.Tensor) -> Tuple[torch.Tensor, t
         call("hnm_merge_topk", ptr(ids.contiguous()), ptr(scores.contiguous()), g, b, k, ptr(out_i), ptr(out_s),
              stream())
     return out_i, out_s
+
+
+# ----------------------------------------------------------------------------- padded (sharded) layout
+@dataclass
+class PaddedLayout:
+    """Node numbering used by the row-sharded propagation: the user block and the item block are each
+    padded to a multiple of the world size so that every rank owns equally sized, contiguous slices
+    (one in-place all-gather per block and layer, no staging copies).  Pad nodes are isolated."""
+    num_users: int
+    num_items: int
+    world: int
+
+    @property
+    def chunk_u(self) -> int:
+        return (self.num_users + self.world - 1) // self.world
+
+    @property
+    def chunk_i(self) -> int:
+        return (self.num_items + self.world - 1) // self.world
+
+    @property
+    def users_padded(self) -> int:
+        return self.chunk_u * self.world
+
+    @property
+    def items_padded(self) -> int:
+        return self.chunk_i * self.world
+
+    @property
+    def num_nodes(self) -> int:
+        return self.users_padded + self.items_padded
+
+    def user_slice(self, r: int) -> Tuple[int, int]:          # communication slice (pad rows included)
+        return r * self.chunk_u, (r + 1) * self.chunk_u
+
+    def item_slice(self, r: int) -> Tuple[int, int]:
+        return self.users_padded + r * self.chunk_i, self.users_padded + (r + 1) * self.chunk_i
+
+    def user_rows(self, r: int) -> Tuple[int, int]:           # rows rank r computes (real nodes only)
+        a, b = self.user_slice(r)
+        return min(a, self.num_users), min(b, self.num_users)
+
+    def item_rows(self, r: int) -> Tuple[int, int]:
+        a, b = self.item_slice(r)
+        hi = self.users_padded + self.num_items
+        return min(a, hi), min(b, hi)
+
+    def remap_edges(self, edge_index: torch.Tensor) -> torch.Tensor:
+        shift = self.users_padded - self.num_users
+        if shift == 0:
+            return edge_index
+        return torch.where(edge_index >= self.num_users, edge_index + shift, edge_index)
+
+
+def propagate_padded(graph: Graph, layout: PaddedLayout, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
+                     rank: int, exchange_users, exchange_items, final_users: bool = True) -> torch.Tensor:
+    """Row-sharded LightGCN.forward in the padded layout.  Returns acc [layout.num_nodes, d]; users are
+    rows [0, U), items rows [users_padded, users_padded + I).  exchange_users(buf) / exchange_items(buf)
+    all-gather the equal slices of the two blocks in place.  With final_users=False the returned user
+    rows are valid only for this rank's slice (enough for a user-sharded scorer)."""
+    _lib.require_device()
+    e0 = e0.detach().to(torch.float32).contiguous()
+    n_real, d = e0.shape
+    U, I = layout.num_users, layout.num_items
+    if n_real != U + I or graph.num_nodes != layout.num_nodes:
+        raise ValueError("layout / graph / embedding sizes disagree")
+    dev = e0.device
+    up = layout.users_padded
+    acc = torch.zeros(layout.num_nodes, d, dtype=torch.float32, device=dev)
+    xs_a = torch.zeros_like(acc)
+    xs_b = torch.zeros_like(acc) if num_layers > 1 else None
+    ranges = [layout.user_rows(rank), layout.item_rows(rank)]
+    with torch.cuda.device(dev):
+        s = stream()
+        call("hnm_lightgcn_prescale", ptr(e0[:U]), ptr(graph.dis[:U]), float(alphas[0]), ptr(xs_a[:U]), ptr(acc[:U]),
+             U, d, s)
+        call("hnm_lightgcn_prescale", ptr(e0[U:]), ptr(graph.dis[up:up + I]), float(alphas[0]), ptr(xs_a[up:up + I]),
+             ptr(acc[up:up + I]), I, d, s)
+        cur, nxt = xs_a, xs_b
+        heavy = ptr(graph.heavy_rows) if graph.num_heavy else None
+        for layer in range(1, num_layers + 1):
+            last = layer == num_layers
+            for r0, r1 in ranges:
+                if r1 > r0:
+                    call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
+                         None if last else ptr(nxt), ptr(acc), float(alphas[layer]), layout.num_nodes, d, r0, r1,
+                         heavy, graph.num_heavy, graph.num_huge, graph.heavy_threshold, s)
+            if not last:
+                exchange_users(nxt)
+                exchange_items(nxt)
+                cur, nxt = nxt, cur
+        exchange_items(acc)
+        if final_users:
+            exchange_users(acc)
+    return acc

@@ -82,16 +82,19 @@ HNM_API int hnm_graph_build(const int64_t* edge_row, const int64_t* edge_col, co
  *         e      = dis[i] * sum_{j in row i} w_ij * xs_in[col_j]      (= (A_hat E)_i, :152)
  *         xs_out[i] = dis[i] * e            (skipped when xs_out is NULL: last layer)
  *         acc[i]   += alpha * e             (:158)
- *     Rows listed in heavy_rows are summed by a whole thread block, the rest by
- *     one warp each.  Row ranges let several GPUs own disjoint row shards.
+ *     Rows listed in heavy_rows (more than heavy_threshold entries) are summed by a whole
+ *     thread block, the first num_huge of them (the very long ones, > HNM_HUGE_ROW entries)
+ *     by a cluster of 8 thread blocks; all other rows by one warp each.  Row ranges let
+ *     several GPUs own disjoint row shards.
  * ---------------------------------------------------------------------- */
 HNM_API int hnm_lightgcn_prescale(const float* e0, const float* dis, float alpha0, float* xs, float* acc,
                           int64_t num_rows, int32_t dim, void* stream);
 HNM_API int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_col, const float* csr_w,
                        const float* dis, const float* xs_in, float* xs_out, float* acc, float alpha,
                        int64_t num_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
-                       const int32_t* heavy_rows, int32_t num_heavy, int32_t heavy_threshold,
-                       void* stream);
+                       const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge,
+                       int32_t heavy_threshold, void* stream);
+#define HNM_HUGE_ROW 8192
 
 /* ------------------------------------------------------------------------
  * LightGCN.predict                              src/models/lightgcn.py:180-184
