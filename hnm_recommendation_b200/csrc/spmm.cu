@@ -21,6 +21,16 @@ constexpr int kHeavyThreads = 512;
 constexpr int kHugeThreads = 256;
 constexpr int kHeavyCluster = 8;
 
+// Where a row's entries live: [b[row - off], e[row - off]).  The whole-row form is {rowptr, rowptr + 1, 0};
+// the user-sharded propagation passes per-rank sub-ranges of the item rows (hnm_lightgcn_partial).
+struct Seg {
+  const int32_t* b;
+  const int32_t* e;
+  int64_t off;
+  __device__ __forceinline__ int beg(int64_t row) const { return __ldg(b + (row - off)); }
+  __device__ __forceinline__ int end(int64_t row) const { return __ldg(e + (row - off)); }
+};
+
 template <int D>
 struct Shape {
   static constexpr int LPR = (D / 4 < 32) ? D / 4 : 32;  // lanes per embedding row
@@ -92,7 +102,11 @@ __device__ __forceinline__ void warp_gather(const int32_t* __restrict__ col, con
 
 // e = dis_i * sum;  xs_out = dis_i * e;  acc += alpha * e   (lightgcn.py:152,158)
 __device__ __forceinline__ void row_epilogue(float4 s, float di, float alpha, float* __restrict__ xs_out_p,
-                                             float* __restrict__ acc_p) {
+                                             float* __restrict__ acc_p, int partial = 0) {
+  if (partial) {          // raw neighbour sum of a sub-range: normalisation happens after the all-reduce
+    *reinterpret_cast<float4*>(xs_out_p) = s;
+    return;
+  }
   float4 e = make_float4(__fmul_rn(di, s.x), __fmul_rn(di, s.y), __fmul_rn(di, s.z), __fmul_rn(di, s.w));
   if (xs_out_p) {
     float4 x = make_float4(__fmul_rn(di, e.x), __fmul_rn(di, e.y), __fmul_rn(di, e.z), __fmul_rn(di, e.w));
@@ -108,7 +122,7 @@ __device__ __forceinline__ void row_epilogue(float4 s, float di, float alpha, fl
 
 template <int D, bool WEIGHTED, int WPC, int RPW>
 __global__ void __launch_bounds__(WPC * 32)
-spmm_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+spmm_rows_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const float* __restrict__ w,
                  const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
                  float* __restrict__ accbuf, float alpha, int64_t row_begin, int64_t row_end,
                  int32_t heavy_threshold) {
@@ -120,16 +134,17 @@ spmm_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   for (int r = 0; r < RPW; ++r) {
     const int64_t row = first + r;
     if (row >= row_end) return;
-    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const int beg = seg.beg(row), end = seg.end(row);
     if (end - beg > heavy_threshold) continue;  // summed by spmm_heavy_kernel
     float4 acc[S::VEC];
     warp_gather<D, WEIGHTED>(col, w, xs_in, beg, end, lane, acc);
     if (lane < S::LPR) {
-      const float di = __ldg(dis + row);
+      const float di = partial ? 1.f : __ldg(dis + row);
+      const size_t orow = partial ? (size_t)(row - seg.off) : (size_t)row;
 #pragma unroll
       for (int t = 0; t < S::VEC; ++t) {
-        const size_t off = (size_t)row * D + (size_t)(t * S::LPR + lane) * 4;
-        row_epilogue(acc[t], di, alpha, xs_out ? xs_out + off : nullptr, accbuf + off);
+        const size_t off = orow * D + (size_t)(t * S::LPR + lane) * 4;
+        row_epilogue(acc[t], di, alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
       }
     }
   }
@@ -139,7 +154,7 @@ spmm_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
 // 32-aligned chunks (coalesced col[] reads) and the partial sums are added in warp order.
 template <int D, bool WEIGHTED>
 __global__ void __launch_bounds__(kHeavyThreads)
-spmm_heavy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+spmm_heavy_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const float* __restrict__ w,
                   const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
                   float* __restrict__ accbuf, float alpha, const int32_t* __restrict__ heavy_rows,
                   int64_t row_begin, int64_t row_end) {
@@ -150,7 +165,7 @@ spmm_heavy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   if (row < row_begin || row >= row_end) return;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const int beg = seg.beg(row), end = seg.end(row);
   const int per = ((end - beg + NW - 1) / NW + 31) & ~31;
   const int b = min(end, beg + warp * per), e = min(end, b + per);
   float4 acc[S::VEC];
@@ -164,8 +179,8 @@ spmm_heavy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     float4 s = part[0][threadIdx.x];
 #pragma unroll
     for (int k = 1; k < NW; ++k) add4(s, part[k][threadIdx.x]);
-    const size_t off = (size_t)row * D + (size_t)threadIdx.x * 4;
-    row_epilogue(s, __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off);
+    const size_t off = (partial ? (size_t)(row - seg.off) : (size_t)row) * D + (size_t)threadIdx.x * 4;
+    row_epilogue(s, partial ? 1.f : __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
   }
 }
 
@@ -175,7 +190,7 @@ spmm_heavy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
 // the single longest row is the critical path of a layer once the work is split over 8 GPUs.
 template <int D, bool WEIGHTED>
 __global__ void __cluster_dims__(kHeavyCluster, 1, 1) __launch_bounds__(kHugeThreads)
-spmm_huge_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+spmm_huge_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const float* __restrict__ w,
                   const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
                   float* __restrict__ accbuf, float alpha, const int32_t* __restrict__ heavy_rows,
                   int64_t row_begin, int64_t row_end) {
@@ -190,7 +205,7 @@ spmm_huge_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   if (row < row_begin || row >= row_end) return;          // uniform over the whole cluster
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const int beg = seg.beg(row), end = seg.end(row);
   constexpr int NWT = NW * kHeavyCluster;                  // warps working on this row
   const int per = ((end - beg + NWT - 1) / NWT + 31) & ~31;
   const int gw = (int)crank * NW + warp;
@@ -215,8 +230,8 @@ spmm_huge_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
       const float4* remote = cluster.map_shared_rank(cta_sum, r);
       add4(s, remote[threadIdx.x]);
     }
-    const size_t off = (size_t)row * D + (size_t)threadIdx.x * 4;
-    row_epilogue(s, __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off);
+    const size_t off = (partial ? (size_t)(row - seg.off) : (size_t)row) * D + (size_t)threadIdx.x * 4;
+    row_epilogue(s, partial ? 1.f : __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
   }
   cluster.sync();                                          // keep every CTA's shared memory alive until read
 }
@@ -224,14 +239,14 @@ spmm_huge_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
 // Any dimension: one warp per row, lanes stride over the columns, edges in order.
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-spmm_generic_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+spmm_generic_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const float* __restrict__ w,
                     const float* __restrict__ dis, const float* __restrict__ xs_in, float* __restrict__ xs_out,
                     float* __restrict__ accbuf, float alpha, int dim, int64_t row_begin, int64_t row_end) {
   const int lane = threadIdx.x & 31;
   const int64_t row = row_begin + (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= row_end) return;
-  const int beg = rowptr[row], end = rowptr[row + 1];
-  const float di = dis[row];
+  const int beg = seg.beg(row), end = seg.end(row);
+  const float di = partial ? 1.f : dis[row];
   for (int c0 = 0; c0 < dim; c0 += 32 * 8) {
     float s[8];
 #pragma unroll
@@ -249,6 +264,10 @@ spmm_generic_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
     for (int t = 0; t < 8; ++t) {
       const int c = c0 + t * 32 + lane;
       if (c < dim) {
+        if (partial) {
+          xs_out[(size_t)(row - seg.off) * dim + c] = s[t];
+          continue;
+        }
         const size_t off = (size_t)row * dim + c;
         const float e = __fmul_rn(di, s[t]);
         if (xs_out) xs_out[off] = __fmul_rn(di, e);
@@ -280,19 +299,19 @@ __global__ void prescale_kernel_v4(const float4* __restrict__ e0, const float* _
 }
 
 template <int D, bool WEIGHTED>
-int launch_layer(const int32_t* rowptr, const int32_t* col, const float* w, const float* dis, const float* xs_in,
+int launch_layer(Seg seg, int partial, const int32_t* col, const float* w, const float* dis, const float* xs_in,
                  float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
                  const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge, int32_t heavy_threshold,
                  cudaStream_t stream) {
   if (num_huge > 0) {
-    spmm_huge_kernel<D, WEIGHTED><<<num_huge * kHeavyCluster, kHugeThreads, 0, stream>>>(rowptr, col, w, dis, xs_in, xs_out,
+    spmm_huge_kernel<D, WEIGHTED><<<num_huge * kHeavyCluster, kHugeThreads, 0, stream>>>(seg, partial, col, w, dis, xs_in, xs_out,
                                                                                       acc, alpha, heavy_rows, row_begin,
                                                                                       row_end);
     HNM_LAUNCH_CHECK();
   }
   if (num_heavy > num_huge) {
     spmm_heavy_kernel<D, WEIGHTED><<<num_heavy - num_huge, kHeavyThreads, 0, stream>>>(
-        rowptr, col, w, dis, xs_in, xs_out, acc, alpha, heavy_rows + num_huge, row_begin, row_end);
+        seg, partial, col, w, dis, xs_in, xs_out, acc, alpha, heavy_rows + num_huge, row_begin, row_end);
     HNM_LAUNCH_CHECK();
   }
   const int64_t rows = row_end - row_begin;
@@ -303,7 +322,7 @@ int launch_layer(const int32_t* rowptr, const int32_t* col, const float* w, cons
     const int64_t per_cta = (int64_t)(WPC) * (RPW);                                                          \
     const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);                                        \
     if (grid > 0)                                                                                            \
-      spmm_rows_kernel<D, WEIGHTED, WPC, RPW><<<grid, (WPC)*32, 0, stream>>>(rowptr, col, w, dis, xs_in, xs_out, acc, \
+      spmm_rows_kernel<D, WEIGHTED, WPC, RPW><<<grid, (WPC)*32, 0, stream>>>(seg, partial, col, w, dis, xs_in, xs_out, acc, \
                                                                              alpha, row_begin, row_end, thr); \
   }
   switch (variant) {
@@ -320,13 +339,13 @@ int launch_layer(const int32_t* rowptr, const int32_t* col, const float* w, cons
 }
 
 template <bool WEIGHTED>
-int dispatch_layer(int dim, const int32_t* rowptr, const int32_t* col, const float* w, const float* dis,
+int dispatch_layer(int dim, Seg seg, int partial, const int32_t* col, const float* w, const float* dis,
                    const float* xs_in, float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
                    const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge, int32_t heavy_threshold,
                    cudaStream_t stream) {
 #define HNM_CASE(DD)                                                                                          \
   case DD:                                                                                                    \
-    return launch_layer<DD, WEIGHTED>(rowptr, col, w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,   \
+    return launch_layer<DD, WEIGHTED>(seg, partial, col, w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,   \
                                       heavy_rows, num_heavy, num_huge, heavy_threshold, stream)
   switch (dim) {
     HNM_CASE(8);
@@ -342,7 +361,7 @@ int dispatch_layer(int dim, const int32_t* rowptr, const int32_t* col, const flo
   const int64_t rows = row_end - row_begin;
   const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   if (grid > 0) {
-    spmm_generic_kernel<WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(rowptr, col, w, dis, xs_in, xs_out, acc,
+    spmm_generic_kernel<WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(seg, partial, col, w, dis, xs_in, xs_out, acc,
                                                                        alpha, dim, row_begin, row_end);
     HNM_LAUNCH_CHECK();
   }
@@ -386,8 +405,68 @@ extern "C" int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_
     return HNM_E_ALIGN;
   if (row_begin == row_end) return HNM_OK;
   if (csr_w)
-    return dispatch_layer<true>(dim, csr_rowptr, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+    return dispatch_layer<true>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0}, 0, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
                                 heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
-  return dispatch_layer<false>(dim, csr_rowptr, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+  return dispatch_layer<false>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0}, 0, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
+}
+
+
+namespace {
+__global__ void finish_kernel(const float4* __restrict__ partial, const float4* __restrict__ xs_in,
+                              const float* __restrict__ dis, float alpha, float4* __restrict__ xs_out,
+                              float4* __restrict__ acc, int64_t row_begin, int64_t total4, int dim4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = row_begin * dim4 + i;               // position in the full [N, dim/4] tables
+    const float di = __ldg(dis + row_begin + i / dim4);
+    float4 s = partial[i];
+    const float4 self = xs_in[g];                          // the self loop (weight 1, lightgcn.py:127-132)
+    s.x += self.x; s.y += self.y; s.z += self.z; s.w += self.w;
+    float4 e = make_float4(__fmul_rn(di, s.x), __fmul_rn(di, s.y), __fmul_rn(di, s.z), __fmul_rn(di, s.w));
+    if (xs_out) xs_out[g] = make_float4(__fmul_rn(di, e.x), __fmul_rn(di, e.y), __fmul_rn(di, e.z), __fmul_rn(di, e.w));
+    float4 a = acc[g];
+    a.x = __fadd_rn(a.x, __fmul_rn(alpha, e.x));
+    a.y = __fadd_rn(a.y, __fmul_rn(alpha, e.y));
+    a.z = __fadd_rn(a.z, __fmul_rn(alpha, e.z));
+    a.w = __fadd_rn(a.w, __fmul_rn(alpha, e.w));
+    acc[g] = a;
+  }
+}
+}  // namespace
+
+extern "C" int hnm_lightgcn_partial(const int32_t* seg_begin, const int32_t* seg_end, const int32_t* csr_col,
+                                    const float* csr_w, const float* xs_in, float* partial, int32_t dim,
+                                    int64_t row_begin, int64_t row_end, const int32_t* heavy_rows, int32_t num_heavy,
+                                    int32_t num_huge, int32_t heavy_threshold, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!seg_begin || !seg_end || !csr_col || !xs_in || !partial) return HNM_E_NULL;
+  if (num_heavy > 0 && !heavy_rows) return HNM_E_NULL;
+  if (num_huge < 0 || num_huge > num_heavy) return HNM_E_RANGE;
+  if (dim <= 0 || row_begin < 0 || row_begin > row_end) return HNM_E_RANGE;
+  if (dim % 4 == 0 && !(hnm_aligned16(xs_in) && hnm_aligned16(partial))) return HNM_E_ALIGN;
+  if (row_begin == row_end) return HNM_OK;
+  const Seg seg{seg_begin, seg_end, row_begin};
+  if (csr_w)
+    return dispatch_layer<true>(dim, seg, 1, csr_col, csr_w, nullptr, xs_in, partial, nullptr, 0.f, row_begin, row_end,
+                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
+  return dispatch_layer<false>(dim, seg, 1, csr_col, csr_w, nullptr, xs_in, partial, nullptr, 0.f, row_begin, row_end,
+                               heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
+}
+
+extern "C" int hnm_lightgcn_finish(const float* partial, const float* xs_in, const float* dis, float alpha,
+                                   float* xs_out, float* acc, int64_t row_begin, int64_t num_rows, int32_t dim,
+                                   void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!partial || !xs_in || !dis || !acc) return HNM_E_NULL;
+  if (num_rows < 0 || row_begin < 0 || dim <= 0 || dim % 4 != 0) return HNM_E_RANGE;
+  if (!(hnm_aligned16(partial) && hnm_aligned16(xs_in) && hnm_aligned16(acc) && (!xs_out || hnm_aligned16(xs_out))))
+    return HNM_E_ALIGN;
+  if (num_rows == 0) return HNM_OK;
+  const int64_t total4 = num_rows * (dim / 4);
+  const int T = 256;
+  const unsigned grid = (unsigned)std::min<int64_t>((total4 + T - 1) / T, (int64_t)hnm_num_sms() * 16);
+  finish_kernel<<<grid, T, 0, stream>>>((const float4*)partial, (const float4*)xs_in, dis, alpha, (float4*)xs_out,
+                                        (float4*)acc, row_begin, total4, dim / 4);
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
 }

@@ -3,10 +3,10 @@
 No counterpart in the reference (single device, scripts/train.py:233-234); the partitioning is the
 one BASELINE.json's north_star prescribes:
 
-  * propagation: rows of A_hat are sharded (each rank owns one equal slice of the user rows and one
-    of the item rows, so every rank gets the same mix of short user rows and long item rows); after
-    every layer the freshly written row slices are all-gathered so the next layer can gather from
-    all rows;
+  * propagation: the USERS are partitioned.  A rank computes its own user rows (they gather from the
+    item block, which every rank holds) and, for every item row, the partial neighbour sum over its own
+    users; one all-reduce per layer adds the partial sums (27 MB at the H&M shape -- an all-gather of
+    the user block would move 351 MB), then every rank normalises the item block locally;
   * scoring, mode "items" (north_star): the item catalog is sharded; each rank runs the fused
     score/select + exact rescoring against its item shard for ALL users, the per-shard exact top-k
     lists are exchanged (all-to-all by user slice), merged by (score desc, item id asc), and the
@@ -149,8 +149,8 @@ class ShardedLightGCN:
         def exchange_items(buf):
             self.coll.allgather_rows(buf, p.item_rows)
 
-        if hasattr(self.backend, "propagate_padded"):
-            return self.backend.propagate_padded(self, all_rows or self.mode != "users")
+        if hasattr(self.backend, "propagate_sharded"):
+            return self.backend.propagate_sharded(self, all_rows or self.mode != "users")
         final = self.backend.propagate(m, my_ranges, exchange,
                                        exchange_items if (self.mode == "users" and not all_rows) else exchange)
         self._scorer = None
@@ -185,38 +185,30 @@ class CudaBackend:
     """The B200 kernels (default)."""
 
     def __init__(self):
-        self._padded_key = None
-        self._padded = None
+        self._shard_key = None
+        self._shard = None
 
-    def propagate_padded(self, sharded, final_users: bool):
-        """Row-sharded propagation in the padded node layout: equal slices, in-place all-gathers."""
+    def propagate_sharded(self, sharded, final_users: bool):
+        """Users partitioned over the ranks; per layer one all-reduce of the item block (engine.propagate_user_sharded)."""
         from . import engine
-        m, coll = sharded.model, sharded.coll
-        layout = engine.PaddedLayout(m.num_users, m.num_items, coll.world)
-        key = (id(m.graph), coll.world)
-        if self._padded_key != key:
-            if m.edge_index is None:
+        m, coll, plan = sharded.model, sharded.coll, sharded.plan
+        key = (id(m.graph), coll.world, coll.rank)
+        if self._shard_key != key:
+            if m.graph is None:
                 raise RuntimeError("Graph not set. Call set_graph() first.")
-            dev = m.embeddings.weight.device
-            ei = layout.remap_edges(m.edge_index.to(dev))
-            self._padded = engine.build_graph(ei, m.edge_weight, layout.num_nodes, dev)
-            self._padded_key = key
-        up = layout.users_padded
+            u0, u1 = plan.user_rows[plan.rank]
+            self._shard = engine.make_user_shard(m.graph, m.num_users, m.num_items, u0, u1)
+            self._shard_key = key
 
-        def xu(buf):
-            a, b = layout.user_slice(coll.rank)
-            dist.all_gather_into_tensor(buf[:up], buf[a:b], group=coll.group)
+        def allreduce(buf):
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=coll.group)
 
-        def xi(buf):
-            a, b = layout.item_slice(coll.rank)
-            dist.all_gather_into_tensor(buf[up:], buf[a:b], group=coll.group)
-
-        acc = engine.propagate_padded(self._padded, layout, m.embeddings.weight, m.alpha, m.num_layers, coll.rank,
-                                      xu, xi, final_users=final_users)
+        acc = engine.propagate_user_sharded(m.graph, self._shard, m.embeddings.weight, m.alpha, m.num_layers,
+                                            m.num_users, allreduce)
+        if final_users:
+            coll.allgather_rows(acc, plan.user_rows)
         sharded._scorer = None
-        sharded.plan.user_slices = [layout.user_rows(r) for r in range(coll.world)]
-        sharded.plan.user_rows = sharded.plan.user_slices
-        return acc[: m.num_users], acc[up:up + m.num_items]
+        return acc[: m.num_users], acc[m.num_users:]
 
     def propagate(self, model, my_ranges, exchange, exchange_final):
         from . import engine
@@ -251,23 +243,33 @@ def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) ->
     g = model.graph
     w = model.embeddings.weight.detach()
     n, d = w.shape
-    if sharded is not None:
-        p = sharded.plan
-        ranges = [p.user_rows[p.rank], p.item_rows[p.rank]]
-    else:
-        ranges = [(0, n)]
+    U = model.num_users
     xs = torch.empty_like(w)
     xo = torch.empty_like(w)
     acc = torch.empty_like(w)
     out: Dict[str, float] = {}
+    shard = None
+    if sharded is not None and hasattr(sharded.backend, "propagate_sharded"):
+        sharded.forward(all_rows=False)                      # builds the rank's UserShard
+        shard = sharded.backend._shard
+        part = torch.empty(n - U, d, dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
         call("hnm_lightgcn_prescale", ptr(w), ptr(g.dis), 0.25, ptr(xs), ptr(acc), n, d, stream())
         heavy = ptr(g.heavy_rows) if g.num_heavy else None
 
         def layer():
-            for r0, r1 in ranges:
+            # one layer's kernels on this rank (no communication)
+            if shard is None:
                 call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
-                     0.25, n, d, r0, r1, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
+                     0.25, n, d, 0, n, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
+                return
+            if shard.u1 > shard.u0:
+                call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
+                     0.25, n, d, shard.u0, shard.u1, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
+            call("hnm_lightgcn_partial", ptr(shard.seg_begin), ptr(shard.seg_end), ptr(g.col), ptr(g.w), ptr(xs),
+                 ptr(part), d, U, n, ptr(shard.heavy_rows) if shard.heavy_rows.numel() else None,
+                 int(shard.heavy_rows.numel()), shard.num_huge, g.heavy_threshold, stream())
+            call("hnm_lightgcn_finish", ptr(part), ptr(xs), ptr(g.dis), 0.25, ptr(xo), ptr(acc), U, n - U, d, stream())
         layer()
         a = ev()
         for _ in range(steps):
@@ -283,7 +285,7 @@ def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) ->
         out["prescale_ms"] = a.elapsed_time(b) / steps
     del xs, xo, acc
     # propagate (all layers, exchanges included when sharded)
-    fwd = sharded.forward if sharded is not None else model.forward
+    fwd = (lambda: sharded.forward(all_rows=sharded.mode != "users")) if sharded is not None else model.forward
     fwd()
     a = ev()
     for _ in range(steps):

@@ -221,96 +221,93 @@ def merge_topk(ids: torch.Tensor, scores: torch.Tensor) -> Tuple[torch.Tensor, t
     return out_i, out_s
 
 
-# ----------------------------------------------------------------------------- padded (sharded) layout
+# ----------------------------------------------------------------------------- user-sharded propagation
 @dataclass
-class PaddedLayout:
-    """Node numbering used by the row-sharded propagation: the user block and the item block are each
-    padded to a multiple of the world size so that every rank owns equally sized, contiguous slices
-    (one in-place all-gather per block and layer, no staging copies).  Pad nodes are isolated."""
-    num_users: int
-    num_items: int
-    world: int
-
-    @property
-    def chunk_u(self) -> int:
-        return (self.num_users + self.world - 1) // self.world
-
-    @property
-    def chunk_i(self) -> int:
-        return (self.num_items + self.world - 1) // self.world
-
-    @property
-    def users_padded(self) -> int:
-        return self.chunk_u * self.world
-
-    @property
-    def items_padded(self) -> int:
-        return self.chunk_i * self.world
-
-    @property
-    def num_nodes(self) -> int:
-        return self.users_padded + self.items_padded
-
-    def user_slice(self, r: int) -> Tuple[int, int]:          # communication slice (pad rows included)
-        return r * self.chunk_u, (r + 1) * self.chunk_u
-
-    def item_slice(self, r: int) -> Tuple[int, int]:
-        return self.users_padded + r * self.chunk_i, self.users_padded + (r + 1) * self.chunk_i
-
-    def user_rows(self, r: int) -> Tuple[int, int]:           # rows rank r computes (real nodes only)
-        a, b = self.user_slice(r)
-        return min(a, self.num_users), min(b, self.num_users)
-
-    def item_rows(self, r: int) -> Tuple[int, int]:
-        a, b = self.item_slice(r)
-        hi = self.users_padded + self.num_items
-        return min(a, hi), min(b, hi)
-
-    def remap_edges(self, edge_index: torch.Tensor) -> torch.Tensor:
-        shift = self.users_padded - self.num_users
-        if shift == 0:
-            return edge_index
-        return torch.where(edge_index >= self.num_users, edge_index + shift, edge_index)
+class UserShard:
+    """What one rank needs to propagate with the USERS partitioned: its user range and, for every item
+    row, the sub-range of CSR entries whose column is one of its users (contiguous: columns are sorted)."""
+    u0: int
+    u1: int
+    seg_begin: torch.Tensor       # int32 [I]
+    seg_end: torch.Tensor         # int32 [I]
+    heavy_rows: torch.Tensor      # int32, item NODE ids whose sub-range is long (very long ones first)
+    num_huge: int
 
 
-def propagate_padded(graph: Graph, layout: PaddedLayout, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
-                     rank: int, exchange_users, exchange_items, final_users: bool = True) -> torch.Tensor:
-    """Row-sharded LightGCN.forward in the padded layout.  Returns acc [layout.num_nodes, d]; users are
-    rows [0, U), items rows [users_padded, users_padded + I).  exchange_users(buf) / exchange_items(buf)
-    all-gather the equal slices of the two blocks in place.  With final_users=False the returned user
-    rows are valid only for this rank's slice (enough for a user-sharded scorer)."""
+def _lower_bound(col: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, target: int) -> torch.Tensor:
+    """Per row, first position p in [lo, hi) with col[p] >= target (vectorised bisection)."""
+    lo, hi = lo.clone(), hi.clone()
+    n = col.numel()
+    for _ in range(34):
+        active = lo < hi
+        if not bool(active.any()):
+            break
+        mid = (lo + hi) // 2
+        less = col[mid.clamp(max=n - 1)] < target
+        lo = torch.where(active & less, mid + 1, lo)
+        hi = torch.where(active & ~less, mid, hi)
+    return lo
+
+
+def make_user_shard(graph: Graph, num_users: int, num_items: int, u0: int, u1: int) -> UserShard:
+    rp = graph.rowptr.long()
+    lo, hi = rp[num_users:num_users + num_items], rp[num_users + 1:num_users + num_items + 1]
+    b = _lower_bound(graph.col, lo, hi, u0)
+    e = _lower_bound(graph.col, lo, hi, u1)
+    length = e - b
+    rows = torch.arange(num_users, num_users + num_items, device=rp.device)
+    heavy = length > graph.heavy_threshold
+    huge = length > HUGE_ROW
+    heavy_rows = torch.cat([rows[huge], rows[heavy & ~huge]]).to(torch.int32).contiguous()
+    return UserShard(u0, u1, b.to(torch.int32).contiguous(), e.to(torch.int32).contiguous(), heavy_rows,
+                     int(huge.sum()))
+
+
+def propagate_user_sharded(graph: Graph, shard: UserShard, e0: torch.Tensor, alphas: Sequence[float],
+                           num_layers: int, num_users: int, allreduce_items) -> torch.Tensor:
+    """LightGCN.forward with the users partitioned over ranks (one process per GPU).
+
+    Every rank keeps all item rows and its own user rows.  Per layer: its user rows gather from the
+    item block as usual; for the item rows it sums only over its own users (hnm_lightgcn_partial),
+    ``allreduce_items(partial)`` adds the ranks' partial sums in place (27 MB at the H&M shape, instead
+    of all-gathering the 351 MB user block), and hnm_lightgcn_finish normalises.  Returns acc [N, d]:
+    valid for the item rows and for user rows [u0, u1).
+    """
     _lib.require_device()
     e0 = e0.detach().to(torch.float32).contiguous()
-    n_real, d = e0.shape
-    U, I = layout.num_users, layout.num_items
-    if n_real != U + I or graph.num_nodes != layout.num_nodes:
-        raise ValueError("layout / graph / embedding sizes disagree")
+    n, d = e0.shape
+    U = num_users
+    I = n - U
+    if d % 4:
+        raise ValueError("user-sharded propagation needs embedding_dim % 4 == 0")
     dev = e0.device
-    up = layout.users_padded
-    acc = torch.zeros(layout.num_nodes, d, dtype=torch.float32, device=dev)
-    xs_a = torch.zeros_like(acc)
-    xs_b = torch.zeros_like(acc) if num_layers > 1 else None
-    ranges = [layout.user_rows(rank), layout.item_rows(rank)]
+    u0, u1 = shard.u0, shard.u1
+    acc = torch.empty_like(e0)
+    xs_a = torch.empty_like(e0)
+    xs_b = torch.empty_like(e0) if num_layers > 1 else None
+    part = torch.empty(I, d, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         s = stream()
-        call("hnm_lightgcn_prescale", ptr(e0[:U]), ptr(graph.dis[:U]), float(alphas[0]), ptr(xs_a[:U]), ptr(acc[:U]),
-             U, d, s)
-        call("hnm_lightgcn_prescale", ptr(e0[U:]), ptr(graph.dis[up:up + I]), float(alphas[0]), ptr(xs_a[up:up + I]),
-             ptr(acc[up:up + I]), I, d, s)
+        if u1 > u0:
+            call("hnm_lightgcn_prescale", ptr(e0[u0:u1]), ptr(graph.dis[u0:u1]), float(alphas[0]), ptr(xs_a[u0:u1]),
+                 ptr(acc[u0:u1]), u1 - u0, d, s)
+        call("hnm_lightgcn_prescale", ptr(e0[U:]), ptr(graph.dis[U:]), float(alphas[0]), ptr(xs_a[U:]), ptr(acc[U:]),
+             I, d, s)
         cur, nxt = xs_a, xs_b
         heavy = ptr(graph.heavy_rows) if graph.num_heavy else None
+        sh_heavy = ptr(shard.heavy_rows) if shard.heavy_rows.numel() else None
         for layer in range(1, num_layers + 1):
             last = layer == num_layers
-            for r0, r1 in ranges:
-                if r1 > r0:
-                    call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
-                         None if last else ptr(nxt), ptr(acc), float(alphas[layer]), layout.num_nodes, d, r0, r1,
-                         heavy, graph.num_heavy, graph.num_huge, graph.heavy_threshold, s)
+            if u1 > u0:
+                call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
+                     None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, u0, u1, heavy, graph.num_heavy,
+                     graph.num_huge, graph.heavy_threshold, s)
+            call("hnm_lightgcn_partial", ptr(shard.seg_begin), ptr(shard.seg_end), ptr(graph.col), ptr(graph.w),
+                 ptr(cur), ptr(part), d, U, n, sh_heavy, int(shard.heavy_rows.numel()), shard.num_huge,
+                 graph.heavy_threshold, s)
+            allreduce_items(part)
+            call("hnm_lightgcn_finish", ptr(part), ptr(cur), ptr(graph.dis), float(alphas[layer]),
+                 None if last else ptr(nxt), ptr(acc), U, I, d, s)
             if not last:
-                exchange_users(nxt)
-                exchange_items(nxt)
                 cur, nxt = nxt, cur
-        exchange_items(acc)
-        if final_users:
-            exchange_users(acc)
     return acc

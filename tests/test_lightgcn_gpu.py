@@ -186,49 +186,43 @@ def test_large_k_falls_back_to_device_sort(hnm_lib):
     assert_topk_matches_scores(got, s, 300, rel_tol=1e-5)
 
 
-def test_padded_sharded_propagate_emulated_ranks(hnm_lib):
-    """The row-sharded propagation in the padded node layout (dist.CudaBackend.propagate_padded), one
-    emulated rank at a time on one GPU: the exchange callbacks fill the slices the other ranks would
-    have sent with oracle values, the rows this rank owns must come out right."""
+def test_user_sharded_propagate_emulated_ranks(hnm_lib):
+    """engine.propagate_user_sharded, one emulated rank at a time on one GPU: the all-reduce callback
+    checks this rank's partial item sums against the oracle and then substitutes the full sums the
+    other ranks would have contributed; the rows the rank owns must come out right."""
     from hnm_recommendation_b200 import engine
-    U, I, d, L, G = 203, 97, 64, 3, 3                      # neither block divides by the world size
+    from hnm_recommendation_b200.dist import even_ranges
+    U, I, d, L, G = 203, 97, 64, 3, 3
     gen = torch.Generator().manual_seed(3)
     u = torch.randint(0, U, (2500,), generator=gen)
     i = torch.randint(0, I, (2500,), generator=gen) + U
     ei = torch.stack([torch.cat([u, i]), torch.cat([i, u])])
+    ew = torch.rand(2500, generator=gen) + 0.5
+    ew = torch.cat([ew, ew])
     w = torch.randn(U + I, d, generator=gen) * 0.1
     alphas = O.layer_weights(L)
-    rowptr, col, val, dis = O.build_norm_adj(ei, None, U + I)
-    layers = [w]
-    for _ in range(L):
-        layers.append(O.lightgcn_oracle._spmm(rowptr, col, val, layers[-1]))
-    final = sum(a * e for a, e in zip(alphas, layers))
-    lay = engine.PaddedLayout(U, I, G)
-    assert lay.users_padded == 204 and lay.items_padded == 99 and lay.num_nodes == 303
-    graph = engine.build_graph(lay.remap_edges(ei), None, lay.num_nodes, torch.device("cuda"))
-    up = lay.users_padded
+    for weights in (None, ew):
+        rowptr, col, val, dis = O.build_norm_adj(ei, weights, U + I)
+        layers = [w]
+        for _ in range(L):
+            layers.append(O.lightgcn_oracle._spmm(rowptr, col, val, layers[-1]))
+        final = sum(a * e for a, e in zip(alphas, layers))
+        graph = engine.build_graph(ei, weights, U + I, torch.device("cuda"))
+        # raw (un-normalised) adjacency user->item block for the partial sums: W[i, u] = sum of edge weights
+        wts = torch.ones(ei.size(1)) if weights is None else weights
+        sel = ei[0] >= U                                         # rows that are items
+        W = torch.zeros(I, U).index_put_((ei[0][sel] - U, ei[1][sel]), wts[sel], accumulate=True)
+        for rank, (u0, u1) in enumerate(even_ranges(U, G)):
+            shard = engine.make_user_shard(graph, U, I, u0, u1)
+            state = {"layer": 0}
 
-    def padded(t):                                           # [U+I, d] -> padded layout
-        out = torch.zeros(lay.num_nodes, d)
-        out[:U] = t[:U]
-        out[up:up + I] = t[U:]
-        return out.cuda()
+            def allreduce(part):
+                xs = dis.unsqueeze(1) * layers[state["layer"]]   # what the kernels gather from
+                mine = W[:, u0:u1] @ xs[u0:u1]
+                assert_close(part, mine, rtol=1e-5, atol_scale=1e-5, what=f"partial sums rank {rank}")
+                part.copy_((W @ xs[:U]).cuda())
+                state["layer"] += 1
 
-    for rank in range(G):
-        calls = {"n": 0}
-
-        def fill(buf, block):
-            # exchanges come in pairs (users, items) per layer, then items (+ users) for the layer sum
-            layer = calls["n"] // 2 + 1
-            src = padded(dis.unsqueeze(1) * layers[layer]) if layer < L else padded(final)
-            a, b = (lay.user_slice(rank) if block == "u" else lay.item_slice(rank))
-            lo, hi = (0, up) if block == "u" else (up, lay.num_nodes)
-            mine = buf[a:b].clone()
-            buf[lo:hi] = src[lo:hi]
-            buf[a:b] = mine
-            calls["n"] += 1
-
-        acc = engine.propagate_padded(graph, lay, w.cuda(), alphas, L, rank,
-                                      lambda b: fill(b, "u"), lambda b: fill(b, "i"), final_users=True)
-        got = torch.cat([acc[:U], acc[up:up + I]]).cpu()
-        assert_close(got, final, what=f"emulated rank {rank}")
+            acc = engine.propagate_user_sharded(graph, shard, w.cuda(), alphas, L, U, allreduce).cpu()
+            assert_close(acc[U:], final[U:], what=f"items, rank {rank}")
+            assert_close(acc[u0:u1], final[u0:u1], what=f"own users, rank {rank}")
