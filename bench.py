@@ -11,9 +11,11 @@ One step = one pass of the hot path over the synthetic H&M-shaped workload
 step through the public model API with the embedding table coming from pinned
 host memory and the [users, 12] result going back to the host.
 
-N > 1 (torchrun, one rank per GPU): rows of the propagation and items of the
-catalog are sharded across ranks (hnm_recommendation_b200/dist.py), weak = false:
-the job is the same total work, so `scaling` is "strong".
+N > 1 (torchrun, one rank per GPU): users are partitioned across the ranks for the
+propagation (one all-reduce of the item block per layer) and for the scoring
+(hnm_recommendation_b200/dist.py; HNM_SHARD_MODE=items selects the item-catalog
+sharding of BASELINE.json's north_star).  The job is the same total work at every N,
+so `scaling` is "strong".
 
 --impl reference times the CPU oracle (plain PyTorch restatement of the
 reference, oracle/) on the host cores of the box; see `cpu_baseline`.
@@ -210,10 +212,24 @@ def run_gpu(args):
     def step_resident():
         return sharded.recommend_all() if sharded else model.recommend_all()
 
+    if sharded and sharded.mode == "users":
+        # a rank only reads its own users' rows and the item block of the table, and owns one slice of the result
+        u0, u1 = sharded.plan.user_rows[rank]
+        h2d_rows = [(u0, u1), (u, u + i)]
+        d2h_rows = (u0, u1)
+    else:
+        h2d_rows = [(0, u + i)]
+        d2h_rows = (0, u) if rank == 0 else (0, 0)
+    h2d_bytes = sum(b - a for a, b in h2d_rows) * DIM * 4
+    d2h_bytes = (d2h_rows[1] - d2h_rows[0]) * K_TOP * 8
+
     def step_e2e():
-        model.embeddings.weight.data.copy_(w_host, non_blocking=True)       # H2D of the step's input
+        wt = model.embeddings.weight.data
+        for a, b in h2d_rows:
+            wt[a:b].copy_(w_host[a:b], non_blocking=True)                   # H2D of the step's input
         ids = sharded.recommend_all() if sharded else model.recommend_all()
-        out_host.copy_(ids, non_blocking=True)                              # D2H of the step's result
+        a, b = d2h_rows
+        out_host[a:b].copy_(ids[a:b], non_blocking=True)                    # D2H of the step's result
         torch.cuda.current_stream().synchronize()
 
     sampler = ClockSampler(local)
@@ -228,6 +244,9 @@ def run_gpu(args):
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
+        t = torch.tensor([h2d_bytes, d2h_bytes], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_bytes, d2h_bytes = (int(x) for x in t.tolist())
 
     # per-stage kernel times on this rank (CUDA events on the launching stream)
     stages = hdist.profile_stages(model, sharded, steps=max(2, args.steps // 2))
@@ -253,7 +272,7 @@ def run_gpu(args):
                    "l2": "inputs larger than L2 (378 MB embedding table, 175 MB fp16 user operand); no explicit flush",
                    "parallelism": "single GPU" if world == 1 else f"{sharded.mode}-sharded scoring + row-sharded propagation (all-gather per layer) x{world}"},
         "e2e": {"value": u / ms_e2e * 1e3, "unit": "users/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(w_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 8)},
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "score_topk_fused_kernel", "achieved": ach_tf,
