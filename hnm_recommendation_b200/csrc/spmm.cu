@@ -298,11 +298,42 @@ __global__ void prescale_kernel_v4(const float4* __restrict__ e0, const float* _
   }
 }
 
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+
+// one side stream + event pair per device, created on first use
+SideStream* side_stream() {
+  static SideStream per_device[16];
+  static bool ready[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!ready[dev]) {
+    SideStream s{};
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    per_device[dev] = s;
+    ready[dev] = true;
+  }
+  return &per_device[dev];
+}
+
 template <int D, bool WEIGHTED>
 int launch_layer(Seg seg, int partial, const int32_t* col, const float* w, const float* dis, const float* xs_in,
                  float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
                  const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge, int32_t heavy_threshold,
                  cudaStream_t stream) {
+  // The long rows run on a side stream next to the warp-per-row kernel (they touch disjoint output
+  // rows); fork/join with events so the caller still sees one stream-ordered operation.
+  cudaStream_t main_stream = stream;
+  SideStream* side = num_heavy > 0 ? side_stream() : nullptr;
+  if (side) {
+    HNM_CUDA_TRY(cudaEventRecord(side->fork, main_stream));
+    HNM_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    stream = side->stream;
+  }
   if (num_huge > 0) {
     spmm_huge_kernel<D, WEIGHTED><<<num_huge * kHeavyCluster, kHugeThreads, 0, stream>>>(seg, partial, col, w, dis, xs_in, xs_out,
                                                                                       acc, alpha, heavy_rows, row_begin,
@@ -313,6 +344,10 @@ int launch_layer(Seg seg, int partial, const int32_t* col, const float* w, const
     spmm_heavy_kernel<D, WEIGHTED><<<num_heavy - num_huge, kHeavyThreads, 0, stream>>>(
         seg, partial, col, w, dis, xs_in, xs_out, acc, alpha, heavy_rows + num_huge, row_begin, row_end);
     HNM_LAUNCH_CHECK();
+  }
+  if (side) {
+    HNM_CUDA_TRY(cudaEventRecord(side->join, side->stream));
+    stream = main_stream;
   }
   const int64_t rows = row_end - row_begin;
   static const int variant = getenv("HNM_SPMM_VARIANT") ? atoi(getenv("HNM_SPMM_VARIANT")) : 0;
@@ -335,6 +370,7 @@ int launch_layer(Seg seg, int partial, const int32_t* col, const float* w, const
   }
 #undef HNM_ROWS
   HNM_LAUNCH_CHECK();
+  if (side) HNM_CUDA_TRY(cudaStreamWaitEvent(main_stream, side->join, 0));
   return HNM_OK;
 }
 
