@@ -5,8 +5,8 @@
 //     W1 [mu ; mi] + b1 = (W1[:, :h] mu) + (W1[:, h:] mi + b1) = P[u] + Q[i],
 // so hnm_ncf_precompute builds P (users) and Q (items, bias folded in) once per weight
 // update and a pair costs one 2*h1-float gather plus the small tail of the MLP.
-// One thread per (user, item) pair; the tail weights sit in shared memory and are read
-// as warp-wide broadcasts.
+// The tail weights sit in shared memory and are read as warp-wide broadcasts; see the two kernels
+// for the thread mapping.
 #include <algorithm>
 #include "common.cuh"
 
@@ -45,54 +45,77 @@ ncf_precompute_kernel(const float* __restrict__ emb, int64_t rows, int h, const 
 }
 
 // Fast path: mf_dim 64, MLP [128 -> 64 -> 32] (the reference default, configs/model/neural_cf.yaml).
-__global__ void __launch_bounds__(256)
+// A warp takes 32 consecutive pairs.  Gather phase: half a warp per pair, 16 lanes x 128-bit, so every
+// 256-byte table row is one coalesced request (a thread-per-pair gather issues 32-sector requests and
+// was LSU bound); h1 = relu(P[u] + Q[i]) goes to a padded shared-memory tile and the GMF dot product is
+// reduced across the 16 lanes.  Compute phase: lane = pair, h1 from shared memory (conflict free),
+// W2 / b2 / wp broadcast from shared memory.
+constexpr int kNcfWarps = 8;
+constexpr int kNcfStride = 65;       // floats per h1 row in shared memory (64 + 1: bank = (pair + c) % 32)
+
+__global__ void __launch_bounds__(kNcfWarps * 32)
 ncf_score_default_kernel(const float* __restrict__ gu, const float* __restrict__ gi, const float* __restrict__ pu,
                          const float* __restrict__ qi, const float* __restrict__ tail, const float* __restrict__ wp,
                          float bp, const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids,
                          const int32_t* __restrict__ cand_items, int cand_per_user, int64_t total,
                          float* __restrict__ out) {
   constexpr int MF = 64, H1 = 64, H2 = 32;
-  __shared__ __align__(16) float s_w2[H2 * H1];
-  __shared__ float s_b2[H2];
-  __shared__ float s_wp[MF + H2];
+  extern __shared__ __align__(16) float smem_ncf[];
+  float* s_w2 = smem_ncf;                       // [H2][H1]
+  float* s_b2 = s_w2 + H2 * H1;                 // [H2]
+  float* s_wp = s_b2 + H2;                      // [MF + H2]
+  float* s_h1 = s_wp + MF + H2 + (threadIdx.x >> 5) * (32 * kNcfStride + 32);   // per warp: [32][65] + gmf[32]
+  float* s_g = s_h1 + 32 * kNcfStride;
   for (int t = threadIdx.x; t < H2 * H1; t += blockDim.x) s_w2[t] = tail[t];
   for (int t = threadIdx.x; t < H2; t += blockDim.x) s_b2[t] = tail[H2 * H1 + t];
   for (int t = threadIdx.x; t < MF + H2; t += blockDim.x) s_wp[t] = wp[t];
   __syncthreads();
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t u, i;
-    if (cand_per_user > 0) {
-      const int64_t r = t / cand_per_user;
-      u = user_ids ? user_ids[r] : r;
-      i = cand_items ? (int64_t)cand_items[t] : t - r * cand_per_user;
-    } else {
-      u = user_ids[t];
-      i = item_ids[t];
+  const int lane = threadIdx.x & 31;
+  const int half = lane >> 4, sub = lane & 15;
+  const int64_t warp_global = (int64_t)blockIdx.x * kNcfWarps + (threadIdx.x >> 5);
+  const int64_t warp_count = (int64_t)gridDim.x * kNcfWarps;
+  const float4 wg = *reinterpret_cast<const float4*>(s_wp + sub * 4);
+  for (int64_t t0 = warp_global * 32; t0 < total; t0 += warp_count * 32) {
+    const int64_t t = t0 + lane;
+    int64_t u = 0, i = 0;
+    if (t < total) {
+      if (cand_per_user > 0) {
+        const int64_t r = t / cand_per_user;
+        u = user_ids ? user_ids[r] : r;
+        i = cand_items ? (int64_t)cand_items[t] : t - r * cand_per_user;
+      } else {
+        u = user_ids[t];
+        i = item_ids[t];
+      }
     }
-    const float* p = pu + (size_t)u * H1;
-    const float* q = qi + (size_t)i * H1;
+    // ---- gather: pair l = 2 * step + half, this lane's 4 columns are [4 sub, 4 sub + 4)
+#pragma unroll 4
+    for (int step = 0; step < 16; ++step) {
+      const int l = 2 * step + half;
+      const int64_t ul = __shfl_sync(0xffffffffu, u, l);
+      const int64_t il = __shfl_sync(0xffffffffu, i, l);
+      const float4 a = ldg_f4(pu + (size_t)ul * H1 + sub * 4), b = ldg_f4(qi + (size_t)il * H1 + sub * 4);
+      const float4 x = ldg_f4(gu + (size_t)ul * MF + sub * 4), z = ldg_f4(gi + (size_t)il * MF + sub * 4);
+      float* h = s_h1 + l * kNcfStride + sub * 4;
+      h[0] = fmaxf(a.x + b.x, 0.f);
+      h[1] = fmaxf(a.y + b.y, 0.f);
+      h[2] = fmaxf(a.z + b.z, 0.f);
+      h[3] = fmaxf(a.w + b.w, 0.f);
+      // GMF term: (gu * gi) . wp[:MF]   (neural_cf.py:127,136-139)
+      float g = wg.x * __fmul_rn(x.x, z.x);
+      g = fmaf(wg.y, __fmul_rn(x.y, z.y), g);
+      g = fmaf(wg.z, __fmul_rn(x.z, z.z), g);
+      g = fmaf(wg.w, __fmul_rn(x.w, z.w), g);
+#pragma unroll
+      for (int off = 8; off; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
+      if (sub == 0) s_g[l] = g;
+    }
+    __syncwarp();
+    // ---- compute: lane = pair
     float h1[H1];
 #pragma unroll
-    for (int c = 0; c < H1; c += 4) {
-      const float4 a = ldg_f4(p + c), b = ldg_f4(q + c);
-      h1[c] = fmaxf(a.x + b.x, 0.f);
-      h1[c + 1] = fmaxf(a.y + b.y, 0.f);
-      h1[c + 2] = fmaxf(a.z + b.z, 0.f);
-      h1[c + 3] = fmaxf(a.w + b.w, 0.f);
-    }
-    // GMF term: (gu * gi) . wp[:MF]   (neural_cf.py:127,136-139)
-    float y = 0.f;
-    const float* a = gu + (size_t)u * MF;
-    const float* b = gi + (size_t)i * MF;
-#pragma unroll
-    for (int c = 0; c < MF; c += 4) {
-      const float4 x = ldg_f4(a + c), z = ldg_f4(b + c);
-      y = fmaf(s_wp[c], __fmul_rn(x.x, z.x), y);
-      y = fmaf(s_wp[c + 1], __fmul_rn(x.y, z.y), y);
-      y = fmaf(s_wp[c + 2], __fmul_rn(x.z, z.z), y);
-      y = fmaf(s_wp[c + 3], __fmul_rn(x.w, z.w), y);
-    }
+    for (int c = 0; c < H1; ++c) h1[c] = s_h1[lane * kNcfStride + c];
+    float y = s_g[lane];
 #pragma unroll 4
     for (int j = 0; j < H2; ++j) {
       float s = 0.f;
@@ -108,7 +131,8 @@ ncf_score_default_kernel(const float* __restrict__ gu, const float* __restrict__
       s = fmaxf(s + s_b2[j], 0.f);
       y = fmaf(s_wp[MF + j], s, y);
     }
-    out[t] = y + bp;
+    if (t < total) out[t] = y + bp;
+    __syncwarp();
   }
 }
 
@@ -186,10 +210,17 @@ int launch_score(const float* gu, const float* gi, const float* pu, const float*
   const bool is_default = num_layers == 2 && mf == 64 && d.width[0] == 64 && d.width[1] == 32 &&
                           hnm_aligned16(gu) && hnm_aligned16(gi) && hnm_aligned16(pu) && hnm_aligned16(qi);
   if (is_default) {
-    const int T = 256;
-    const unsigned grid = (unsigned)std::min<int64_t>((total + T - 1) / T, (int64_t)hnm_num_sms() * 8);
-    ncf_score_default_kernel<<<grid, T, 0, stream>>>(gu, gi, pu, qi, tail, wp, bp, user_ids, item_ids, cand_items,
-                                                    cand_per_user, total, out);
+    const int T = kNcfWarps * 32;
+    const size_t smem = sizeof(float) * (64 * 32 + 32 + 64 + 32 + kNcfWarps * (32 * kNcfStride + 32));
+    static bool attr_default = false;
+    if (!attr_default) {
+      HNM_CUDA_TRY(cudaFuncSetAttribute(ncf_score_default_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+      attr_default = true;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>((total + T - 1) / T, (int64_t)hnm_num_sms() * 6);
+    ncf_score_default_kernel<<<grid, T, smem, stream>>>(gu, gi, pu, qi, tail, wp, bp, user_ids, item_ids, cand_items,
+                                                       cand_per_user, total, out);
   } else {
     const size_t smem = sizeof(float) * (size_t)d.tail_floats;
     if (smem > 200 * 1024) return HNM_E_DIM;
