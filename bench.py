@@ -40,6 +40,9 @@ K_TOP = 12
 DIM = 64
 LAYERS = 3
 METRIC = "users/sec full-catalog top-12 (LightGCN 3-layer dim-64 propagate + score + top-12)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this very
+# command at N = 1 (profiles/r1_bench.md); not measured live -- a run under a profiler is never a bench run.
+NCU_DRAM_BYTES = {"fused": 0.29e9 + 0.99e9, "spmm_layer": 3.1e9 + 0.57e9}
 
 
 def peaks():
@@ -277,7 +280,8 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "score_topk_fused_kernel", "achieved": ach_tf,
                      "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": ach_tf / pk["tflops_sustained"] if ach_tf else None, "traffic": None,
+                     "frac": ach_tf / pk["tflops_sustained"] if ach_tf else None,
+                     "traffic": NCU_DRAM_BYTES["fused"] if (world == 1 and args.config == "hm") else None,
                      "peak_source": pk["source"] + " (cuBLAS bf16 sustained; burst %.1f)" % pk["tflops_burst"],
                      "algorithmic_flops": flops / world, "ms": fused_ms},
         "roofline_spmm": {"bound": "hbm", "kernel": "spmm_rows_kernel+spmm_heavy_kernel (one layer)",
@@ -285,7 +289,8 @@ def run_gpu(args):
                           "peak": pk["hbm_gbs"], "unit": "GB/s",
                           "frac": spmm_alg_bytes / world / spmm_ms / 1e6 / pk["hbm_gbs"] if spmm_ms else None,
                           "gather_model_gbs": (nnz * (4 + 4 * DIM) + n_nodes * 4 * DIM) / world / spmm_ms / 1e6 if spmm_ms else None,
-                          "algorithmic_bytes": spmm_alg_bytes / world, "ms": spmm_ms, "traffic": None},
+                          "algorithmic_bytes": spmm_alg_bytes / world, "ms": spmm_ms,
+                          "traffic": NCU_DRAM_BYTES["spmm_layer"] if (world == 1 and args.config == "hm") else None},
         "stages_ms": stages,
     }
     if world == 1 and not args.no_cpu:

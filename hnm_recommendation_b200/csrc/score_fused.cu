@@ -494,6 +494,8 @@ constexpr int kMaxPerLane = 8;   // candidate capacity handled = 32 * kMaxPerLan
 constexpr int kGroup = 4;        // items per nominated group (select32)
 constexpr int kMaxGroups = 64;   // surviving groups hnm_rescore_topk can take per user
 constexpr int kMaxContenders = 128;  // rescored items above the cut it can rank per user
+constexpr int kRescoreWarps = 4;     // one user per warp
+constexpr int kTileStride = 65;      // floats per staged item row (64 + 1: conflict-free column walks)
 
 __device__ __forceinline__ bool in_sorted(const int64_t* __restrict__ a, int64_t lo, int64_t hi, int64_t x) {
   while (lo < hi) {
@@ -510,7 +512,7 @@ __device__ __forceinline__ bool before32(double sa, int ia, double sb, int ib) {
   return sa > sb || (sa == sb && ia < ib);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kRescoreWarps * 32)
 rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
                const int64_t* __restrict__ user_ids, int64_t batch, int dim, int64_t item_begin, int num_items_local,
                const uint2* __restrict__ cand, int cap, const int32_t* __restrict__ cand_count,
@@ -518,9 +520,10 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
                const float* __restrict__ center, const int64_t* __restrict__ excl_ptr,
                const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
                double* __restrict__ out_scores, int32_t* __restrict__ certified) {
-  __shared__ uint32_t s_col[8][kMaxGroups];
-  __shared__ double s_sc[8][kMaxContenders];
-  __shared__ int s_id[8][kMaxContenders];
+  __shared__ uint32_t s_col[kRescoreWarps][kMaxGroups];
+  __shared__ float s_tile[kRescoreWarps][32 * kTileStride];
+  __shared__ double s_sc[kRescoreWarps][kMaxContenders];
+  __shared__ int s_id[kRescoreWarps][kMaxContenders];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -555,71 +558,86 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
   const bool too_many = groups > kMaxGroups;
   groups = min(groups, kMaxGroups);
   int total = 0;                                            // contenders found so far
-  double un = 0.0, uc = 0.0, uc_abs = 0.0;                  // ||u||^2, u.c, sum |u_k c_k|
-  double cut = 0.0;
-  for (int gb = 0; gb < groups || gb == 0; gb += 32) {      // 32 groups per round; one round is the rule
-  const int col0 = gb + lane < groups ? (int)s_col[wib][gb + lane] : -1;
-
-  // 2. exact fp64 scores (k = 0..dim-1 fma chain per item) of the four items of my group; the four
-  //    chains advance together so eight row loads are in flight and u is converted once per step
-  bool live[kGroup];
-  const float* irow[kGroup];
-  double acc[kGroup];
-#pragma unroll
-  for (int e = 0; e < kGroup; ++e) {
-    const int item = col0 + e;
-    live[e] = col0 >= 0 && item < num_items_local;          // columns past the catalog are zero padding
-    if (live[e] && ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)item)) live[e] = false;
-    irow[e] = item_emb + (size_t)(live[e] ? item : 0) * dim;
-    acc[e] = 0.0;
-  }
-  for (int kk = 0; kk < dim; kk += 4) {
+  // ||u||_2, u.c and sum |u_k c_k| for the bound, each k on one lane
+  double un = 0.0, uc = 0.0, uc_abs = 0.0;
+  for (int kk = 4 * lane; kk < dim; kk += 128) {
     const float4 uf = ldg_f4(urow + kk);
-    float4 vf[kGroup];
-#pragma unroll
-    for (int e = 0; e < kGroup; ++e) vf[e] = ldg_f4(irow[e] + kk);
     const double u0 = (double)uf.x, u1 = (double)uf.y, u2 = (double)uf.z, u3 = (double)uf.w;
-#pragma unroll
-    for (int e = 0; e < kGroup; ++e) {
-      acc[e] = fma(u0, (double)vf[e].x, acc[e]);
-      acc[e] = fma(u1, (double)vf[e].y, acc[e]);
-      acc[e] = fma(u2, (double)vf[e].z, acc[e]);
-      acc[e] = fma(u3, (double)vf[e].w, acc[e]);
+    un = fma(u0, u0, un); un = fma(u1, u1, un); un = fma(u2, u2, un); un = fma(u3, u3, un);
+    if (center) {
+      const float4 cf = ldg_f4(center + kk);
+      const double c0 = (double)cf.x, c1 = (double)cf.y, c2 = (double)cf.z, c3 = (double)cf.w;
+      uc = fma(u0, c0, uc); uc = fma(u1, c1, uc); uc = fma(u2, c2, uc); uc = fma(u3, c3, uc);
+      uc_abs += fabs(u0 * c0) + fabs(u1 * c1) + fabs(u2 * c2) + fabs(u3 * c3);
     }
-    if (gb == 0 && lane == ((kk >> 2) & 31)) {   // every lane sees the whole user row: count each k on one lane
-      un = fma(u0, u0, un); un = fma(u1, u1, un); un = fma(u2, u2, un); un = fma(u3, u3, un);
-      if (center) {
-        const float4 cf = ldg_f4(center + kk);
-        const double c0 = (double)cf.x, c1 = (double)cf.y, c2 = (double)cf.z, c3 = (double)cf.w;
-        uc = fma(u0, c0, uc); uc = fma(u1, c1, uc); uc = fma(u2, c2, uc); uc = fma(u3, c3, uc);
-        uc_abs += fabs(u0 * c0) + fabs(u1 * c1) + fabs(u2 * c2) + fabs(u3 * c3);
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    un += __shfl_xor_sync(0xffffffffu, un, off);
+    uc += __shfl_xor_sync(0xffffffffu, uc, off);
+    uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
+  }
+  un = sqrt(un);
+  // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
+  const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
+  const double cut = (double)thr * inv_scale + eps + uc;
+
+  // 2. exact fp64 scores (k = 0..dim-1 fma chain per item) of the items of the kept groups, 32 items
+  //    per round: the rows are fetched by half warps (one coalesced 256-byte request per row) into a
+  //    padded shared-memory tile, then lane j runs the chain of item j out of the tile.
+  // 3. contenders = rescored items strictly above the cut, appended to the warp's list.
+  float* tile = s_tile[wib];
+  const int half = lane >> 4, sub = lane & 15;
+  const int num_cand_items = groups * kGroup;
+  for (int base = 0; base < num_cand_items || base == 0; base += 32) {
+    const int it = base + lane;
+    int item = -1;
+    if (it < num_cand_items) item = (int)s_col[wib][it / kGroup] + (it % kGroup);
+    bool live = item >= 0 && item < num_items_local;        // columns past the catalog are zero padding
+    if (live && ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)item)) live = false;
+    if (dim == kDim) {
+#pragma unroll 4
+      for (int step = 0; step < 16; ++step) {
+        const int l = 2 * step + half;
+        const int il = __shfl_sync(0xffffffffu, live ? item : -1, l);
+        if (il >= 0) {
+          const float4 v = ldg_f4(item_emb + (size_t)il * kDim + sub * 4);
+          float* t = tile + l * kTileStride + sub * 4;
+          t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        }
+      }
+      __syncwarp();
+    }
+    double acc = 0.0;
+    if (live) {
+      if (dim == kDim) {
+        const float* t = tile + lane * kTileStride;
+#pragma unroll 4
+        for (int kk = 0; kk < kDim; kk += 4) {
+          const float4 uf = ldg_f4(urow + kk);
+          acc = fma((double)uf.x, (double)t[kk], acc);
+          acc = fma((double)uf.y, (double)t[kk + 1], acc);
+          acc = fma((double)uf.z, (double)t[kk + 2], acc);
+          acc = fma((double)uf.w, (double)t[kk + 3], acc);
+        }
+      } else {
+        const float* irow = item_emb + (size_t)item * dim;
+        for (int kk = 0; kk < dim; kk += 4) {
+          const float4 uf = ldg_f4(urow + kk), v = ldg_f4(irow + kk);
+          acc = fma((double)uf.x, (double)v.x, acc);
+          acc = fma((double)uf.y, (double)v.y, acc);
+          acc = fma((double)uf.z, (double)v.z, acc);
+          acc = fma((double)uf.w, (double)v.w, acc);
+        }
       }
     }
-  }
-  if (gb == 0) {
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      un += __shfl_xor_sync(0xffffffffu, un, off);
-      uc += __shfl_xor_sync(0xffffffffu, uc, off);
-      uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
-    }
-    un = sqrt(un);
-    // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
-    const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
-    cut = (double)thr * inv_scale + eps + uc;
-  }
-
-  // 3. contenders = rescored items strictly above the cut.  With at least k of them the k best
-  //    contenders are provably the exact top-k; compact them one per lane and sort the warp.
-#pragma unroll
-  for (int e = 0; e < kGroup; ++e) {
-    const bool c = live[e] && acc[e] > cut;
+    const bool c = live && acc > cut;
     const unsigned mask = __ballot_sync(0xffffffffu, c);
     const int pos = total + __popc(mask & ((1u << lane) - 1u));
-    if (c && pos < kMaxContenders) { s_sc[wib][pos] = acc[e]; s_id[wib][pos] = col0 + e; }
+    if (c && pos < kMaxContenders) { s_sc[wib][pos] = acc; s_id[wib][pos] = item; }
     total += __popc(mask);
+    __syncwarp();
   }
-  }   // rounds of 32 groups
   __syncwarp();
   if (total <= 32) {
     // the rule: one contender per lane, one warp-wide bitonic sort
@@ -773,7 +791,7 @@ extern "C" int hnm_rescore_topk(const float* user_emb, const float* item_emb, co
   if (batch < 0 || dim <= 0 || dim % 4 != 0 || k < 1 || k > 32 || cand_cap < 1 || cand_cap > 32 * kMaxPerLane ||
       num_items_local < 1 || num_items_local > INT32_MAX)
     return HNM_E_RANGE;
-  const int wpc = 8;
+  const int wpc = kRescoreWarps;
   rescore_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
       user_emb, item_emb, user_ids, batch, dim, item_begin, (int)num_items_local, (const uint2*)cand, cand_cap,
       cand_count, cand_thresh,
