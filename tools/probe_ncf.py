@@ -2,7 +2,6 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import oracle as O
 from hnm_recommendation_b200 import NeuralCF, synth
 
 U, I, C = synth.HM_USERS, synth.HM_ITEMS, 1000
@@ -25,10 +24,3 @@ for u0 in range(0, U, chunk):
 e.record(); torch.cuda.synchronize()
 ms = s.elapsed_time(e)
 print(f"ncf candidates: {n/1e9:.3f} G pairs in {ms:.1f} ms -> {n/ms/1e6:.2f} G pairs/s ; {n*20736/ms/1e9:.1f} TFLOP/s (reference formulation) ; compulsory bytes {n*8/ms/1e6:.0f} GB/s", flush=True)
-# CPU oracle on a sample
-orc = O.NeuralCFOracle(U, I, state={k: v.cpu() for k, v in m.state_dict().items()})
-su = 512
-uu = torch.arange(su).repeat_interleave(C); ii = cand[:su].cpu().long().view(-1)
-t = time.time(); ref = orc.forward(uu, ii); dt = time.time() - t
-got = m.score_candidates(torch.arange(su), cand[:su]).cpu().view(-1)
-print(f"cpu oracle: {su*C/dt/1e6:.2f} M pairs/s on {torch.get_num_threads()} threads; max rel err {float(((got-ref).abs()/(ref.abs()+1e-6)).max()):.2e}", flush=True)
