@@ -142,3 +142,28 @@ def test_ncf_candidates_default_arch(hnm_lib):
     assert not torch.allclose(out, out2)
     with pytest.raises(IndexError):
         m(torch.tensor([2000]), torch.tensor([0]))
+
+
+def test_ncf_recommend_filter_and_errors(hnm_lib):
+    from hnm_recommendation_b200 import NeuralCF
+    torch.manual_seed(1)
+    m = NeuralCF(300, 120, mf_dim=16, mlp_dims=[32, 16, 8], top_k=7).to("cuda")
+    uids = torch.tensor([3, 14, 15])
+    s = m.predict_all_items(uids).cpu()
+    filt = {3: set(torch.sort(s[0], descending=True).indices[:4].tolist()), 15: {0, 1}}
+    rec = m.recommend(uids, filter_items=filt).cpu()
+    s_f = s.clone()
+    for r, u in enumerate(uids.tolist()):
+        if u in filt:
+            s_f[r, list(filt[u])] = float("-inf")
+    assert torch.equal(rec, O.topk_canonical(s_f, 7))
+    assert not m.training
+    with pytest.raises(RuntimeError, match="out of range"):
+        m.recommend(uids, k=121)
+    with pytest.raises(IndexError):
+        m.predict_all_items(torch.tensor([300]))
+    with pytest.raises(RuntimeError):
+        m(torch.tensor([1, 2]), torch.tensor([1]))
+    cpu_model = NeuralCF(10, 10)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cpu_model(torch.tensor([1]), torch.tensor([1]))

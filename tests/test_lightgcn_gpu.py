@@ -226,3 +226,34 @@ def test_user_sharded_propagate_emulated_ranks(hnm_lib):
             acc = engine.propagate_user_sharded(graph, shard, w.cuda(), alphas, L, U, allreduce).cpu()
             assert_close(acc[U:], final[U:], what=f"items, rank {rank}")
             assert_close(acc[u0:u1], final[u0:u1], what=f"own users, rank {rank}")
+
+
+@pytest.mark.parametrize("dim,weighted", [(32, False), (128, True), (256, False), (64, True), (20, True)])
+def test_propagate_dims_and_long_rows(hnm_lib, dim, weighted):
+    """Every template instantiation of the propagate kernels (d = 32 / 64 / 128 / 256 and the generic one),
+    with rows in all three length classes: warp-per-row, whole-CTA (> 1024 entries) and CTA-cluster (> 8192)."""
+    from hnm_recommendation_b200 import LightGCN
+    U, I, L = 12000, 40, 2
+    gen = torch.Generator().manual_seed(dim)
+    # item 0 is bought by every user (12 000 entries), items 1-3 by every 4th user (3 000), the rest at random
+    u = torch.cat([torch.arange(U), torch.arange(0, U, 4).repeat(3), torch.randint(0, U, (5000,), generator=gen)])
+    i = torch.cat([torch.zeros(U, dtype=torch.long), torch.arange(1, 4).repeat_interleave(U // 4),
+                   torch.randint(4, I, (5000,), generator=gen)]) + U
+    ei = torch.stack([torch.cat([u, i]), torch.cat([i, u])])
+    ew = None
+    if weighted:
+        half = torch.rand(u.numel(), generator=gen) + 0.5
+        ew = torch.cat([half, half])
+    m = LightGCN(U, I, embedding_dim=dim, num_layers=L).to("cuda")
+    m.set_graph(ei, ew)
+    assert m.graph.num_huge >= 1 and m.graph.num_heavy > m.graph.num_huge
+    orc = O.LightGCNOracle(U, I, dim, L, weight=m.embeddings.weight.detach().cpu())
+    orc.set_graph(ei, ew)
+    gu, gi = m.forward()
+    ou, oi = orc.forward()
+    assert_close(gu, ou, what=f"users d={dim}")
+    assert_close(gi, oi, what=f"items d={dim}")
+    # deterministic: the long rows are summed in a fixed order
+    m.cache_embeddings = False
+    gu2, gi2 = m.forward()
+    assert torch.equal(gu, gu2) and torch.equal(gi, gi2)
