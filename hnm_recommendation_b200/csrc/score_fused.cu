@@ -25,7 +25,7 @@
 // largest of them, tau, is a lower bound on the kth_sel-th best score seen so far.  A column group
 // is inspected element-wise only if its maximum exceeds tau; survivors are appended to the user's
 // candidate list in global memory.  tau is refreshed (in-place sorting network over the bucket
-// registers) every time the number of item tiles seen has grown by 1/8.  The first kBootTiles item
+// registers) every time the number of item tiles seen has grown by 1/4.  The first kBootTiles item
 // tiles are run twice: once to seed the buckets, once to collect.
 #include <algorithm>
 #include <cuda.h>
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                         int num_users, int num_user_tiles, int num_item_tiles, int kth_sel,
                         uint2* __restrict__ cand, int cap, int32_t* __restrict__ cand_count,
-                        float* __restrict__ cand_thresh, int mode) {
+                        float* __restrict__ cand_thresh, int mode, int boot_tiles, int refresh_div) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                   // [2][kMU][kTileBytes]
@@ -280,7 +280,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int boot = num_item_tiles < kBootTiles ? num_item_tiles : kBootTiles;
+  const int boot = num_item_tiles < boot_tiles ? num_item_tiles : boot_tiles;
   const int num_iters = num_item_tiles + boot;
   // user tiles are dealt out evenly: CTA b owns [t_begin, t_end) and walks it in passes of up to kMU
   // tiles, so CTAs differ by at most one tile (a third of a pass), not by a whole pass
@@ -407,7 +407,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
           // it == boot: the seed pass is over, collecting starts (again from tile 0)
           rs.tau = refresh_tau(rs.bm, kth_sel);
           const int seen = max(boot, it - boot);         // item tiles behind the current bucket maxima
-          next_refresh = it + max(2, seen / 8);
+          next_refresh = it + max(2, seen / refresh_div);
         }
         mbar_wait(&bars->t_full[m], uses & 1);
         ++uses;
@@ -766,12 +766,14 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
     attr_set = true;
   }
   static const int debug_mode = getenv("HNM_FUSED_DEBUG") ? atoi(getenv("HNM_FUSED_DEBUG")) : 0;
+  static const int boot_tiles = getenv("HNM_FUSED_BOOT") ? std::max(1, atoi(getenv("HNM_FUSED_BOOT"))) : kBootTiles;
+  static const int refresh_div = getenv("HNM_FUSED_REFRESH") ? std::max(1, atoi(getenv("HNM_FUSED_REFRESH"))) : 4;
   const int num_user_tiles = (int)(users_padded / kUserTile);
   const int num_tiles = (int)(items_padded / kItemTile);
   const int grid = std::min((num_user_tiles + kMU - 1) / kMU, hnm_num_sms());
   score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_u, map_i, (int)num_users, num_user_tiles,
                                                                   num_tiles, kth_sel, (uint2*)cand,
-                                                                  cand_cap, cand_count, cand_thresh, debug_mode);
+                                                                  cand_cap, cand_count, cand_thresh, debug_mode, boot_tiles, refresh_div);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
