@@ -21,6 +21,19 @@ def test_library_exports_every_declared_symbol(hnm_lib):
     assert declared == set(_lib._SIGNATURES), "ctypes signature table out of sync with the header"
 
 
+def test_ctypes_signatures_match_header_arity():
+    """Every prototype in include/hnm_b200.h has as many parameters as its ctypes argtypes entry."""
+    from hnm_recommendation_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "hnm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"HNM_API\s+[\w\s\*]+?\b(hnm_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) == len(_lib._SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(_lib._SIGNATURES[name][1]), f"{name}: header has {n} parameters"
+
+
 def test_abi_version_and_strerror(hnm_lib):
     assert hnm_lib.hnm_abi_version() == 1
     assert hnm_lib.hnm_strerror(0) == b"ok"
