@@ -39,7 +39,9 @@ _SIGNATURES = {
     "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, I32, P, P, P]),
     "hnm_score_pack": (C.c_int, [P, P, I64, I64, I32, P, F32, P, P, P]),
     "hnm_absmax": (C.c_int, [P, I64, P, I32, P, P]),
-    "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, P, I32, P, P, P]),
+    "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, P, I32, P, P, P, I64, P]),
+    "hnm_score_topk_fused_workspace_bytes": (C.c_int64, [I64, I64]),
+    "hnm_score_topk_fused_plan": (C.c_int, [I64, I64, P]),
     "hnm_rescore_topk": (C.c_int, [P, P, P, I64, I32, I64, I64, P, I32, P, P, F64, F64, P, P, P, I32, P, P, P, P]),
     "hnm_merge_topk": (C.c_int, [P, P, I32, I64, I32, P, P, P]),
     "hnm_ncf_precompute": (C.c_int, [P, I64, I32, P, I32, I32, I32, P, P, P]),
@@ -95,6 +97,8 @@ def call(fn: str, *args) -> None:
     global LAUNCHES
     check(fn, getattr(load(), fn)(*args))
     n = _LAUNCHES_PER_CALL.get(fn, 1)
+    if fn == "hnm_score_topk_fused" and args[12] > 256:
+        n = 2                                     # + merge of the per-slice candidate lists
     if fn == "hnm_lightgcn_layer" and args[13]:
         n = 2 + (1 if args[14] else 0)            # cluster pass + whole-CTA pass over the long rows + warp-per-row pass
     LAUNCHES += n

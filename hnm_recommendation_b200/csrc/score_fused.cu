@@ -266,12 +266,85 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& 
   finish32<UPDATE>(q1, 3, item0 + 96, st, cand, cap);
 }
 
+// ----------------------------------------------------------------------------- work distribution
+// A pass = up to kMU user tiles against a range of item tiles, and it costs the same for one tile as for
+// three (the three tiles run concurrently).  Dealing whole tiles to the CTAs therefore quantises badly:
+// 1 340 tiles over 148 CTAs (one rank of an 8-GPU run) is 9.05 tiles per CTA = 4 passes instead of 3.02.
+// So every CTA runs `full_passes` passes of exactly kMU tiles over the whole catalog, and the left-over
+// tiles (fewer than kMU per CTA) are grouped in triples whose ITEM range is cut into `slices` slices, one
+// (triple, slice) per CTA.  A sliced user gets one candidate list and one tau per slice (split_* buffers);
+// merge_split_kernel then keeps the groups above the largest of the slice thresholds -- each slice's tau
+// is a lower bound on the kth_sel-th best score of a subset of the catalog, hence also of the catalog.
+struct SplitPlan {
+  int full_passes;      // passes of kMU tiles over the whole catalog, per CTA
+  int tile0;            // first left-over user tile (= gridDim.x * kMU * full_passes)
+  int triples;          // ceil(left-over tiles / kMU)
+  int slices;           // item-range slices per triple; triples * slices <= gridDim.x
+  uint2* cand;          // [left-over users][slices][cap]
+  int cap;
+  int32_t* count;       // [left-over users][slices]
+  float* thresh;        // [left-over users][slices]
+};
+
+struct PassDesc {
+  int t0, mc;           // user tiles [t0, t0 + mc)
+  int i0, ni;           // item tiles [i0, i0 + ni)
+  int boot;             // seed tiles (visited twice)
+  int rot;              // rotation of the sweep inside the range
+  int slice;            // >= 0: outputs go to the split buffers
+};
+
+__device__ __forceinline__ bool pass_desc(int n, int num_user_tiles, int num_item_tiles, int boot_tiles,
+                                          const SplitPlan& sp, PassDesc& p) {
+  const int b = (int)blockIdx.x;
+  if (n < sp.full_passes) {
+    p.t0 = (b * sp.full_passes + n) * kMU;
+    p.mc = kMU;
+    p.i0 = 0;
+    p.ni = num_item_tiles;
+    // every CTA sweeps the catalog from a different starting tile: otherwise all 148 SMs ask the L2 for
+    // the same 16 KB item tile at the same moment
+    p.rot = (int)(((long long)b * num_item_tiles) / (int)gridDim.x);
+    p.slice = -1;
+    p.boot = min(num_item_tiles, boot_tiles);
+    return true;
+  }
+  if (n > sp.full_passes || b >= sp.triples * sp.slices) return false;
+  const int j = b / sp.slices, sl = b - j * sp.slices;
+  p.t0 = sp.tile0 + j * kMU;
+  p.mc = min(kMU, num_user_tiles - p.t0);
+  p.i0 = (int)(((long long)sl * num_item_tiles) / sp.slices);
+  p.ni = (int)(((long long)(sl + 1) * num_item_tiles) / sp.slices) - p.i0;
+  p.rot = 0;
+  if (sp.slices > 1) {
+    p.slice = sl;
+    p.boot = max(1, min(boot_tiles, p.ni / 4));
+  } else {
+    p.slice = -1;
+    p.boot = min(p.ni, boot_tiles);
+  }
+  return true;
+}
+
+// index of a row's {list, count, tau}: the row itself, or (left-over row, slice)
+__device__ __forceinline__ uint32_t out_slot(const PassDesc& p, const SplitPlan& sp, int m, int q, int lane) {
+  const int row = (p.t0 + m) * kUserTile + q * 32 + lane;
+  return p.slice < 0 ? (uint32_t)row : (uint32_t)((row - sp.tile0 * kUserTile) * sp.slices + p.slice);
+}
+
+__device__ __forceinline__ int pass_tile(const PassDesc& p, int it) {
+  int t = (it < p.boot ? it : it - p.boot) + p.rot;
+  if (t >= p.ni) t -= p.ni;
+  return p.i0 + t;
+}
+
 // ----------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                         int num_users, int num_user_tiles, int num_item_tiles, int kth_sel,
                         uint2* __restrict__ cand, int cap, int32_t* __restrict__ cand_count,
-                        float* __restrict__ cand_thresh, int mode, int boot_tiles, int refresh_div) {
+                        float* __restrict__ cand_thresh, int mode, int boot_tiles, int refresh_div,
+                        const SplitPlan sp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                   // [2][kMU][kTileBytes]
@@ -280,16 +353,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int boot = num_item_tiles < boot_tiles ? num_item_tiles : boot_tiles;
-  const int num_iters = num_item_tiles + boot;
-  // user tiles are dealt out evenly: CTA b owns [t_begin, t_end) and walks it in passes of up to kMU
-  // tiles, so CTAs differ by at most one tile (a third of a pass), not by a whole pass
-  const int t_base = num_user_tiles / (int)gridDim.x, t_rem = num_user_tiles % (int)gridDim.x;
-  const int t_begin = (int)blockIdx.x * t_base + min((int)blockIdx.x, t_rem);
-  const int t_end = t_begin + t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
-  // every CTA sweeps the catalog from a different starting tile: otherwise all 148 SMs ask the L2 for
-  // the same 16 KB item tile at the same moment
-  const int rot = (int)(((long long)blockIdx.x * num_item_tiles) / (int)gridDim.x);
+  PassDesc p;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_users);
@@ -317,18 +381,17 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t g = 0;
-      int n = 0;
-      for (int t0 = t_begin; t0 < t_end; t0 += kMU, ++n) {
-        const int mc = min(kMU, t_end - t0);
+      for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
+        const int mc = p.mc;
         const int abuf = n & 1;
         mbar_wait(&bars->a_empty[abuf], ((n >> 1) & 1) ^ 1);
         mbar_expect_tx(&bars->a_full[abuf], mc * kTileBytes);
         for (int m = 0; m < mc; ++m)
           tma_load_2d(smem_a + (abuf * kMU + m) * kTileBytes, &map_users, &bars->a_full[abuf], 0,
-                      (t0 + m) * kUserTile);
+                      (p.t0 + m) * kUserTile);
+        const int num_iters = p.ni + p.boot;
         for (int it = 0; it < num_iters; ++it, ++g) {
-          int tile = (it < boot ? it : it - boot) + rot;
-          if (tile >= num_item_tiles) tile -= num_item_tiles;
+          const int tile = pass_tile(p, it);
           const int stage = g % kStagesB;
           mbar_wait(&bars->b_empty[stage], ((g / kStagesB) & 1) ^ 1);
           mbar_expect_tx(&bars->b_full[stage], kTileBytes);
@@ -345,11 +408,10 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     const int m = warp - 1;
     if (lane == 0) {
       uint32_t g = 0, uses = 0;
-      int n = 0;
       const uint64_t desc_hi = umma_desc_sw128(0) & ~uint64_t(0x3FFF);
-      for (int t0 = t_begin; t0 < t_end; t0 += kMU, ++n) {
-        const int mc = min(kMU, t_end - t0);
-        const bool active = m < mc;
+      for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
+        const int num_iters = p.ni + p.boot;
+        const bool active = m < p.mc;
         const int abuf = n & 1;
         mbar_wait(&bars->a_full[abuf], (n >> 1) & 1);
         tc_fence_after();
@@ -388,21 +450,30 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     uint32_t uses = 0;
     const uint32_t taddr = lane_base + m * kItemTile;
     uint64_t* t_empty = &bars->t_empty[m];
-    for (int t0 = t_begin; t0 < t_end; t0 += kMU) {
-      const int mc = min(kMU, t_end - t0);
-      if (m >= mc) continue;                                                // short last pass: this warpgroup rests
-      const int row = (t0 + m) * kUserTile + q * 32 + lane;
-      uint2* my_cand = cand + (size_t)(row < num_users ? row : 0) * cap;
-      const int my_cap = row < num_users ? cap : 0;      // padded rows count but never store
+    for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
+      if (m >= p.mc) continue;                                              // short pass: this warpgroup rests
+      const int boot = p.boot;
+      const int num_iters = p.ni + boot;
+      // where this row's candidates go: its own list, or its list for this item slice
+      const uint32_t slot = out_slot(p, sp, m, q, lane);
+      const bool real = (p.t0 + m) * kUserTile + q * 32 + lane < num_users;
+      const int out_cap = p.slice < 0 ? cap : sp.cap;
+      uint2* my_cand = (p.slice < 0 ? cand : sp.cand) + (size_t)(real ? slot : 0) * out_cap;
+      const int my_cap = real ? out_cap : 0;             // padded rows count but never store
       RowState rs;
       rs.tau = INFINITY;
       rs.cnt = 0;
 #pragma unroll
       for (int i = 0; i < kNumBuckets; ++i) rs.bm[i] = -INFINITY;
       int next_refresh = boot;
+      // item tile of this iteration.  Only whole-catalog passes are rotated, so the sweep wraps at the end of
+      // the catalog in both kinds of pass (a slice never gets there before its last iteration).
+      const int restart = p.i0 + p.rot;
+      int cur = restart;
       for (int it = 0; it < num_iters; ++it) {
-        int tile = (it < boot ? it : it - boot) + rot;
-        if (tile >= num_item_tiles) tile -= num_item_tiles;
+        if (it == boot) cur = restart;                   // the seed tiles are visited a second time
+        const int tile = cur;
+        if (++cur == num_item_tiles) cur = 0;
         if (it == next_refresh && mode == 0) {
           // it == boot: the seed pass is over, collecting starts (again from tile 0)
           rs.tau = refresh_tau(rs.bm, kth_sel);
@@ -428,9 +499,11 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
         }
       }
       if (mode == 0) rs.tau = refresh_tau(rs.bm, kth_sel);
-      if (row < num_users) {
-        cand_count[row] = rs.cnt;
-        cand_thresh[row] = rs.tau;
+      pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p);      // recomputed: not kept live in the loop
+      if ((p.t0 + m) * kUserTile + q * 32 + lane < num_users) {
+        const uint32_t slot2 = out_slot(p, sp, m, q, lane);
+        (p.slice < 0 ? cand_count : sp.count)[slot2] = rs.cnt;
+        (p.slice < 0 ? cand_thresh : sp.thresh)[slot2] = rs.tau;
       }
     }
   }
@@ -440,6 +513,87 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// One warp per sliced user.  thr0 = max of the slice thresholds is a valid threshold (every group that a
+// slice did not store has a maximum <= that slice's tau <= thr0), but a loose one: a slice's tau is the
+// kth_sel-th best of a fraction of the catalog.  The stored group maxima belong to distinct items, so the
+// kth_sel-th largest of them over all slices is again a lower bound on the kth_sel-th best score, and every
+// group above it is stored.  thr = max(thr0, that); the groups above thr are gathered into the user's
+// ordinary list.  What hnm_rescore_topk's certificate assumes holds: every item outside the kept groups
+// scored <= thr.
+__device__ __forceinline__ void cmpx_lane(float& v, int lane, int stride, bool desc) {
+  const float o = __shfl_xor_sync(0xffffffffu, v, stride);
+  const bool lower = (lane & stride) == 0;
+  v = (lower == desc) ? fmaxf(v, o) : fminf(v, o);    // best-first block: the lower lane keeps the larger value
+}
+
+__global__ void __launch_bounds__(128)
+merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, uint2* __restrict__ cand, int cap,
+                   int32_t* __restrict__ cand_count, float* __restrict__ cand_thresh) {
+  const int lane = threadIdx.x & 31;
+  const int lu = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int row = sp.tile0 * kUserTile + lu;
+  if (row >= num_users) return;
+  const size_t base = (size_t)lu * sp.slices;
+  float thr = -INFINITY;
+  bool over = false;
+  for (int s = lane; s < sp.slices; s += 32) {
+    thr = fmaxf(thr, sp.thresh[base + s]);
+    over |= sp.count[base + s] > sp.cap;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) thr = fmaxf(thr, __shfl_xor_sync(0xffffffffu, thr, off));
+  over = __any_sync(0xffffffffu, over);
+  if (over) {                      // a slice ran out of room: the user is not certifiable from these lists
+    if (lane == 0) {
+      cand_count[row] = cap + 1;
+      cand_thresh[row] = INFINITY;
+    }
+    return;
+  }
+  // kth_sel-th largest stored group maximum: running top 32 over all slice lists, lane i = (i+1)-th largest
+  float top = -INFINITY;
+  for (int s = 0; s < sp.slices; ++s) {
+    const int cnt = sp.count[base + s];
+    const uint2* in = sp.cand + (base + s) * sp.cap;
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      float v = i0 + lane < cnt ? __uint_as_float(in[i0 + lane].x) : -INFINITY;
+      if (!__any_sync(0xffffffffu, v > thr)) continue;          // nothing here can move a threshold above thr0
+#pragma unroll
+      for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_lane(v, lane, stride, (lane & size) == 0);
+      }
+      top = fmaxf(top, __shfl_sync(0xffffffffu, v, 31 - lane));
+#pragma unroll
+      for (int stride = 16; stride > 0; stride >>= 1) cmpx_lane(top, lane, stride, true);
+    }
+  }
+  thr = fmaxf(thr, __shfl_sync(0xffffffffu, top, kth_sel - 1));
+  uint2* out = cand + (size_t)row * cap;
+  int total = 0;
+  for (int s = 0; s < sp.slices; ++s) {
+    const int cnt = sp.count[base + s];
+    const uint2* in = sp.cand + (base + s) * sp.cap;
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      const int i = i0 + lane;
+      uint2 c = make_uint2(0u, 0u);
+      bool keep = false;
+      if (i < cnt) {
+        c = in[i];
+        keep = __uint_as_float(c.x) > thr;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      const int pos = total + __popc(mask & ((1u << lane) - 1u));
+      if (keep && pos < cap) out[pos] = c;
+      total += __popc(mask);
+    }
+  }
+  if (lane == 0) {
+    cand_count[row] = total;       // > cap: overflow, flagged by hnm_rescore_topk
+    cand_thresh[row] = total > cap ? INFINITY : thr;
   }
 }
 
@@ -694,6 +848,272 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
   }
 }
 
+// ----------------------------------------------------------------------------- rescoring, dim = 64
+// The first version of this kernel ran the fp64 chain for every item of every kept group (~70 per
+// user) and spent 57 % of its stall samples on F2F.F64.F32 (two fp32->fp64 conversions per DFMA at
+// 16 conversions/clk/SM; profiles/r1_bench.md).  Now:
+//   pass 1  fp32: a_j = fl(u.x_j) and s_j = fl(sum |u_k x_k|) for every candidate item, rows staged by
+//           half warps into shared memory.  |a_j - u.x_j| <= gamma_64 * sum|u_k x_k|, so
+//           lo_j = a_j - 2^-17 s_j <= u.x_j <= a_j + 2^-17 s_j = up_j  (2^-17 = 2 * 64 * 2^-24).
+//           T = k-th largest lo_j (warp-wide bitonic merge of the running top 32).  An item with
+//           up_j < T has k items strictly above it and can be dropped; so can an item with up_j <= cut.
+//   pass 2  fp64, survivors only (k plus the near ties, 16 per round): the half warp that stages a row
+//           writes the PRODUCTS u_k * x_jk as doubles (exact: 24 + 24 significant bits), lane j then adds
+//           them in the order k = 0..63.  round(p + acc) is what fma(u, x, acc) returns when p is exact,
+//           so the scores are bit-identical to the fp64 fma chain of the oracle and of hnm_topk_exact.
+// The certificate is unchanged: every item with an exact score above the cut among the top k survives
+// pass 1, so "k contenders above the cut" holds for the same users as before.
+constexpr int kRows2 = 16;                 // items per pass-2 round
+constexpr int kStride1 = 68;               // floats per staged fp32 row (16-byte aligned, LDS.128 conflict free)
+constexpr int kStride2 = 65;               // doubles per staged product row
+constexpr int kMaxSel = 128;               // pass-1 survivors a user may have (more: not certified)
+static_assert(32 * kStride1 * 4 <= kRows2 * kStride2 * 8 + 384, "tile union");
+
+struct __align__(16) RescoreSmem {
+  double tile[kRows2 * kStride2 + 48];     // pass 1: float [32][kStride1]; pass 2: double [16][kStride2]
+  double sc[kMaxContenders];               // pass 1: float up[256]; pass 2 on: contender scores
+  float uf[kDim];
+  int id[kMaxContenders];
+  uint32_t col[kMaxGroups];
+  uint8_t sel[kMaxSel];
+};
+
+__device__ __forceinline__ void cmpx_desc(float& v, int lane, int stride, bool desc) {
+  const float o = __shfl_xor_sync(0xffffffffu, v, stride);
+  const bool lower = (lane & stride) == 0;
+  // in a best-first block the lower lane keeps the larger value
+  v = (lower == desc) ? fmaxf(v, o) : fminf(v, o);
+}
+
+__global__ void __launch_bounds__(kRescoreWarps * 32)
+rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
+                 const int64_t* __restrict__ user_ids, int64_t batch, int64_t item_begin, int num_items_local,
+                 const uint2* __restrict__ cand, int cap, const int32_t* __restrict__ cand_count,
+                 const float* __restrict__ cand_thresh, double inv_scale, double max_item_norm,
+                 const float* __restrict__ center, const int64_t* __restrict__ excl_ptr,
+                 const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
+                 double* __restrict__ out_scores, int32_t* __restrict__ certified) {
+  __shared__ RescoreSmem smem[kRescoreWarps];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * kRescoreWarps + wib;
+  if (b >= batch) return;
+  RescoreSmem& sm = smem[wib];
+  float* tile1 = reinterpret_cast<float*>(sm.tile);
+  float* s_up = reinterpret_cast<float*>(sm.sc);
+  const int64_t uid = user_ids ? user_ids[b] : b;
+  const float* urow = user_emb + (size_t)uid * kDim;
+  const int raw = cand_count[b];
+  const int n = min(raw, cap);
+  const float thr = cand_thresh[b];
+  const uint2* mine = cand + (size_t)b * cap;
+  int64_t ex_lo = 0, ex_hi = 0;
+  if (excl_ptr) { ex_lo = excl_ptr[b]; ex_hi = excl_ptr[b + 1]; }
+  const int half = lane >> 4, sub = lane & 15;
+
+  // 1. keep the groups whose maximum ended above the final threshold, compacted: slot j = kept group j
+  int groups = 0;
+#pragma unroll
+  for (int e = 0; e < kMaxPerLane; ++e) {
+    const int idx = lane + 32 * e;
+    uint2 c = make_uint2(0u, 0u);
+    bool keep = false;
+    if (idx < n) {
+      c = mine[idx];
+      keep = __uint_as_float(c.x) > thr;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    const int pos = groups + __popc(mask & ((1u << lane) - 1u));
+    if (keep && pos < kMaxGroups) sm.col[pos] = c.y;
+    groups += __popc(mask);
+  }
+  const bool too_many = groups > kMaxGroups;
+  groups = min(groups, kMaxGroups);
+
+  // the user's row: fp32 copy in shared memory for pass 1, this lane's four values as doubles for pass 2
+  const float4 uf = ldg_f4(urow + sub * 4);
+  if (half == 0) *reinterpret_cast<float4*>(sm.uf + sub * 4) = uf;
+  const double ud0 = (double)uf.x, ud1 = (double)uf.y, ud2 = (double)uf.z, ud3 = (double)uf.w;
+  double un = 0.0, uc = 0.0, uc_abs = 0.0;
+  if (half == 0) {
+    un = fma(ud0, ud0, un); un = fma(ud1, ud1, un); un = fma(ud2, ud2, un); un = fma(ud3, ud3, un);
+    if (center) {
+      const float4 cf = ldg_f4(center + sub * 4);
+      const double c0 = (double)cf.x, c1 = (double)cf.y, c2 = (double)cf.z, c3 = (double)cf.w;
+      uc = fma(ud0, c0, uc); uc = fma(ud1, c1, uc); uc = fma(ud2, c2, uc); uc = fma(ud3, c3, uc);
+      uc_abs = fabs(ud0 * c0) + fabs(ud1 * c1) + fabs(ud2 * c2) + fabs(ud3 * c3);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    un += __shfl_xor_sync(0xffffffffu, un, off);
+    uc += __shfl_xor_sync(0xffffffffu, uc, off);
+    uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
+  }
+  un = sqrt(un);
+  // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
+  const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)kDim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
+  const double cut = (double)thr * inv_scale + eps + uc;
+  const float cutf = __double2float_rd(cut);                // up_j <= cutf  =>  u.x_j <= cut
+  __syncwarp();
+
+  // 2. pass 1: fp32 scores with a rigorous error radius, running top-32 of the lower bounds
+  const int num_cand_items = groups * kGroup;
+  float top = -INFINITY;                                    // lane i: (i+1)-th largest lower bound so far
+  for (int base = 0; base < num_cand_items; base += 32) {
+    const int it = base + lane;
+    int item = -1;
+    if (it < num_cand_items) item = (int)sm.col[it / kGroup] + (it % kGroup);
+    bool live = item >= 0 && item < num_items_local;        // columns past the catalog are zero padding
+    if (live && ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)item)) live = false;
+    const int litem = live ? item : -1;
+#pragma unroll
+    for (int h0 = 0; h0 < 16; h0 += 8) {
+      float4 v[8];
+      int il[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        il[s] = __shfl_sync(0xffffffffu, litem, 2 * (h0 + s) + half);
+        v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (il[s] >= 0) v[s] = ldg_f4(item_emb + (size_t)il[s] * kDim + sub * 4);
+      }
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        *reinterpret_cast<float4*>(tile1 + (2 * (h0 + s) + half) * kStride1 + sub * 4) = v[s];
+    }
+    __syncwarp();
+    float a = 0.f, sabs = 0.f;
+    {
+      const float* t = tile1 + lane * kStride1;
+#pragma unroll
+      for (int kk = 0; kk < kDim; kk += 4) {
+        const float4 u4 = *reinterpret_cast<const float4*>(sm.uf + kk);
+        const float4 x4 = *reinterpret_cast<const float4*>(t + kk);
+        a = fmaf(u4.x, x4.x, a); sabs = fmaf(fabsf(u4.x), fabsf(x4.x), sabs);
+        a = fmaf(u4.y, x4.y, a); sabs = fmaf(fabsf(u4.y), fabsf(x4.y), sabs);
+        a = fmaf(u4.z, x4.z, a); sabs = fmaf(fabsf(u4.z), fabsf(x4.z), sabs);
+        a = fmaf(u4.w, x4.w, a); sabs = fmaf(fabsf(u4.w), fabsf(x4.w), sabs);
+      }
+    }
+    // radius: 2 * gamma_64 * s covers the rounding of s itself and of a -+ radius; the absolute term covers
+    // products that underflow in fp32
+    const float rad = fmaf(sabs, 7.62939453125e-6f, 1e-36f);
+    const float up = live ? a + rad : -INFINITY;
+    float lo = live ? a - rad : -INFINITY;
+    s_up[it] = up;
+    // sort this round's lower bounds best-first, fold them into the running top 32
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_desc(lo, lane, stride, (lane & size) == 0);
+    }
+    top = fmaxf(top, __shfl_sync(0xffffffffu, lo, 31 - lane));   // bitonic: holds the 32 largest of both
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) cmpx_desc(top, lane, stride, true);
+    __syncwarp();
+  }
+  const float T = __shfl_sync(0xffffffffu, top, k - 1);       // -inf when fewer than k live candidates
+
+  // 3. survivors of pass 1
+  int nsel = 0;
+  for (int base = 0; base < num_cand_items; base += 32) {
+    const float up = s_up[base + lane];
+    const bool s = up >= T && up > cutf;
+    const unsigned mask = __ballot_sync(0xffffffffu, s);
+    const int pos = nsel + __popc(mask & ((1u << lane) - 1u));
+    if (s && pos < kMaxSel) sm.sel[pos] = (uint8_t)(base + lane);
+    nsel += __popc(mask);
+  }
+  const bool sel_overflow = nsel > kMaxSel;
+  if (sel_overflow) nsel = 0;
+  __syncwarp();                                             // s_up is dead from here on: sm.sc takes its place
+
+  // 4. pass 2: exact scores of the survivors; contenders = strictly above the cut
+  int total = 0;
+  for (int base = 0; base < nsel; base += kRows2) {
+#pragma unroll
+    for (int s = 0; s < kRows2 / 2; ++s) {
+      const int l = 2 * s + half;
+      if (base + l < nsel) {
+        const int it = sm.sel[base + l];
+        const int item = (int)sm.col[it / kGroup] + (it % kGroup);
+        const float4 v = ldg_f4(item_emb + (size_t)item * kDim + sub * 4);
+        double* t = sm.tile + l * kStride2 + sub * 4;
+        t[0] = ud0 * (double)v.x; t[1] = ud1 * (double)v.y; t[2] = ud2 * (double)v.z; t[3] = ud3 * (double)v.w;
+      }
+    }
+    __syncwarp();
+    double acc = 0.0;
+    int item = -1;
+    const bool mine2 = lane < kRows2 && base + lane < nsel;
+    if (mine2) {
+      const int it = sm.sel[base + lane];
+      item = (int)sm.col[it / kGroup] + (it % kGroup);
+      const double* t = sm.tile + lane * kStride2;
+#pragma unroll 16
+      for (int kk = 0; kk < kDim; ++kk) acc = __dadd_rn(t[kk], acc);   // == fma(u_k, x_k, acc): the product is exact
+    }
+    const bool c = mine2 && acc > cut;
+    const unsigned mask = __ballot_sync(0xffffffffu, c);
+    const int pos = total + __popc(mask & ((1u << lane) - 1u));
+    if (c) { sm.sc[pos] = acc; sm.id[pos] = item; }           // pos < nsel <= kMaxSel = kMaxContenders
+    total += __popc(mask);
+    __syncwarp();
+  }
+  if (total <= 32) {
+    // the rule: one contender per lane, one warp-wide bitonic sort
+    double ms = lane < total ? sm.sc[lane] : -INFINITY;
+    int mi = lane < total ? sm.id[lane] : INT32_MAX;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, ms, stride);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, stride);
+        const bool lower = (lane & stride) == 0;
+        const bool desc = (lane & size) == 0;
+        const bool other_first = before32(os, oi, ms, mi);
+        const bool take = (lower == desc) ? other_first : !other_first && !(os == ms && oi == mi);
+        if (take) { ms = os; mi = oi; }
+      }
+    }
+    if (lane < k) {
+      out_ids[(size_t)b * k + lane] = mi == INT32_MAX ? INT64_MAX : item_begin + (int64_t)mi;
+      out_scores[(size_t)b * k + lane] = ms;
+    }
+  } else {
+    // the exception (many near ties around the k-th score): k rounds of warp argmax over the list
+    for (int t = 0; t < k; ++t) {
+      double bs = -INFINITY;
+      int bi = INT32_MAX, bp = -1;
+      for (int p = lane; p < total; p += 32) {
+        const double x = sm.sc[p];
+        const int xi = sm.id[p];
+        if (before32(x, xi, bs, bi)) { bs = x; bi = xi; bp = p; }
+      }
+      double ws = bs;
+      int wi = bi;
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, ws, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
+        if (before32(os, oi, ws, wi)) { ws = os; wi = oi; }
+      }
+      if (bp >= 0 && wi == bi && ws == bs) { sm.sc[bp] = -INFINITY; sm.id[bp] = INT32_MAX; }
+      __syncwarp();
+      if (lane == 0) {
+        out_ids[(size_t)b * k + t] = item_begin + (int64_t)wi;
+        out_scores[(size_t)b * k + t] = ws;
+      }
+    }
+  }
+  if (lane == 0) {
+    // bit 0: provably exact; bits 1.. say why not (list overflow, > 64 groups, < k contenders, > 128 survivors)
+    const int why = (raw > cap ? 2 : 0) | (too_many ? 4 : 0) | (total < k ? 8 : 0) | (sel_overflow ? 16 : 0);
+    certified[b] = why == 0 ? 1 : why;
+  }
+}
+
 int make_map(CUtensorMap* map, const void* base, int64_t rows) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
@@ -743,10 +1163,67 @@ extern "C" int hnm_score_pack(const float* emb, const int64_t* row_ids, int64_t 
   return HNM_OK;
 }
 
+namespace {
+constexpr int kSplitCap = 256;      // candidate entries per (sliced user, item slice)
+constexpr int kMinSliceTiles = 32;  // an item slice is at least this many item tiles
+
+// The work distribution of one launch (see SplitPlan); pointers are filled in by the caller.
+SplitPlan make_plan(int num_user_tiles, int num_item_tiles, int grid) {
+  SplitPlan sp{};
+  static const bool no_split = getenv("HNM_FUSED_NOSPLIT") != nullptr;      // A/B switch for profiling
+  sp.full_passes = num_user_tiles / (grid * kMU);
+  sp.tile0 = grid * kMU * sp.full_passes;
+  const int left = num_user_tiles - sp.tile0;
+  sp.triples = (left + kMU - 1) / kMU;
+  sp.slices = 0;
+  if (sp.triples > 0) {
+    sp.slices = std::max(1, std::min(grid / sp.triples, num_item_tiles / kMinSliceTiles));
+    if (no_split) sp.slices = 1;
+  }
+  sp.cap = kSplitCap;
+  return sp;
+}
+
+int fused_grid(int num_user_tiles) {
+  static const bool no_split = getenv("HNM_FUSED_NOSPLIT") != nullptr;
+  if (no_split) return std::min((num_user_tiles + kMU - 1) / kMU, hnm_num_sms());
+  return hnm_num_sms();
+}
+
+size_t split_bytes(const SplitPlan& sp, size_t* off_count, size_t* off_thresh) {
+  if (sp.slices <= 1) { *off_count = *off_thresh = 0; return 0; }
+  const size_t slots = (size_t)sp.triples * kMU * kUserTile * sp.slices;
+  *off_count = slots * kSplitCap * sizeof(uint2);
+  *off_thresh = *off_count + slots * sizeof(int32_t);
+  return *off_thresh + slots * sizeof(float);
+}
+}  // namespace
+
+extern "C" int64_t hnm_score_topk_fused_workspace_bytes(int64_t users_padded, int64_t items_padded) {
+  if (users_padded <= 0 || items_padded <= 0 || users_padded % kUserTile || items_padded % kItemTile ||
+      users_padded > INT32_MAX || items_padded > INT32_MAX)
+    return -1;
+  const int tiles = (int)(users_padded / kUserTile);
+  size_t a, b;
+  return (int64_t)split_bytes(make_plan(tiles, (int)(items_padded / kItemTile), fused_grid(tiles)), &a, &b) + 256;
+}
+
+extern "C" int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_padded, int32_t* out5) {
+  if (!out5) return HNM_E_NULL;
+  if (users_padded <= 0 || items_padded <= 0 || users_padded % kUserTile || items_padded % kItemTile ||
+      users_padded > INT32_MAX || items_padded > INT32_MAX)
+    return HNM_E_RANGE;
+  const int tiles = (int)(users_padded / kUserTile);
+  const int grid = fused_grid(tiles);
+  const SplitPlan sp = make_plan(tiles, (int)(items_padded / kItemTile), grid);
+  out5[0] = grid; out5[1] = sp.full_passes; out5[2] = sp.tile0; out5[3] = sp.triples; out5[4] = sp.slices;
+  return HNM_OK;
+}
+
 extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, int64_t users_padded,
                                     const void* items_f16, int64_t num_items, int64_t items_padded, int32_t kth_sel,
                                     void* cand, int32_t cand_cap, int32_t* cand_count, float* cand_thresh,
-                                    void* stream_) {
+                                    void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!users_f16 || !items_f16 || !cand || !cand_count || !cand_thresh) return HNM_E_NULL;
   if (num_users <= 0 || num_items <= 0 || users_padded < num_users || items_padded < num_items) return HNM_E_RANGE;
@@ -770,11 +1247,32 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   static const int refresh_div = getenv("HNM_FUSED_REFRESH") ? std::max(1, atoi(getenv("HNM_FUSED_REFRESH"))) : 4;
   const int num_user_tiles = (int)(users_padded / kUserTile);
   const int num_tiles = (int)(items_padded / kItemTile);
-  const int grid = std::min((num_user_tiles + kMU - 1) / kMU, hnm_num_sms());
+  const int grid = fused_grid(num_user_tiles);
+  SplitPlan sp = make_plan(num_user_tiles, num_tiles, grid);
+  size_t off_count = 0, off_thresh = 0;
+  const size_t need = split_bytes(sp, &off_count, &off_thresh);
+  if (need > 0) {
+    if (!workspace) return HNM_E_NULL;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    if ((int64_t)(need + (size_t)(ws - reinterpret_cast<uint8_t*>(workspace))) > workspace_bytes) return HNM_E_WORKSPACE;
+    sp.cand = reinterpret_cast<uint2*>(ws);
+    sp.count = reinterpret_cast<int32_t*>(ws + off_count);
+    sp.thresh = reinterpret_cast<float*>(ws + off_thresh);
+  }
   score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_u, map_i, (int)num_users, num_user_tiles,
                                                                   num_tiles, kth_sel, (uint2*)cand,
-                                                                  cand_cap, cand_count, cand_thresh, debug_mode, boot_tiles, refresh_div);
+                                                                  cand_cap, cand_count, cand_thresh, debug_mode, boot_tiles,
+                                                                  refresh_div, sp);
   HNM_LAUNCH_CHECK();
+  if (need > 0 && debug_mode == 0) {
+    const int64_t split_users = std::min<int64_t>((int64_t)sp.triples * kMU * kUserTile,
+                                                  num_users - (int64_t)sp.tile0 * kUserTile);
+    if (split_users > 0) {
+      merge_split_kernel<<<(unsigned)((split_users + 3) / 4), 128, 0, stream>>>(sp, (int)num_users, kth_sel, (uint2*)cand, cand_cap,
+                                                                                cand_count, cand_thresh);
+      HNM_LAUNCH_CHECK();
+    }
+  }
   return HNM_OK;
 }
 
@@ -794,6 +1292,16 @@ extern "C" int hnm_rescore_topk(const float* user_emb, const float* item_emb, co
       num_items_local < 1 || num_items_local > INT32_MAX)
     return HNM_E_RANGE;
   const int wpc = kRescoreWarps;
+  static const bool generic = getenv("HNM_RESCORE_GENERIC") != nullptr;     // A/B switch for profiling
+  if (dim == kDim && !generic && hnm_aligned16(user_emb) && hnm_aligned16(item_emb) &&
+      (!center || hnm_aligned16(center))) {
+    rescore64_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
+        user_emb, item_emb, user_ids, batch, item_begin, (int)num_items_local, (const uint2*)cand, cand_cap,
+        cand_count, cand_thresh, inv_scale_product, max_item_norm, center, excl_ptr, excl_items, k, out_ids,
+        out_scores, out_certified);
+    HNM_LAUNCH_CHECK();
+    return HNM_OK;
+  }
   rescore_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
       user_emb, item_emb, user_ids, batch, dim, item_begin, (int)num_items_local, (const uint2*)cand, cand_cap,
       cand_count, cand_thresh,

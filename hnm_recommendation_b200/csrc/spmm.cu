@@ -103,7 +103,7 @@ __device__ __forceinline__ void warp_gather(const int32_t* __restrict__ col, con
 // e = dis_i * sum;  xs_out = dis_i * e;  acc += alpha * e   (lightgcn.py:152,158)
 __device__ __forceinline__ void row_epilogue(float4 s, float di, float alpha, float* __restrict__ xs_out_p,
                                              float* __restrict__ acc_p, int partial = 0) {
-  if (partial) {          // raw neighbour sum of a sub-range: normalisation happens after the all-reduce
+  if (partial & 1) {      // raw neighbour sum of a sub-range: normalisation happens after the all-reduce
     *reinterpret_cast<float4*>(xs_out_p) = s;
     return;
   }
@@ -111,6 +111,14 @@ __device__ __forceinline__ void row_epilogue(float4 s, float di, float alpha, fl
   if (xs_out_p) {
     float4 x = make_float4(__fmul_rn(di, e.x), __fmul_rn(di, e.y), __fmul_rn(di, e.z), __fmul_rn(di, e.w));
     *reinterpret_cast<float4*>(xs_out_p) = x;
+  }
+  if (partial & 2) {
+    // acc += alpha * e as a fire-and-forget vector reduction in L2: the warp does not wait for the old
+    // value to come back (one writer per element, so the result is the same round-to-nearest add).
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc_p), "f"(__fmul_rn(alpha, e.x)),
+                 "f"(__fmul_rn(alpha, e.y)), "f"(__fmul_rn(alpha, e.z)), "f"(__fmul_rn(alpha, e.w))
+                 : "memory");
+    return;
   }
   float4 a = *reinterpret_cast<const float4*>(acc_p);
   a.x = __fadd_rn(a.x, __fmul_rn(alpha, e.x));
@@ -139,8 +147,8 @@ spmm_rows_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const fl
     float4 acc[S::VEC];
     warp_gather<D, WEIGHTED>(col, w, xs_in, beg, end, lane, acc);
     if (lane < S::LPR) {
-      const float di = partial ? 1.f : __ldg(dis + row);
-      const size_t orow = partial ? (size_t)(row - seg.off) : (size_t)row;
+      const float di = (partial & 1) ? 1.f : __ldg(dis + row);
+      const size_t orow = (partial & 1) ? (size_t)(row - seg.off) : (size_t)row;
 #pragma unroll
       for (int t = 0; t < S::VEC; ++t) {
         const size_t off = orow * D + (size_t)(t * S::LPR + lane) * 4;
@@ -179,8 +187,8 @@ spmm_heavy_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const f
     float4 s = part[0][threadIdx.x];
 #pragma unroll
     for (int k = 1; k < NW; ++k) add4(s, part[k][threadIdx.x]);
-    const size_t off = (partial ? (size_t)(row - seg.off) : (size_t)row) * D + (size_t)threadIdx.x * 4;
-    row_epilogue(s, partial ? 1.f : __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
+    const size_t off = ((partial & 1) ? (size_t)(row - seg.off) : (size_t)row) * D + (size_t)threadIdx.x * 4;
+    row_epilogue(s, (partial & 1) ? 1.f : __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
   }
 }
 
@@ -230,8 +238,8 @@ spmm_huge_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const fl
       const float4* remote = cluster.map_shared_rank(cta_sum, r);
       add4(s, remote[threadIdx.x]);
     }
-    const size_t off = (partial ? (size_t)(row - seg.off) : (size_t)row) * D + (size_t)threadIdx.x * 4;
-    row_epilogue(s, partial ? 1.f : __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
+    const size_t off = ((partial & 1) ? (size_t)(row - seg.off) : (size_t)row) * D + (size_t)threadIdx.x * 4;
+    row_epilogue(s, (partial & 1) ? 1.f : __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
   }
   cluster.sync();                                          // keep every CTA's shared memory alive until read
 }
@@ -397,7 +405,7 @@ int dispatch_layer(int dim, Seg seg, int partial, const int32_t* col, const floa
   const int64_t rows = row_end - row_begin;
   const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   if (grid > 0) {
-    spmm_generic_kernel<WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(seg, partial, col, w, dis, xs_in, xs_out, acc,
+    spmm_generic_kernel<WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(seg, partial & 1, col, w, dis, xs_in, xs_out, acc,
                                                                        alpha, dim, row_begin, row_end);
     HNM_LAUNCH_CHECK();
   }
@@ -440,10 +448,12 @@ extern "C" int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_
   if (dim % 4 == 0 && !(hnm_aligned16(xs_in) && hnm_aligned16(acc) && (!xs_out || hnm_aligned16(xs_out))))
     return HNM_E_ALIGN;
   if (row_begin == row_end) return HNM_OK;
+  // bit 1 of the mode word: layer sum by red.global.add instead of load + add + store (A/B switch)
+  static const int red_mode = (getenv("HNM_SPMM_RED") ? atoi(getenv("HNM_SPMM_RED")) : 1) ? 2 : 0;
   if (csr_w)
-    return dispatch_layer<true>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0}, 0, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+    return dispatch_layer<true>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0}, red_mode, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
                                 heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
-  return dispatch_layer<false>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0}, 0, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+  return dispatch_layer<false>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0}, red_mode, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
 }
 

@@ -22,7 +22,7 @@ CAND_CAP = 256
 K_MAX = 16
 SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maximum
 MAX_USERS_PER_LAUNCH = 1 << 21
-TIER2_MIN_USERS = 384
+TIER2_MIN_USERS = 32
 
 
 def _pow2_scale(absmax: float) -> float:
@@ -108,8 +108,9 @@ class FusedScorer:
                 bad_uids = bad if uids is None else uids[bad]
                 sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev) if excl[0] is not None else (None, None)
                 sel2 = min(32, k + 12)
-                # a second tensor-core pass pays off only when it fills a good part of the machine;
-                # a handful of users go straight to the exact kernel (which splits the catalog over CTAs)
+                # the second tensor-core pass slices the item range of its few user tiles over the CTAs
+                # (SplitPlan in csrc/score_fused.cu), so it is cheap for any count; only a handful of users
+                # go straight to the exact kernel (which splits the catalog over CTAs too)
                 if sel2 > sel and n_bad >= TIER2_MIN_USERS:
                     ids2 = torch.empty(n_bad, k, dtype=torch.int64, device=dev)
                     sc2 = torch.empty(n_bad, k, dtype=torch.float64, device=dev)
@@ -171,10 +172,14 @@ class FusedScorer:
             cand = torch.empty(n, CAND_CAP, 2, dtype=torch.int32, device=dev)
             count = torch.empty(n, dtype=torch.int32, device=dev)
             thresh = torch.empty(n, dtype=torch.float32, device=dev)
+            ws_bytes = int(_lib.load().hnm_score_topk_fused_workspace_bytes(padded, self.items_padded))
+            if ws_bytes < 0:
+                raise ValueError("bad padded sizes for the fused scorer")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             note("pack_end")
             note("fused_begin")
             call("hnm_score_topk_fused", ptr(users_f16), n, padded, ptr(self.items_f16), self.num_items,
-                 self.items_padded, sel, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), s)
+                 self.items_padded, sel, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(ws), ws_bytes, s)
             note("fused_end")
             ex_ptr = excl[0][b0:b1 + 1] if excl[0] is not None else None
             note("rescore_begin")

@@ -196,7 +196,16 @@ HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */,
                          int32_t kth_sel /* 1..32 */,
                          void* cand /* [num_users, cand_cap] x {uint32 score bits, uint32 local item} */,
                          int32_t cand_cap, int32_t* cand_count /* [num_users] */,
-                         float* cand_thresh /* [num_users] final tau (scaled units) */, void* stream);
+                         float* cand_thresh /* [num_users] final tau (scaled units) */,
+                         void* workspace /* hnm_score_topk_fused_workspace_bytes(), may be NULL when that is 0 */,
+                         int64_t workspace_bytes, void* stream);
+/* Scratch for the user tiles that do not fill a whole pass of the persistent grid: their item range is cut
+ * into slices handled by different CTAs, with one candidate list per (user, slice) that a second kernel
+ * merges into `cand` (at most ~30 MB).  < 0 on bad sizes. */
+HNM_API int64_t hnm_score_topk_fused_workspace_bytes(int64_t users_padded, int64_t items_padded);
+/* Host only: how the launch distributes its work.  out5 = {grid, full passes per CTA (3 user tiles x whole
+ * catalog each), first left-over user tile, left-over triples, item slices per triple}. */
+HNM_API int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_padded, int32_t* out5);
 HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb /* local shard rows */,
                      const int64_t* user_ids /* NULL = identity */, int64_t batch, int32_t dim, int64_t item_begin,
                      int64_t num_items_local /* rows of item_emb; columns past it are zero padding */,

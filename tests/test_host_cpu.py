@@ -102,3 +102,34 @@ def test_metrics_standin():
     assert set(out) == {"map_at_k", "recall_at_k", "precision_at_k", "ndcg_at_k"}
     assert out["recall_at_k"] == pytest.approx(0.5) and out["precision_at_k"] == pytest.approx(1 / 3)
     assert out["map_at_k"] == pytest.approx((1 + 2 / 3) / 2 / 2)
+
+
+@pytest.mark.parametrize("user_tiles,item_tiles", [(1, 2), (8, 825), (63, 40), (444, 825), (1340, 825),
+                                                   (10719, 825), (2680, 825), (445, 9), (7, 3)])
+def test_fused_work_plan_covers_every_tile_pair_once(hnm_lib, user_tiles, item_tiles):
+    """hnm_score_topk_fused_plan: whole-catalog passes of 3 user tiles per CTA, the left-over tiles in triples
+    whose item range is sliced over the CTAs -- every (user tile, item tile) pair belongs to exactly one CTA."""
+    import ctypes as C
+    out = (C.c_int32 * 5)()
+    assert hnm_lib.hnm_score_topk_fused_plan(user_tiles * 128, item_tiles * 128, out) == 0
+    grid, full, tile0, triples, slices = list(out)
+    assert grid >= 1 and tile0 == grid * 3 * full and 0 <= user_tiles - tile0 < 3 * grid
+    assert triples == -(-(user_tiles - tile0) // 3)
+    if triples:
+        assert 1 <= slices and triples * slices <= grid
+    seen = np.zeros((user_tiles, item_tiles), dtype=np.int32)
+    for b in range(grid):
+        for n in range(full):                       # CTA b, pass n: tiles (b*full + n)*3 .. +3, all items
+            t0 = (b * full + n) * 3
+            seen[t0:t0 + 3, :] += 1
+        if b < triples * slices:
+            j, sl = divmod(b, slices)
+            t0 = tile0 + 3 * j
+            i0, i1 = sl * item_tiles // slices, (sl + 1) * item_tiles // slices
+            assert i1 > i0
+            seen[t0:min(t0 + 3, user_tiles), i0:i1] += 1
+    assert (seen == 1).all()
+    ws = hnm_lib.hnm_score_topk_fused_workspace_bytes(user_tiles * 128, item_tiles * 128)
+    need = triples * 3 * 128 * slices * (256 * 8 + 8) if slices > 1 else 0
+    assert ws >= need and ws <= need + 4096
+    assert hnm_lib.hnm_score_topk_fused_workspace_bytes(100, 128) < 0
