@@ -232,9 +232,23 @@ __device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col
       st.tau = INFINITY;
       st.cnt = cap + 1;
     } else {
+      // eight PREDICATED stores, no branches: ptxas turned the plain `if (q[h] > tau) cand[cnt++] = ...` into
+      // eight BSSY/BSYNC regions whose branch-resolving stalls made this path 40 % of the epilogue time
+      // (the block runs whenever any of the warp's 32 rows has a hit: 39 % of the chunks at the H&M shape)
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
-        if (q[h] > st.tau) cand[st.cnt++] = make_uint2(__float_as_uint(q[h]), (uint32_t)(col0 + 4 * h));
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .u64 a;\n"
+            "setp.gt.f32 p, %2, %3;\n"
+            "mad.wide.s32 a, %0, 8, %1;\n"
+            "@p st.global.f32 [a], %2;\n"
+            "@p st.global.u32 [a + 4], %4;\n"
+            "@p add.s32 %0, %0, 1;\n"
+            "}\n"
+            : "+r"(st.cnt)
+            : "l"(cand), "f"(q[h]), "f"(st.tau), "r"(col0 + 4 * h));      // the list is write-only here
       }
     }
   }
@@ -849,20 +863,24 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
 }
 
 // ----------------------------------------------------------------------------- rescoring, dim = 64
-// The first version of this kernel ran the fp64 chain for every item of every kept group (~70 per
+// The first version of this kernel ran the fp64 chain for every item of every kept group (~90 per
 // user) and spent 57 % of its stall samples on F2F.F64.F32 (two fp32->fp64 conversions per DFMA at
-// 16 conversions/clk/SM; profiles/r1_bench.md).  Now:
-//   pass 1  fp32: a_j = fl(u.x_j) and s_j = fl(sum |u_k x_k|) for every candidate item, rows staged by
-//           half warps into shared memory.  |a_j - u.x_j| <= gamma_64 * sum|u_k x_k|, so
-//           lo_j = a_j - 2^-17 s_j <= u.x_j <= a_j + 2^-17 s_j = up_j  (2^-17 = 2 * 64 * 2^-24).
-//           T = k-th largest lo_j (warp-wide bitonic merge of the running top 32).  An item with
-//           up_j < T has k items strictly above it and can be dropped; so can an item with up_j <= cut.
+// 16 conversions/clk/SM; profiles/r1_bench.md).  Now the work shrinks in three steps:
+//   groups  g_i = the nominated groups' maxima (tensor-core scores of DISTINCT items, each within eps of the
+//           exact score -- the bound the certificate rests on).  With g_(k) the k-th largest of them, k items
+//           have an exact score >= T0 = g_(k)/(su si) - eps + u.c, so a group with g_i < g_(k) - 2 eps su si
+//           cannot hold a top-k item and is dropped before anything is fetched.
+//   pass 1  fp32: a_j = fl(u.x_j), rows staged by half warps into shared memory.
+//           |a_j - u.x_j| <= gamma_64 * sum_k |u_k x_jk| <= gamma_64 ||u|| ||x_j||, so with
+//           rad = 2^-17 ||u|| (max_j ||x_j - c|| + ||c||)   (2^-17 = 2 * 64 * 2^-24)
+//           an item with a_j + rad < T0 has k items strictly above it; one with a_j + rad <= cut is not a
+//           contender.  Both are dropped.
 //   pass 2  fp64, survivors only (k plus the near ties, 16 per round): the half warp that stages a row
 //           writes the PRODUCTS u_k * x_jk as doubles (exact: 24 + 24 significant bits), lane j then adds
 //           them in the order k = 0..63.  round(p + acc) is what fma(u, x, acc) returns when p is exact,
 //           so the scores are bit-identical to the fp64 fma chain of the oracle and of hnm_topk_exact.
-// The certificate is unchanged: every item with an exact score above the cut among the top k survives
-// pass 1, so "k contenders above the cut" holds for the same users as before.
+// The certificate is unchanged: every item with an exact score above the cut among the top k survives,
+// so "k contenders above the cut" holds for the same users as before.
 constexpr int kRows2 = 16;                 // items per pass-2 round
 constexpr int kStride1 = 68;               // floats per staged fp32 row (16-byte aligned, LDS.128 conflict free)
 constexpr int kStride2 = 65;               // doubles per staged product row
@@ -871,10 +889,11 @@ static_assert(32 * kStride1 * 4 <= kRows2 * kStride2 * 8 + 384, "tile union");
 
 struct __align__(16) RescoreSmem {
   double tile[kRows2 * kStride2 + 48];     // pass 1: float [32][kStride1]; pass 2: double [16][kStride2]
-  double sc[kMaxContenders];               // pass 1: float up[256]; pass 2 on: contender scores
+  double sc[kMaxContenders];               // contender scores
   float uf[kDim];
   int id[kMaxContenders];
   uint32_t col[kMaxGroups];
+  float gmax[kMaxGroups];
   uint8_t sel[kMaxSel];
 };
 
@@ -900,7 +919,6 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   if (b >= batch) return;
   RescoreSmem& sm = smem[wib];
   float* tile1 = reinterpret_cast<float*>(sm.tile);
-  float* s_up = reinterpret_cast<float*>(sm.sc);
   const int64_t uid = user_ids ? user_ids[b] : b;
   const float* urow = user_emb + (size_t)uid * kDim;
   const int raw = cand_count[b];
@@ -911,11 +929,26 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   if (excl_ptr) { ex_lo = excl_ptr[b]; ex_hi = excl_ptr[b + 1]; }
   const int half = lane >> 4, sub = lane & 15;
 
+  // the user's row: fp32 copy in shared memory for pass 1, this lane's four values as doubles for pass 2
+  const float4 uf = ldg_f4(urow + sub * 4);
+  if (half == 0) *reinterpret_cast<float4*>(sm.uf + sub * 4) = uf;
+  const double ud0 = (double)uf.x, ud1 = (double)uf.y, ud2 = (double)uf.z, ud3 = (double)uf.w;
+  double un = 0.0, uc = 0.0, uc_abs = 0.0, cn = 0.0;
+  if (half == 0) {
+    un = fma(ud0, ud0, un); un = fma(ud1, ud1, un); un = fma(ud2, ud2, un); un = fma(ud3, ud3, un);
+    if (center) {
+      const float4 cf = ldg_f4(center + sub * 4);
+      const double c0 = (double)cf.x, c1 = (double)cf.y, c2 = (double)cf.z, c3 = (double)cf.w;
+      uc = fma(ud0, c0, uc); uc = fma(ud1, c1, uc); uc = fma(ud2, c2, uc); uc = fma(ud3, c3, uc);
+      uc_abs = fabs(ud0 * c0) + fabs(ud1 * c1) + fabs(ud2 * c2) + fabs(ud3 * c3);
+      cn = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+    }
+  }
+
   // 1. keep the groups whose maximum ended above the final threshold, compacted: slot j = kept group j
   int groups = 0;
-#pragma unroll
-  for (int e = 0; e < kMaxPerLane; ++e) {
-    const int idx = lane + 32 * e;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int idx = e0 + lane;
     uint2 c = make_uint2(0u, 0u);
     bool keep = false;
     if (idx < n) {
@@ -924,42 +957,75 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     }
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     const int pos = groups + __popc(mask & ((1u << lane) - 1u));
-    if (keep && pos < kMaxGroups) sm.col[pos] = c.y;
+    if (keep && pos < kMaxGroups) { sm.col[pos] = c.y; sm.gmax[pos] = __uint_as_float(c.x); }
     groups += __popc(mask);
   }
   const bool too_many = groups > kMaxGroups;
   groups = min(groups, kMaxGroups);
 
-  // the user's row: fp32 copy in shared memory for pass 1, this lane's four values as doubles for pass 2
-  const float4 uf = ldg_f4(urow + sub * 4);
-  if (half == 0) *reinterpret_cast<float4*>(sm.uf + sub * 4) = uf;
-  const double ud0 = (double)uf.x, ud1 = (double)uf.y, ud2 = (double)uf.z, ud3 = (double)uf.w;
-  double un = 0.0, uc = 0.0, uc_abs = 0.0;
-  if (half == 0) {
-    un = fma(ud0, ud0, un); un = fma(ud1, ud1, un); un = fma(ud2, ud2, un); un = fma(ud3, ud3, un);
-    if (center) {
-      const float4 cf = ldg_f4(center + sub * 4);
-      const double c0 = (double)cf.x, c1 = (double)cf.y, c2 = (double)cf.z, c3 = (double)cf.w;
-      uc = fma(ud0, c0, uc); uc = fma(ud1, c1, uc); uc = fma(ud2, c2, uc); uc = fma(ud3, c3, uc);
-      uc_abs = fabs(ud0 * c0) + fabs(ud1 * c1) + fabs(ud2 * c2) + fabs(ud3 * c3);
-    }
-  }
 #pragma unroll
-  for (int off = 16; off; off >>= 1) {
+  for (int off = 8; off; off >>= 1) {          // the four sums live on lanes 0..15
     un += __shfl_xor_sync(0xffffffffu, un, off);
     uc += __shfl_xor_sync(0xffffffffu, uc, off);
     uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
+    cn += __shfl_xor_sync(0xffffffffu, cn, off);
   }
+  un = __shfl_sync(0xffffffffu, un, 0);
+  uc = __shfl_sync(0xffffffffu, uc, 0);
+  uc_abs = __shfl_sync(0xffffffffu, uc_abs, 0);
+  cn = __shfl_sync(0xffffffffu, cn, 0);
   un = sqrt(un);
   // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
   const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)kDim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
   const double cut = (double)thr * inv_scale + eps + uc;
-  const float cutf = __double2float_rd(cut);                // up_j <= cutf  =>  u.x_j <= cut
+  const float cutf = __double2float_rd(cut);                // a_j + rad <= cutf  =>  u.x_j <= cut
+  // fp32 dot product radius: 2 gamma_64 ||u|| ||x_j||, ||x_j|| <= max ||x - c|| + ||c||; the absolute term
+  // covers products that underflow in fp32
+  const float rad = __double2float_ru(7.62939453125e-6 * un * (max_item_norm + sqrt(cn)) * 1.0001 + 1e-36);
   __syncwarp();
 
-  // 2. pass 1: fp32 scores with a rigorous error radius, running top-32 of the lower bounds
+  // 2. g_(k) over (at most the first 32 of) the kept groups whose four items all exist and are not excluded
+  float gv = -INFINITY;
+  if (lane < groups) {
+    const int c0 = (int)sm.col[lane];
+    bool ok = c0 + kGroup <= num_items_local;               // a maximum that came from zero padding is no item
+    if (ok && ex_lo < ex_hi) {
+      for (int j = 0; j < kGroup; ++j) ok = ok && !in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)(c0 + j));
+    }
+    if (ok) gv = sm.gmax[lane];
+  }
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_desc(gv, lane, stride, (lane & size) == 0);
+  }
+  const float gk = __shfl_sync(0xffffffffu, gv, k - 1);      // -inf when fewer than k such groups
+  // k items score >= T0 exactly; groups entirely below it are dropped (scaled units, rounded down)
+  const double t0 = (double)gk * inv_scale - eps + uc;
+  const float t0f = gk > -INFINITY ? __double2float_rd(t0) : -INFINITY;
+  const float gmin = gk > -INFINITY ? __double2float_rd((double)gk - 2.0 * eps / inv_scale) : -INFINITY;
+  {
+    int kept = 0;
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+      const int gi = g0 + lane;
+      uint32_t c = 0u;
+      bool keep = false;
+      if (gi < groups) {
+        c = sm.col[gi];
+        keep = sm.gmax[gi] >= gmin;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) sm.col[kept + __popc(mask & ((1u << lane) - 1u))] = c;      // write position <= read position
+      kept += __popc(mask);
+      __syncwarp();
+    }
+    groups = kept;
+  }
+
+  // 3. pass 1: fp32 scores; survivors are compacted into sm.sel as they are found
   const int num_cand_items = groups * kGroup;
-  float top = -INFINITY;                                    // lane i: (i+1)-th largest lower bound so far
+  int nsel = 0;
   for (int base = 0; base < num_cand_items; base += 32) {
     const int it = base + lane;
     int item = -1;
@@ -970,63 +1036,41 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
 #pragma unroll
     for (int h0 = 0; h0 < 16; h0 += 8) {
       float4 v[8];
-      int il[8];
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        il[s] = __shfl_sync(0xffffffffu, litem, 2 * (h0 + s) + half);
+        const int il = __shfl_sync(0xffffffffu, litem, 2 * (h0 + s) + half);
         v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (il[s] >= 0) v[s] = ldg_f4(item_emb + (size_t)il[s] * kDim + sub * 4);
+        if (il >= 0) v[s] = ldg_f4(item_emb + (size_t)il * kDim + sub * 4);
       }
 #pragma unroll
       for (int s = 0; s < 8; ++s)
         *reinterpret_cast<float4*>(tile1 + (2 * (h0 + s) + half) * kStride1 + sub * 4) = v[s];
     }
     __syncwarp();
-    float a = 0.f, sabs = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // four partial sums: any order satisfies the bound
     {
       const float* t = tile1 + lane * kStride1;
 #pragma unroll
       for (int kk = 0; kk < kDim; kk += 4) {
         const float4 u4 = *reinterpret_cast<const float4*>(sm.uf + kk);
         const float4 x4 = *reinterpret_cast<const float4*>(t + kk);
-        a = fmaf(u4.x, x4.x, a); sabs = fmaf(fabsf(u4.x), fabsf(x4.x), sabs);
-        a = fmaf(u4.y, x4.y, a); sabs = fmaf(fabsf(u4.y), fabsf(x4.y), sabs);
-        a = fmaf(u4.z, x4.z, a); sabs = fmaf(fabsf(u4.z), fabsf(x4.z), sabs);
-        a = fmaf(u4.w, x4.w, a); sabs = fmaf(fabsf(u4.w), fabsf(x4.w), sabs);
+        a0 = fmaf(u4.x, x4.x, a0);
+        a1 = fmaf(u4.y, x4.y, a1);
+        a2 = fmaf(u4.z, x4.z, a2);
+        a3 = fmaf(u4.w, x4.w, a3);
       }
     }
-    // radius: 2 * gamma_64 * s covers the rounding of s itself and of a -+ radius; the absolute term covers
-    // products that underflow in fp32
-    const float rad = fmaf(sabs, 7.62939453125e-6f, 1e-36f);
-    const float up = live ? a + rad : -INFINITY;
-    float lo = live ? a - rad : -INFINITY;
-    s_up[it] = up;
-    // sort this round's lower bounds best-first, fold them into the running top 32
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-      for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_desc(lo, lane, stride, (lane & size) == 0);
-    }
-    top = fmaxf(top, __shfl_sync(0xffffffffu, lo, 31 - lane));   // bitonic: holds the 32 largest of both
-#pragma unroll
-    for (int stride = 16; stride > 0; stride >>= 1) cmpx_desc(top, lane, stride, true);
-    __syncwarp();
-  }
-  const float T = __shfl_sync(0xffffffffu, top, k - 1);       // -inf when fewer than k live candidates
-
-  // 3. survivors of pass 1
-  int nsel = 0;
-  for (int base = 0; base < num_cand_items; base += 32) {
-    const float up = s_up[base + lane];
-    const bool s = up >= T && up > cutf;
+    const float up = ((a0 + a1) + (a2 + a3)) + rad;
+    const bool s = live && up >= t0f && up > cutf;
     const unsigned mask = __ballot_sync(0xffffffffu, s);
     const int pos = nsel + __popc(mask & ((1u << lane) - 1u));
-    if (s && pos < kMaxSel) sm.sel[pos] = (uint8_t)(base + lane);
+    if (s && pos < kMaxSel) sm.sel[pos] = (uint8_t)it;
     nsel += __popc(mask);
+    __syncwarp();
   }
   const bool sel_overflow = nsel > kMaxSel;
   if (sel_overflow) nsel = 0;
-  __syncwarp();                                             // s_up is dead from here on: sm.sc takes its place
+  __syncwarp();
 
   // 4. pass 2: exact scores of the survivors; contenders = strictly above the cut
   int total = 0;
