@@ -32,7 +32,7 @@ _SIGNATURES = {
     "hnm_graph_build": (C.c_int, [P, P, P, I64, I64, P, P, P, P, I32, P, P, P, SZ, P]),
     "hnm_lightgcn_prescale": (C.c_int, [P, P, F32, P, P, I64, I32, P]),
     "hnm_lightgcn_layer": (C.c_int, [P, P, P, P, P, P, P, F32, I64, I32, I64, I64, P, I32, I32, I32, P]),
-    "hnm_lightgcn_partial": (C.c_int, [P, P, P, P, P, P, I32, I64, I64, P, I32, I32, I32, P]),
+    "hnm_lightgcn_partial": (C.c_int, [P, P, P, P, P, P, I32, I64, I64, P, I32, I32, I32, I32, P]),
     "hnm_lightgcn_finish": (C.c_int, [P, P, P, F32, P, P, I64, I64, I32, P]),
     "hnm_pair_scores": (C.c_int, [P, P, P, P, I64, I32, I64, I64, P, P]),
     "hnm_score_all_items": (C.c_int, [P, P, P, I64, I64, I32, P, P]),
@@ -99,6 +99,8 @@ def call(fn: str, *args) -> None:
     n = _LAUNCHES_PER_CALL.get(fn, 1)
     if fn == "hnm_score_topk_fused" and args[12] > 256:
         n = 2                                     # + merge of the per-slice candidate lists
+    if fn == "hnm_lightgcn_partial" and args[10]:
+        n = 2 + (1 if args[11] else 0)
     if fn == "hnm_lightgcn_layer" and args[13]:
         n = 2 + (1 if args[14] else 0)            # cluster pass + whole-CTA pass over the long rows + warp-per-row pass
     LAUNCHES += n

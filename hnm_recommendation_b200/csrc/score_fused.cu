@@ -585,7 +585,10 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, uint2* __restrict__
       for (int stride = 16; stride > 0; stride >>= 1) cmpx_lane(top, lane, stride, true);
     }
   }
-  thr = fmaxf(thr, __shfl_sync(0xffffffffu, top, kth_sel - 1));
+  // An unsliced row's tau is the kth_sel-th largest of 32 BUCKET maxima, which sits near the (kth_sel + 4)-th
+  // best score because good items share buckets.  Taking the exact kth_sel-th best group here would leave less
+  // room between the k-th score and the threshold, and 30x more sliced users failed their certificate.
+  thr = fmaxf(thr, __shfl_sync(0xffffffffu, top, min(kth_sel + 4, 32) - 1));
   uint2* out = cand + (size_t)row * cap;
   int total = 0;
   for (int s = 0; s < sp.slices; ++s) {
@@ -885,6 +888,7 @@ constexpr int kRows2 = 16;                 // items per pass-2 round
 constexpr int kStride1 = 68;               // floats per staged fp32 row (16-byte aligned, LDS.128 conflict free)
 constexpr int kStride2 = 65;               // doubles per staged product row
 constexpr int kMaxSel = 128;               // pass-1 survivors a user may have (more: not certified)
+constexpr int kRescorePrefetch = 4096;     // users ahead whose inputs are pulled into the L2 (> users resident on the GPU)
 static_assert(32 * kStride1 * 4 <= kRows2 * kStride2 * 8 + 384, "tile union");
 
 struct __align__(16) RescoreSmem {
@@ -904,7 +908,7 @@ __device__ __forceinline__ void cmpx_desc(float& v, int lane, int stride, bool d
   v = (lower == desc) ? fmaxf(v, o) : fminf(v, o);
 }
 
-__global__ void __launch_bounds__(kRescoreWarps * 32)
+__global__ void __launch_bounds__(kRescoreWarps * 32, 5)
 rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
                  const int64_t* __restrict__ user_ids, int64_t batch, int64_t item_begin, int num_items_local,
                  const uint2* __restrict__ cand, int cap, const int32_t* __restrict__ cand_count,
@@ -928,6 +932,20 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   int64_t ex_lo = 0, ex_hi = 0;
   if (excl_ptr) { ex_lo = excl_ptr[b]; ex_hi = excl_ptr[b + 1]; }
   const int half = lane >> 4, sub = lane & 15;
+  {
+    // The kernel is a chain of dependent loads per user (count -> list -> item rows), so warm the L2 for a user
+    // that a later CTA will take: its list head (lane i: 32 bytes), count, threshold and embedding row.
+    const int64_t pb = b + kRescorePrefetch;
+    if (pb < batch) {
+      const char* pa = reinterpret_cast<const char*>(cand + (size_t)pb * cap) + lane * 32;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+      const char* pm = nullptr;
+      if (lane == 0) pm = reinterpret_cast<const char*>(cand_count + pb);
+      else if (lane == 1) pm = reinterpret_cast<const char*>(cand_thresh + pb);
+      else if (lane < 10 && !user_ids) pm = reinterpret_cast<const char*>(user_emb + (size_t)pb * kDim) + (lane - 2) * 32;
+      if (pm) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm));
+    }
+  }
 
   // the user's row: fp32 copy in shared memory for pass 1, this lane's four values as doubles for pass 2
   const float4 uf = ldg_f4(urow + sub * 4);
@@ -1075,15 +1093,27 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   // 4. pass 2: exact scores of the survivors; contenders = strictly above the cut
   int total = 0;
   for (int base = 0; base < nsel; base += kRows2) {
+    {
+      // all eight row loads of this half warp are issued before the first one is used
+      float4 v[kRows2 / 2];
 #pragma unroll
-    for (int s = 0; s < kRows2 / 2; ++s) {
-      const int l = 2 * s + half;
-      if (base + l < nsel) {
-        const int it = sm.sel[base + l];
-        const int item = (int)sm.col[it / kGroup] + (it % kGroup);
-        const float4 v = ldg_f4(item_emb + (size_t)item * kDim + sub * 4);
-        double* t = sm.tile + l * kStride2 + sub * 4;
-        t[0] = ud0 * (double)v.x; t[1] = ud1 * (double)v.y; t[2] = ud2 * (double)v.z; t[3] = ud3 * (double)v.w;
+      for (int s = 0; s < kRows2 / 2; ++s) {
+        const int l = 2 * s + half;
+        v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (base + l < nsel) {
+          const int it = sm.sel[base + l];
+          const int item = (int)sm.col[it / kGroup] + (it % kGroup);
+          v[s] = ldg_f4(item_emb + (size_t)item * kDim + sub * 4);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < kRows2 / 2; ++s) {
+        const int l = 2 * s + half;
+        if (base + l < nsel) {
+          double* t = sm.tile + l * kStride2 + sub * 4;
+          t[0] = ud0 * (double)v[s].x; t[1] = ud1 * (double)v[s].y; t[2] = ud2 * (double)v[s].z;
+          t[3] = ud3 * (double)v[s].w;
+        }
       }
     }
     __syncwarp();

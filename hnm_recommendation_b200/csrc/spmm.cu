@@ -103,8 +103,12 @@ __device__ __forceinline__ void warp_gather(const int32_t* __restrict__ col, con
 // e = dis_i * sum;  xs_out = dis_i * e;  acc += alpha * e   (lightgcn.py:152,158)
 __device__ __forceinline__ void row_epilogue(float4 s, float di, float alpha, float* __restrict__ xs_out_p,
                                              float* __restrict__ acc_p, int partial = 0) {
-  if (partial & 1) {      // raw neighbour sum of a sub-range: normalisation happens after the all-reduce
-    *reinterpret_cast<float4*>(xs_out_p) = s;
+  if (partial & 1) {      // raw neighbour sum of a sub-range: normalisation happens in hnm_lightgcn_finish
+    if (partial & 4)      // ... added to what earlier sub-ranges of the same rows left there
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(xs_out_p), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w)
+                   : "memory");
+    else
+      *reinterpret_cast<float4*>(xs_out_p) = s;
     return;
   }
   float4 e = make_float4(__fmul_rn(di, s.x), __fmul_rn(di, s.y), __fmul_rn(di, s.z), __fmul_rn(di, s.w));
@@ -273,7 +277,8 @@ spmm_generic_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const
       const int c = c0 + t * 32 + lane;
       if (c < dim) {
         if (partial) {
-          xs_out[(size_t)(row - seg.off) * dim + c] = s[t];
+          float* o = xs_out + (size_t)(row - seg.off) * dim + c;
+          *o = (partial & 4) ? *o + s[t] : s[t];
           continue;
         }
         const size_t off = (size_t)row * dim + c;
@@ -405,7 +410,7 @@ int dispatch_layer(int dim, Seg seg, int partial, const int32_t* col, const floa
   const int64_t rows = row_end - row_begin;
   const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   if (grid > 0) {
-    spmm_generic_kernel<WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(seg, partial & 1, col, w, dis, xs_in, xs_out, acc,
+    spmm_generic_kernel<WEIGHTED><<<grid, kWarpsPerCta * 32, 0, stream>>>(seg, partial & 5, col, w, dis, xs_in, xs_out, acc,
                                                                        alpha, dim, row_begin, row_end);
     HNM_LAUNCH_CHECK();
   }
@@ -483,9 +488,10 @@ __global__ void finish_kernel(const float4* __restrict__ partial, const float4* 
 extern "C" int hnm_lightgcn_partial(const int32_t* seg_begin, const int32_t* seg_end, const int32_t* csr_col,
                                     const float* csr_w, const float* xs_in, float* partial, int32_t dim,
                                     int64_t row_begin, int64_t row_end, const int32_t* heavy_rows, int32_t num_heavy,
-                                    int32_t num_huge, int32_t heavy_threshold, void* stream_) {
+                                    int32_t num_huge, int32_t heavy_threshold, int32_t accumulate, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!seg_begin || !seg_end || !csr_col || !xs_in || !partial) return HNM_E_NULL;
+  const int mode = accumulate ? 5 : 1;
   if (num_heavy > 0 && !heavy_rows) return HNM_E_NULL;
   if (num_huge < 0 || num_huge > num_heavy) return HNM_E_RANGE;
   if (dim <= 0 || row_begin < 0 || row_begin > row_end) return HNM_E_RANGE;
@@ -493,9 +499,9 @@ extern "C" int hnm_lightgcn_partial(const int32_t* seg_begin, const int32_t* seg
   if (row_begin == row_end) return HNM_OK;
   const Seg seg{seg_begin, seg_end, row_begin};
   if (csr_w)
-    return dispatch_layer<true>(dim, seg, 1, csr_col, csr_w, nullptr, xs_in, partial, nullptr, 0.f, row_begin, row_end,
+    return dispatch_layer<true>(dim, seg, mode, csr_col, csr_w, nullptr, xs_in, partial, nullptr, 0.f, row_begin, row_end,
                                 heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
-  return dispatch_layer<false>(dim, seg, 1, csr_col, csr_w, nullptr, xs_in, partial, nullptr, 0.f, row_begin, row_end,
+  return dispatch_layer<false>(dim, seg, mode, csr_col, csr_w, nullptr, xs_in, partial, nullptr, 0.f, row_begin, row_end,
                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
 }
 

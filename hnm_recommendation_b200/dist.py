@@ -149,7 +149,7 @@ class ShardedLightGCN:
         def exchange_items(buf):
             self.coll.allgather_rows(buf, p.item_rows)
 
-        if hasattr(self.backend, "propagate_sharded"):
+        if hasattr(self.backend, "propagate_sharded") and self.backend.can_partition_users(m):
             return self.backend.propagate_sharded(self, all_rows or self.mode != "users")
         final = self.backend.propagate(m, my_ranges, exchange,
                                        exchange_items if (self.mode == "users" and not all_rows) else exchange)
@@ -187,6 +187,12 @@ class CudaBackend:
     def __init__(self):
         self._shard_key = None
         self._shard = None
+
+    def can_partition_users(self, model) -> bool:
+        """The user-partitioned form needs a bipartite graph (item rows hold users and their self loop only);
+        anything else takes the row-sliced form with an all-gather per layer."""
+        from . import engine
+        return model.embedding_dim % 4 == 0 and engine.is_bipartite(model.graph, model.num_users)
 
     def propagate_sharded(self, sharded, final_users: bool):
         """Users partitioned over the ranks; per layer one all-reduce of the item block (engine.propagate_user_sharded)."""
@@ -257,8 +263,21 @@ def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) ->
         call("hnm_lightgcn_prescale", ptr(w), ptr(g.dis), 0.25, ptr(xs), ptr(acc), n, d, stream())
         heavy = ptr(g.heavy_rows) if g.num_heavy else None
 
+        chunks = getattr(model, "_item_chunks", None) if shard is None else None
+        if chunks is not None:
+            part = torch.empty(n - U, d, dtype=torch.float32, device=w.device)
+
         def layer():
             # one layer's kernels on this rank (no communication)
+            if chunks is not None:
+                call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
+                     0.25, n, d, 0, U, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
+                for c, sh in enumerate(chunks.chunks):
+                    call("hnm_lightgcn_partial", ptr(sh.seg_begin), ptr(sh.seg_end), ptr(g.col), ptr(g.w), ptr(xs),
+                         ptr(part), d, U, n, ptr(sh.heavy_rows) if sh.heavy_rows.numel() else None,
+                         int(sh.heavy_rows.numel()), sh.num_huge, g.heavy_threshold, 1 if c else 0, stream())
+                call("hnm_lightgcn_finish", ptr(part), ptr(xs), ptr(g.dis), 0.25, ptr(xo), ptr(acc), U, n - U, d, stream())
+                return
             if shard is None:
                 call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
                      0.25, n, d, 0, n, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
@@ -268,7 +287,7 @@ def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) ->
                      0.25, n, d, shard.u0, shard.u1, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
             call("hnm_lightgcn_partial", ptr(shard.seg_begin), ptr(shard.seg_end), ptr(g.col), ptr(g.w), ptr(xs),
                  ptr(part), d, U, n, ptr(shard.heavy_rows) if shard.heavy_rows.numel() else None,
-                 int(shard.heavy_rows.numel()), shard.num_huge, g.heavy_threshold, stream())
+                 int(shard.heavy_rows.numel()), shard.num_huge, g.heavy_threshold, 0, stream())
             call("hnm_lightgcn_finish", ptr(part), ptr(xs), ptr(g.dis), 0.25, ptr(xo), ptr(acc), U, n - U, d, stream())
         layer()
         a = ev()

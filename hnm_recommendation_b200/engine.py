@@ -80,7 +80,7 @@ def build_graph(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n
 
 def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
               row_ranges: Optional[Sequence[Tuple[int, int]]] = None, exchange=None,
-              exchange_final=None) -> torch.Tensor:
+              exchange_final=None, item_chunks: Optional["ItemChunks"] = None) -> torch.Tensor:
     """LightGCN.forward (lightgcn.py:147-158): returns final [N, d] = sum_l alpha_l * A_hat^l E0.
 
     row_ranges/exchange serve the row-sharded multi-GPU form: this rank computes the listed
@@ -97,6 +97,8 @@ def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layer
     if n != graph.num_nodes:
         raise ValueError("embedding rows != graph nodes")
     ranges = list(row_ranges) if row_ranges is not None else [(0, n)]
+    if item_chunks is not None and row_ranges is None and exchange is None and d % 4 == 0:
+        return _propagate_chunked(graph, e0, alphas, num_layers, item_chunks)
     acc = torch.empty_like(e0)
     xs_a = torch.empty_like(e0)
     xs_b = torch.empty_like(e0) if num_layers > 1 else None
@@ -263,6 +265,80 @@ def make_user_shard(graph: Graph, num_users: int, num_items: int, u0: int, u1: i
                      int(huge.sum()))
 
 
+def is_bipartite(graph: Graph, num_users: int) -> bool:
+    """True when user rows only point at items and item rows only at users (self loops aside) -- what the
+    user-partitioned and the chunked propagation assume.  One device reduction, cached on the graph."""
+    cache = graph.__dict__.setdefault("_bipartite", {})
+    if num_users not in cache:
+        n = graph.num_nodes
+        split = int(graph.rowptr[num_users])
+        in_user_rows = int((graph.col[:split] >= num_users).sum())      # item columns (+ nothing else allowed)
+        in_item_rows = int((graph.col[split:] >= num_users).sum())      # must be exactly the self loops
+        cache[num_users] = (in_user_rows == split - num_users) and (in_item_rows == n - num_users)
+    return cache[num_users]
+
+
+@dataclass
+class ItemChunks:
+    """Sub-ranges of the item rows per L2-sized chunk of users (see hnm_lightgcn_partial in the header)."""
+    num_users: int
+    chunks: List[UserShard]
+
+
+def make_item_chunks(graph: Graph, num_users: int, num_items: int, dim: int,
+                     num_chunks: Optional[int] = None) -> Optional[ItemChunks]:
+    """None unless chunking was asked for (num_chunks > 1 or HNM_SPMM_CHUNKS) and the graph is bipartite."""
+    import os
+    if num_chunks is None and os.environ.get("HNM_SPMM_CHUNKS"):
+        num_chunks = int(os.environ["HNM_SPMM_CHUNKS"])
+    if num_chunks is None:
+        # measured at the H&M shape (profiles/r1_spmm_notes.md): 1.76 ms per layer in one pass, 1.93 / 1.95 /
+        # 2.64 ms with 4 / 8 / 16 chunks -- the pass is bound by the L2 -> SM gather traffic, not by the HBM
+        # re-reads the chunks remove, so the chunked form stays opt-in (HNM_SPMM_CHUNKS, or num_chunks here)
+        num_chunks = 1
+    if num_chunks <= 1 or num_users + num_items != graph.num_nodes or not is_bipartite(graph, num_users):
+        return None
+    base, rem = divmod(num_users, num_chunks)
+    out, a = [], 0
+    for c in range(num_chunks):
+        b = a + base + (1 if c < rem else 0)
+        out.append(make_user_shard(graph, num_users, num_items, a, b))
+        a = b
+    return ItemChunks(num_users, out)
+
+
+def _propagate_chunked(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
+                       ic: ItemChunks) -> torch.Tensor:
+    """LightGCN.forward on one GPU with the item rows summed chunk of users by chunk of users, so that the
+    user rows a chunk gathers stay in the L2 (each leaves HBM once per layer instead of ~6 times)."""
+    n, d = e0.shape
+    U = ic.num_users
+    I = n - U
+    acc = torch.empty_like(e0)
+    xs_a = torch.empty_like(e0)
+    xs_b = torch.empty_like(e0) if num_layers > 1 else None
+    part = torch.empty(I, d, dtype=torch.float32, device=e0.device)
+    with torch.cuda.device(e0.device):
+        s = stream()
+        call("hnm_lightgcn_prescale", ptr(e0), ptr(graph.dis), float(alphas[0]), ptr(xs_a), ptr(acc), n, d, s)
+        cur, nxt = xs_a, xs_b
+        heavy = ptr(graph.heavy_rows) if graph.num_heavy else None
+        for layer in range(1, num_layers + 1):
+            last = layer == num_layers
+            call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
+                 None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, 0, U, heavy, graph.num_heavy,
+                 graph.num_huge, graph.heavy_threshold, s)
+            for c, sh in enumerate(ic.chunks):
+                call("hnm_lightgcn_partial", ptr(sh.seg_begin), ptr(sh.seg_end), ptr(graph.col), ptr(graph.w), ptr(cur),
+                     ptr(part), d, U, n, ptr(sh.heavy_rows) if sh.heavy_rows.numel() else None,
+                     int(sh.heavy_rows.numel()), sh.num_huge, graph.heavy_threshold, 1 if c else 0, s)
+            call("hnm_lightgcn_finish", ptr(part), ptr(cur), ptr(graph.dis), float(alphas[layer]),
+                 None if last else ptr(nxt), ptr(acc), U, I, d, s)
+            if not last:
+                cur, nxt = nxt, cur
+    return acc
+
+
 def propagate_user_sharded(graph: Graph, shard: UserShard, e0: torch.Tensor, alphas: Sequence[float],
                            num_layers: int, num_users: int, allreduce_items) -> torch.Tensor:
     """LightGCN.forward with the users partitioned over ranks (one process per GPU).
@@ -304,7 +380,7 @@ def propagate_user_sharded(graph: Graph, shard: UserShard, e0: torch.Tensor, alp
                      graph.num_huge, graph.heavy_threshold, s)
             call("hnm_lightgcn_partial", ptr(shard.seg_begin), ptr(shard.seg_end), ptr(graph.col), ptr(graph.w),
                  ptr(cur), ptr(part), d, U, n, sh_heavy, int(shard.heavy_rows.numel()), shard.num_huge,
-                 graph.heavy_threshold, s)
+                 graph.heavy_threshold, 0, s)
             allreduce_items(part)
             call("hnm_lightgcn_finish", ptr(part), ptr(cur), ptr(graph.dis), float(alphas[layer]),
                  None if last else ptr(nxt), ptr(acc), U, I, d, s)

@@ -85,6 +85,8 @@ class LightGCN(ModelBase):
         self.edge_index = edge_index
         self.edge_weight = edge_weight
         self.graph = engine.build_graph(edge_index, edge_weight, self.num_nodes, self.embeddings.weight.device)
+        # item rows gather from the user block; when that does not fit the L2 they are walked chunk by chunk
+        self._item_chunks = engine.make_item_chunks(self.graph, self.num_users, self.num_items, self.embedding_dim)
         self._cache_key = None
 
     # ---------------------------------------------------------------- forward
@@ -97,7 +99,8 @@ class LightGCN(ModelBase):
         key = (w.data_ptr(), w._version, id(self.graph), tuple(self.alpha), self.num_layers)
         if self.cache_embeddings and self._cache_key == key and self._cache_val is not None:
             return self._cache_val
-        final = engine.propagate(self.graph, w, self.alpha, self.num_layers)
+        final = engine.propagate(self.graph, w, self.alpha, self.num_layers,
+                                 item_chunks=getattr(self, "_item_chunks", None))
         self._cache_key, self._cache_val = key, final
         self._scorer = None
         return final

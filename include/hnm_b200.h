@@ -108,7 +108,12 @@ HNM_API int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_col
 HNM_API int hnm_lightgcn_partial(const int32_t* seg_begin, const int32_t* seg_end, const int32_t* csr_col,
                          const float* csr_w, const float* xs_in, float* partial, int32_t dim,
                          int64_t row_begin, int64_t row_end, const int32_t* heavy_rows, int32_t num_heavy,
-                         int32_t num_huge, int32_t heavy_threshold, void* stream);
+                         int32_t num_huge, int32_t heavy_threshold,
+                         int32_t accumulate /* 0: partial = sum; 1: partial += sum (see below) */, void* stream);
+/* The same pair also serves one GPU: the item rows gather from the user block, which at the H&M shape
+ * (351 MB) does not fit the L2, so every user row was fetched from HBM ~6 times per layer.  Walking the
+ * item rows once per L2-sized CHUNK of users (sub-ranges again, accumulate = 1 after the first chunk)
+ * makes each user row leave HBM once. */
 HNM_API int hnm_lightgcn_finish(const float* partial /* [num_rows, dim] */, const float* xs_in /* [N, dim] */,
                         const float* dis, float alpha, float* xs_out /* [N, dim] or NULL */, float* acc /* [N, dim] */,
                         int64_t row_begin, int64_t num_rows, int32_t dim, void* stream);

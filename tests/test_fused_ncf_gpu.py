@@ -57,6 +57,36 @@ def test_fused_subset_filter_and_shard(hnm_lib):
     assert torch.equal(ids.cpu(), w_ids + 1000) and torch.equal(s.cpu(), w_s)
 
 
+@pytest.mark.parametrize("u,i,kind", [(300, 16500, "randn"), (1000, 33000, "small"), (57000, 8300, "randn")])
+def test_fused_sliced_left_over_tiles_bit_exact(hnm_lib, u, i, kind):
+    """User tiles that do not fill a whole pass of the persistent grid have their item range sliced over
+    the CTAs (one candidate list per slice, merged under a recomputed threshold): same lists, bit for bit."""
+    import ctypes as C
+    from hnm_recommendation_b200 import engine
+    from hnm_recommendation_b200.scorer import FusedScorer
+    plan = (C.c_int32 * 5)()
+    pad = lambda x: (x + 127) // 128 * 128
+    assert hnm_lib.hnm_score_topk_fused_plan(pad(u), pad(i), plan) == 0
+    grid, full, tile0, triples, slices = list(plan)
+    assert triples > 0 and slices > 1, list(plan)                  # the case under test
+    ue, ie = _emb(u, i, seed=u + i, kind=kind)
+    ue, ie = ue.cuda(), ie.cuda()
+    sc = FusedScorer(ue, ie)
+    ids, s = sc.topk(None, 12)
+    assert sc.last_stats["uncertified"] <= max(3, u // 50), sc.last_stats
+    # the sliced users are the last ones; check all of them (and a sample of the rest) against brute force
+    first_sliced = min(u, tile0 * 128)
+    check = torch.cat([torch.arange(first_sliced, u), torch.randperm(max(first_sliced, 1))[:256] % u]).cuda()
+    w_ids, w_s = engine.topk_exact(ue, ie, check, 12)
+    assert torch.equal(ids[check], w_ids) and torch.equal(s[check], w_s)
+    # a filter that removes every sliced user's best items
+    some = check[:200].tolist()
+    filt = {x: set(w_ids[r, :6].tolist()) for r, x in enumerate(some)}
+    f_ids, f_s = sc.topk(check[:200], 12, filt)
+    e_ids, e_s = engine.topk_exact(ue, ie, check[:200], 12, engine.exclusion_csr(check[:200], filt, ue.device))
+    assert torch.equal(f_ids, e_ids) and torch.equal(f_s, e_s)
+
+
 def test_fused_exact_ties_fall_back(hnm_lib):
     """Duplicate item rows make exact ties at the cut: the certificate must refuse and the fallback decide by id."""
     from hnm_recommendation_b200.scorer import FusedScorer

@@ -257,3 +257,62 @@ def test_propagate_dims_and_long_rows(hnm_lib, dim, weighted):
     m.cache_embeddings = False
     gu2, gi2 = m.forward()
     assert torch.equal(gu, gu2) and torch.equal(gi, gi2)
+
+
+@pytest.mark.parametrize("dim,weighted,chunks", [(64, False, 3), (64, True, 5), (128, False, 2), (32, True, 4)])
+def test_propagate_item_rows_in_user_chunks(hnm_lib, dim, weighted, chunks):
+    """The single-GPU form that walks the item rows once per chunk of users (hnm_lightgcn_partial with
+    accumulate + hnm_lightgcn_finish): same embeddings as the oracle and as the one-pass kernels, for rows of
+    every length class, and deterministic."""
+    from hnm_recommendation_b200 import LightGCN, engine
+    U, I, L = 30000, 40, 3
+    gen = torch.Generator().manual_seed(dim + chunks)
+    u = torch.cat([torch.arange(U), torch.arange(0, U, 4).repeat(3), torch.randint(0, U, (5000,), generator=gen)])
+    i = torch.cat([torch.zeros(U, dtype=torch.long), torch.arange(1, 4).repeat_interleave(U // 4),
+                   torch.randint(4, I, (5000,), generator=gen)]) + U
+    ei = torch.stack([torch.cat([u, i]), torch.cat([i, u])])
+    ew = None
+    if weighted:
+        half = torch.rand(u.numel(), generator=gen) + 0.5
+        ew = torch.cat([half, half])
+    m = LightGCN(U, I, embedding_dim=dim, num_layers=L).to("cuda")
+    m.set_graph(ei, ew)
+    assert m._item_chunks is None                                  # the user block fits the L2: one pass
+    assert engine.is_bipartite(m.graph, U)
+    one_pass = engine.propagate(m.graph, m.embeddings.weight, m.alpha, L)
+    ic = engine.make_item_chunks(m.graph, U, I, dim, num_chunks=chunks)
+    assert ic is not None and len(ic.chunks) == chunks
+    # item 0 (bought by every user) is a cluster-kernel row in a chunk of >= 8192 users, a whole-CTA row otherwise
+    assert all(sh.heavy_rows.numel() >= 1 for sh in ic.chunks)
+    assert any(sh.num_huge for sh in ic.chunks) == (U // chunks > 8192)
+    chunked = engine.propagate(m.graph, m.embeddings.weight, m.alpha, L, item_chunks=ic)
+    orc = O.LightGCNOracle(U, I, dim, L, weight=m.embeddings.weight.detach().cpu())
+    orc.set_graph(ei, ew)
+    ou, oi = orc.forward()
+    assert_close(chunked[:U], ou, what="users, chunked")
+    # item 0's row is a 30 000-term fp32 sum with cancellation: entries near zero carry ~sqrt(n) ulp of the terms
+    assert_close(chunked[U:], oi, atol_scale=1e-5, what="items, chunked")
+    assert_close(chunked[:U], one_pass[:U], what="users, chunked vs one pass")
+    assert_close(chunked[U:], one_pass[U:], atol_scale=1e-5, what="items, chunked vs one pass")
+    again = engine.propagate(m.graph, m.embeddings.weight, m.alpha, L, item_chunks=ic)
+    assert torch.equal(chunked, again)                             # chunk order is fixed: deterministic
+
+
+def test_non_bipartite_graph_is_detected_and_not_chunked(hnm_lib):
+    """A user-user edge: still a valid graph for set_graph/forward, but neither chunked nor user-partitioned."""
+    from hnm_recommendation_b200 import LightGCN, engine
+    U, I = 50, 30
+    gen = torch.Generator().manual_seed(1)
+    u = torch.randint(0, U, (400,), generator=gen)
+    i = torch.randint(0, I, (400,), generator=gen) + U
+    ei = torch.stack([torch.cat([u, i, torch.tensor([3])]), torch.cat([i, u, torch.tensor([7])])])
+    m = LightGCN(U, I, embedding_dim=16, num_layers=2).to("cuda")
+    m.set_graph(ei)
+    assert not engine.is_bipartite(m.graph, U)
+    assert engine.make_item_chunks(m.graph, U, I, 16, num_chunks=4) is None
+    orc = O.LightGCNOracle(U, I, 16, 2, weight=m.embeddings.weight.detach().cpu())
+    orc.set_graph(ei)
+    gu, gi = m.forward()
+    ou, oi = orc.forward()
+    assert_close(gu, ou, what="users")
+    assert_close(gi, oi, what="items")

@@ -15,7 +15,7 @@ with torch.no_grad():
 m.set_graph(data.edge_index().cuda())
 ue, ie = m.forward()
 print("emb absmax", float(ue.abs().max()), float(ie.abs().max()), "item mean norm", float(ie.mean(0).norm()), "item norm mean", float(ie.norm(dim=1).mean()), flush=True)
-for margin in (2, 3, 4):
+for margin in [int(x) for x in os.environ.get('PROBE_MARGINS', '2,3,4').split(',')]:
     sc = FusedScorer(ue, ie, sel_margin=margin)
     sc.profile = True
     for rep in range(3):
