@@ -14,8 +14,10 @@ Differences from the reference, all deliberate:
     embeddings, i.e. the ordering the reference's fp32 sgemm approximates;
   * ``forward()`` is cached until the weights or the graph change
     (the reference recomputes it on every call, SURVEY.md F7) -- results are identical;
-  * ``forward()`` is inference-only (no autograd through the propagate kernel);
-    training (``bpr_loss``) is outside the accelerated path;
+  * ``forward()`` returns detached, cached tensors; the differentiable form is
+    ``forward_with_grad()`` (what ``bpr_loss`` / ``training_step`` use, lightgcn.py:206-265):
+    its backward pass is the same propagate kernels on the transposed adjacency,
+    ``dL/dE0 = sum_l alpha_l (A_hat^T)^l dL/dfinal``;
   * ``recommend(user_ids, filter_items=None, k=None)`` accepts ``k`` (README.md:131).
 """
 from __future__ import annotations
@@ -31,6 +33,22 @@ from .metrics import RecommendationMetrics
 
 
 SMALL_BATCH = 128
+
+
+class _Propagate(torch.autograd.Function):
+    """final = sum_l alpha_l A_hat^l E0 and its adjoint, both by engine.propagate (lightgcn.py:147-158)."""
+
+    @staticmethod
+    def forward(ctx, weight: torch.Tensor, model: "LightGCN") -> torch.Tensor:
+        ctx.model = model
+        return engine.propagate(model.graph, weight, model.alpha, model.num_layers,
+                                item_chunks=getattr(model, "_item_chunks", None))
+
+    @staticmethod
+    def backward(ctx, grad_final: torch.Tensor):
+        m = ctx.model
+        grad = engine.propagate(m._adjoint_graph(), grad_final.contiguous(), m.alpha, m.num_layers)
+        return grad, None
 
 
 class LightGCN(ModelBase):
@@ -75,6 +93,7 @@ class LightGCN(ModelBase):
         self.metrics = RecommendationMetrics(top_k=top_k)
 
         self.cache_embeddings = True
+        self._graph_t = None
         self._cache_key = None
         self._cache_val: Optional[torch.Tensor] = None
         self._scorer = None
@@ -88,6 +107,23 @@ class LightGCN(ModelBase):
         # item rows gather from the user block; when that does not fit the L2 they are walked chunk by chunk
         self._item_chunks = engine.make_item_chunks(self.graph, self.num_users, self.num_items, self.embedding_dim)
         self._cache_key = None
+        self._graph_t = None
+
+    def _adjoint_graph(self) -> engine.Graph:
+        """CSR of A_hat^T: the transposed edge list with the ORIGINAL deg^-1/2 (A_hat^T_ji = dis_i w_ij dis_j).
+        For the symmetric edge lists the reference is fed (tests/test_models.py:182-185) it is the graph itself."""
+        if self._graph_t is None:
+            g = self.graph
+            ei = self.edge_index.to(g.rowptr.device)
+            t = engine.build_graph(ei.flip(0), self.edge_weight, self.num_nodes, g.rowptr.device)
+            same = torch.equal(t.rowptr, g.rowptr) and torch.equal(t.col, g.col) and (
+                (t.w is None and g.w is None) or (t.w is not None and g.w is not None and torch.equal(t.w, g.w)))
+            if same:
+                self._graph_t = g
+            else:
+                t.dis = g.dis
+                self._graph_t = t
+        return self._graph_t
 
     # ---------------------------------------------------------------- forward
     def _final_embeddings(self) -> torch.Tensor:
@@ -109,6 +145,42 @@ class LightGCN(ModelBase):
         """lightgcn.py:136-164: (user_embeddings [U,d], item_embeddings [I,d]), views of one buffer."""
         final = self._final_embeddings()
         return final[: self.num_users], final[self.num_users:]
+
+    def forward_with_grad(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The reference's forward() as it behaves under autograd (lightgcn.py:136-164): gradients flow to
+        ``embeddings.weight`` through the propagate kernels.  Not cached."""
+        if self.graph is None:
+            raise RuntimeError("Graph not set. Call set_graph() first.")
+        final = _Propagate.apply(self.embeddings.weight, self)
+        return final[: self.num_users], final[self.num_users:]
+
+    def bpr_loss(self, user_ids: torch.Tensor, pos_item_ids: torch.Tensor, neg_item_ids: torch.Tensor) -> torch.Tensor:
+        """lightgcn.py:206-245: BPR loss on the propagated embeddings + L2 on the layer-0 rows of the batch."""
+        user_embeds_0 = self.embeddings(user_ids)
+        pos_item_embeds_0 = self.embeddings(pos_item_ids + self.num_users)
+        neg_item_embeds_0 = self.embeddings(neg_item_ids + self.num_users)
+        user_embeddings, item_embeddings = self.forward_with_grad()
+        user_embeds = user_embeddings[user_ids]
+        pos_scores = (user_embeds * item_embeddings[pos_item_ids]).sum(dim=1)
+        neg_scores = (user_embeds * item_embeddings[neg_item_ids]).sum(dim=1)
+        loss = -torch.log(torch.sigmoid(pos_scores - neg_scores) + 1e-10).mean()
+        reg_loss = self.weight_decay * (
+            user_embeds_0.norm(2).pow(2) + pos_item_embeds_0.norm(2).pow(2) + neg_item_embeds_0.norm(2).pow(2)
+        ) / user_embeds_0.size(0)
+        return loss + reg_loss
+
+    def training_step(self, batch: Dict[str, Any], batch_idx: int) -> torch.Tensor:
+        """lightgcn.py:247-265."""
+        loss = self.bpr_loss(batch["user_ids"], batch["pos_items"], batch["neg_items"])
+        self.log("train_loss", loss, prog_bar=True)
+        return loss
+
+    def configure_optimizers(self):
+        """lightgcn.py:307-330 (Adam, no optimizer weight decay, ReduceLROnPlateau on val_map_at_k)."""
+        optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate, weight_decay=0.0)
+        scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode="max", factor=0.5, patience=5)
+        return {"optimizer": optimizer,
+                "lr_scheduler": {"scheduler": scheduler, "monitor": "val_map_at_k", "frequency": 1}}
 
     def predict(self, user_ids: torch.Tensor, item_ids: torch.Tensor) -> torch.Tensor:
         """lightgcn.py:166-186."""

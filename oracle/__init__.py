@@ -18,6 +18,6 @@ section "Oracle" for exactly what those stand-ins supply.
 from .lightgcn_oracle import (  # noqa: F401
     layer_weights, add_self_loops, build_norm_adj, propagate, forward,
     predict, predict_all_items, apply_filter, topk_canonical, exact_scores_fp64,
-    recommend, recommend_exact, LightGCNOracle,
+    recommend, recommend_exact, LightGCNOracle, bpr_loss,
 )
 from .ncf_oracle import ncf_forward, ncf_predict_all_items, NeuralCFOracle  # noqa: F401

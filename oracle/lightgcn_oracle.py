@@ -100,6 +100,28 @@ def forward(e0, rowptr, col, val, num_users: int, num_layers: int, alphas):
     return final[:num_users], final[num_users:]       # :161-162
 
 
+def bpr_loss(e0, rowptr, col, val, num_users: int, num_layers: int, alphas, user_ids, pos_item_ids,
+             neg_item_ids, weight_decay: float):
+    """src/models/lightgcn.py:206-245, differentiable w.r.t. ``e0`` through the dense restatement of the
+    propagation (small graphs only: A_hat is densified so that plain autograd applies)."""
+    n = rowptr.numel() - 1
+    a = torch.sparse_csr_tensor(rowptr, col, val.to(e0.dtype), size=(n, n), check_invariants=False).to_dense()
+    embs, e = [e0], e0
+    for _ in range(num_layers):                       # :151-153
+        e = a @ e
+        embs.append(e)
+    final = torch.zeros_like(e0)
+    for i, x in enumerate(embs):                      # :156-158
+        final = final + alphas[i] * x
+    ue, ie = final[:num_users], final[num_users:]
+    u0, p0, n0 = e0[user_ids], e0[pos_item_ids + num_users], e0[neg_item_ids + num_users]   # :218-220
+    pos = (ue[user_ids] * ie[pos_item_ids]).sum(dim=1)                                      # :225-232
+    neg = (ue[user_ids] * ie[neg_item_ids]).sum(dim=1)
+    loss = -torch.log(torch.sigmoid(pos - neg) + 1e-10).mean()                              # :235
+    reg = weight_decay * (u0.norm(2).pow(2) + p0.norm(2).pow(2) + n0.norm(2).pow(2)) / u0.size(0)   # :238-243
+    return loss + reg
+
+
 def predict(user_emb, item_emb, user_ids, item_ids):
     """Row-wise dot product.  src/models/lightgcn.py:180-184."""
     return (user_emb[user_ids] * item_emb[item_ids]).sum(dim=1)

@@ -316,3 +316,68 @@ def test_non_bipartite_graph_is_detected_and_not_chunked(hnm_lib):
     ou, oi = orc.forward()
     assert_close(gu, ou, what="users")
     assert_close(gi, oi, what="items")
+
+
+@pytest.mark.parametrize("symmetric,weighted,alpha", [(True, False, None), (True, True, 0.5), (False, True, None)])
+def test_bpr_loss_gradients_match_autograd_oracle(hnm_lib, symmetric, weighted, alpha):
+    """forward_with_grad(): the backward pass is the propagate kernels on the transposed adjacency
+    (dL/dE0 = sum_l alpha_l (A_hat^T)^l dL/dfinal).  Loss and gradient of bpr_loss (lightgcn.py:206-245) against
+    plain autograd through a dense fp64 restatement -- also for an edge list that is NOT symmetric."""
+    from hnm_recommendation_b200 import LightGCN
+    U, I, d, L, E, B = 180, 70, 64, 3, 1500, 256
+    gen = torch.Generator().manual_seed(11)
+    u = torch.randint(0, U, (E,), generator=gen)
+    i = torch.randint(0, I, (E,), generator=gen) + U
+    if symmetric:
+        ei = torch.stack([torch.cat([u, i]), torch.cat([i, u])])
+        half = torch.rand(E, generator=gen) + 0.5
+        ew = torch.cat([half, half]) if weighted else None
+    else:
+        keep = torch.rand(E, generator=gen) < 0.6                      # only some reverse edges exist
+        ei = torch.stack([torch.cat([u, i[keep]]), torch.cat([i, u[keep]])])
+        ew = torch.rand(ei.size(1), generator=gen) + 0.5
+    m = LightGCN(U, I, embedding_dim=d, num_layers=L, alpha=alpha, weight_decay=1e-2).to("cuda")
+    with torch.no_grad():
+        m.embeddings.weight.copy_(torch.randn(U + I, d, generator=gen) * 0.3)
+    m.set_graph(ei, ew)
+    uid = torch.randint(0, U, (B,), generator=gen)
+    pos = torch.randint(0, I, (B,), generator=gen)
+    neg = torch.randint(0, I, (B,), generator=gen)
+    loss = m.training_step({"user_ids": uid.cuda(), "pos_items": pos.cuda(), "neg_items": neg.cuda()}, 0)
+    loss.backward()
+    grad = m.embeddings.weight.grad
+    assert (m._adjoint_graph() is m.graph) == symmetric
+
+    rowptr, col, val, _ = O.build_norm_adj(ei, ew, U + I, dtype=torch.float64)
+    w64 = m.embeddings.weight.detach().cpu().double().requires_grad_()
+    want = O.bpr_loss(w64, rowptr, col, val, U, L, m.alpha, uid, pos, neg, m.weight_decay)
+    want.backward()
+    assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
+    assert_close(grad, w64.grad, rtol=1e-4, atol_scale=1e-5, what="dL/d embeddings.weight")
+    # forward() itself stays the cached inference path
+    assert not m.forward()[0].requires_grad
+    # an optimizer step through the reference's configuration changes the weights and invalidates the cache
+    before = m.forward()[0].clone()
+    opt = m.configure_optimizers()["optimizer"]
+    opt.step()
+    assert not torch.equal(m.forward()[0], before)
+
+
+@pytest.mark.parametrize("path", golden_files("train"), ids=lambda p: p.split("train_")[-1][:-4])
+def test_training_step_matches_reference_golden(hnm_lib, path):
+    """training_step -> bpr_loss -> backward through the propagate kernels, against the loss and gradient of
+    the reference's own training_step on the same inputs (tests/golden/make_golden_train.py)."""
+    from hnm_recommendation_b200 import LightGCN
+    g = load_golden(path)
+    alpha = None if np.isnan(g["alpha"]) else float(g["alpha"])
+    m = LightGCN(int(g["num_users"]), int(g["num_items"]), embedding_dim=int(g["embedding_dim"]),
+                 num_layers=int(g["num_layers"]), alpha=alpha, weight_decay=float(g["weight_decay"]))
+    m.load_state_dict({"embeddings.weight": torch.from_numpy(g["weight"])})
+    m = m.to("cuda")
+    ew = torch.from_numpy(g["edge_weight"]) if g["edge_weight"].size else None
+    m.set_graph(torch.from_numpy(g["edge_index"]), ew)
+    batch = {k: torch.from_numpy(g[k]).cuda() for k in ("user_ids", "pos_items", "neg_items")}
+    loss = m.training_step(batch, 0)
+    loss.backward()
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
+    assert_close(m.embeddings.weight.grad, g["grad"], rtol=1e-4, atol_scale=1e-5, what="gradient")

@@ -105,3 +105,25 @@ def test_ncf_oracle_matches_reference(path):
     assert_close(alls, g["all_scores"], what="all_scores")
     assert torch.equal(O.topk_canonical(torch.from_numpy(g["all_scores"]), int(g["top_k"])),
                        torch.from_numpy(g["topk_canonical"]))
+
+
+TRAIN = golden_files("train")
+
+
+@pytest.mark.parametrize("path", TRAIN, ids=lambda p: p.split("train_")[-1][:-4])
+def test_bpr_loss_oracle_matches_reference(path):
+    """oracle.bpr_loss (dense fp64 restatement + plain autograd) against the loss and the gradient the
+    reference's own LightGCN.training_step produced (tests/golden/make_golden_train.py)."""
+    g = load_golden(path)
+    U, L = int(g["num_users"]), int(g["num_layers"])
+    n = U + int(g["num_items"])
+    alpha = None if np.isnan(g["alpha"]) else float(g["alpha"])
+    ew = torch.from_numpy(g["edge_weight"]) if g["edge_weight"].size else None
+    rowptr, col, val, _ = O.build_norm_adj(torch.from_numpy(g["edge_index"]), ew, n, dtype=torch.float64)
+    w = torch.from_numpy(g["weight"]).double().requires_grad_()
+    loss = O.bpr_loss(w, rowptr, col, val, U, L, O.layer_weights(L, alpha), torch.from_numpy(g["user_ids"]),
+                      torch.from_numpy(g["pos_items"]), torch.from_numpy(g["neg_items"]), float(g["weight_decay"]))
+    loss.backward()
+    assert len(TRAIN) >= 2
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
+    assert_close(w.grad, g["grad"], rtol=1e-4, atol_scale=1e-5, what="gradient")
