@@ -230,9 +230,12 @@ def run_gpu(args):
         wt = model.embeddings.weight.data
         for a, b in h2d_rows:
             wt[a:b].copy_(w_host[a:b], non_blocking=True)                   # H2D of the step's input
-        ids = sharded.recommend_all() if sharded else model.recommend_all()
-        a, b = d2h_rows
-        out_host[a:b].copy_(ids[a:b], non_blocking=True)                    # D2H of the step's result
+        if sharded:
+            ids = sharded.recommend_all()
+            a, b = d2h_rows
+            out_host[a:b].copy_(ids[a:b], non_blocking=True)                # D2H of the step's result
+        else:
+            model.recommend_all(out_host=out_host)                          # D2H streamed chunk by chunk
         torch.cuda.current_stream().synchronize()
 
     sampler = ClockSampler(local)

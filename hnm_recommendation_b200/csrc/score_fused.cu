@@ -44,7 +44,7 @@ constexpr int kSlots = kMU;                 // one TMEM accumulator (128 columns
 constexpr int kSuper = kUserTile * kMU;     // 384 users per CTA pass
 constexpr int kItemTile = 128;              // UMMA N
 constexpr int kStagesB = 6;
-constexpr int kBootTiles = 32;              // item tiles used to seed the bucket maxima (run twice)
+constexpr int kBootTiles = 16;              // item tiles used to seed the bucket maxima (run twice)
 constexpr int kEpiWarps = 4 * kMU;
 constexpr int kThreads = (4 + kEpiWarps) * 32;   // 512
 constexpr int kTileBytes = kItemTile * kDim * 2; // 16384 (A tile and B tile have the same shape)

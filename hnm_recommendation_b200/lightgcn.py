@@ -219,8 +219,12 @@ class LightGCN(ModelBase):
             ids, _ = engine.topk_exact(ue, ie, uids, k, excl)
         return ids
 
-    def recommend_all(self, k: Optional[int] = None, return_scores: bool = False):
-        """Full-catalog top-k for every user (the BASELINE.json headline path): [num_users, k]."""
+    def recommend_all(self, k: Optional[int] = None, return_scores: bool = False,
+                      out_host: Optional[torch.Tensor] = None):
+        """Full-catalog top-k for every user (the BASELINE.json headline path): [num_users, k].
+
+        out_host: optional pinned int64 [num_users, k] tensor that receives the ids as they are produced
+        (device-to-host copies overlap the scoring of the following users); complete when the call returns."""
         self.eval()
         k = self.top_k if k is None else int(k)
         if k > self.num_items or k <= 0:
@@ -231,9 +235,11 @@ class LightGCN(ModelBase):
             if FusedScorer.supports(self.embedding_dim, k, self.num_items):
                 if self._scorer is None:
                     self._scorer = FusedScorer(ue, ie)
-                ids, sc = self._scorer.topk(None, k, None)
+                ids, sc = self._scorer.topk(None, k, None, out_host=out_host)
             else:
                 ids, sc = engine.topk_exact(ue, ie, None, k)
+                if out_host is not None:
+                    out_host.copy_(ids)
         return (ids, sc) if return_scores else ids
 
     def _recommend_by_sort(self, ue, ie, uids, filter_items, k):

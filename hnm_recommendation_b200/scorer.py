@@ -72,13 +72,18 @@ class FusedScorer:
         self._events = []
 
     def topk(self, user_ids: Optional[torch.Tensor], k: int, filter_items: Optional[Dict[int, set]] = None,
-             fallback: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+             fallback: bool = True, out_host: Optional[torch.Tensor] = None,
+             chunk_users: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """ids [B,k] int64 (global item indices), scores [B,k] fp64; canonical (score desc, id asc).
 
         Three tiers, each only for the users the previous one could not certify:
         1. tensor-core nomination with tau tracking the (k + sel_margin)-th best score, exact rescoring;
         2. the same with a wider margin (k + 12): near-ties between the k-th score and tau disappear;
         3. exact fp64 brute force (hnm_topk_exact): exact ties, overflowing lists, anything else.
+
+        out_host (pinned int64 [B, k]): the ids are also delivered to the host, chunk of users by chunk of
+        users on a copy stream while the next chunk is being scored; the few rows the fallback tiers rewrite
+        are patched afterwards.  The call returns with out_host complete.
         """
         dev = self.item_emb.device
         uids = engine._norm_ids(user_ids, self.user_emb.size(0), dev)
@@ -93,9 +98,21 @@ class FusedScorer:
             excl = engine.exclusion_csr(uids, filter_items, dev)
         self._events = []
         sel = min(32, k + self.sel_margin)
-        for b0 in range(0, total, MAX_USERS_PER_LAUNCH):
-            b1 = min(total, b0 + MAX_USERS_PER_LAUNCH)
+        step = MAX_USERS_PER_LAUNCH
+        copy_stream = None
+        if out_host is not None:
+            if tuple(out_host.shape) != (total, k) or out_host.dtype != torch.int64 or not out_host.is_pinned():
+                raise ValueError("out_host must be a pinned int64 tensor of shape [users, k]")
+            # four chunks: the device-to-host copy of one hides behind the scoring of the next
+            step = chunk_users or max(USER_BLOCK * 256, -(-total // 4 // USER_BLOCK) * USER_BLOCK)
+            copy_stream = self._copy_stream()
+        for b0 in range(0, total, step):
+            b1 = min(total, b0 + step)
             self._launch(uids, b0, b1, k, sel, excl, ids, sc, cert)
+            if copy_stream is not None:
+                copy_stream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(copy_stream):
+                    out_host[b0:b1].copy_(ids[b0:b1], non_blocking=True)
         self.last_stats = {"users": total, "uncertified": 0, "tier2": 0, "tier3": 0}
         why = None
         self._mark("fallback_begin")
@@ -131,6 +148,14 @@ class FusedScorer:
                     ids[bad] = e_ids
                     sc[bad] = e_sc
         self._mark("fallback_end")
+        if copy_stream is not None:
+            fixed = (cert != 1).nonzero().view(-1) if (fallback and total) else None
+            if fixed is not None and fixed.numel():
+                rows = ids[fixed].cpu()                        # after the fallback tiers, on the compute stream
+                copy_stream.synchronize()
+                out_host[fixed.cpu()] = rows
+            else:
+                copy_stream.synchronize()
         if self.profile:
             torch.cuda.synchronize(dev)
             if fallback and total and why is not None:
@@ -143,6 +168,11 @@ class FusedScorer:
                     ms[n0[:-6]] = ms.get(n0[:-6], 0.0) + e0.elapsed_time(e1)
             self.stage_ms = ms
         return ids, sc
+
+    def _copy_stream(self) -> torch.cuda.Stream:
+        if getattr(self, "_cstream", None) is None:
+            self._cstream = torch.cuda.Stream(device=self.item_emb.device)
+        return self._cstream
 
     def _mark(self, name: str) -> None:
         if self.profile:

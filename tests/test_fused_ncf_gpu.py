@@ -197,3 +197,21 @@ def test_ncf_recommend_filter_and_errors(hnm_lib):
     cpu_model = NeuralCF(10, 10)
     with pytest.raises(RuntimeError, match="CUDA"):
         cpu_model(torch.tensor([1]), torch.tensor([1]))
+
+
+def test_streamed_host_delivery_matches_device_result(hnm_lib):
+    """topk(out_host=...): ids reach pinned host memory chunk by chunk on a copy stream; rows rewritten by the
+    fallback tiers are patched.  Near-duplicate items force some users through the fallback."""
+    from hnm_recommendation_b200.scorer import FusedScorer
+    ue, ie = _emb(3000, 2000, seed=77)
+    ie[1000:] = ie[:1000]                                     # exact ties: every user needs the fallback
+    ie[1500:] += 1e-3                                          # ... except where the twins are told apart
+    sc = FusedScorer(ue.cuda(), ie.cuda())
+    want, _ = sc.topk(None, 12)
+    assert sc.last_stats["uncertified"] > 0
+    host = torch.empty(3000, 12, dtype=torch.int64).pin_memory()
+    host.fill_(-1)
+    got, _ = sc.topk(None, 12, out_host=host, chunk_users=640)          # five chunks
+    assert torch.equal(got, want) and torch.equal(host, want.cpu())
+    with pytest.raises(ValueError):
+        sc.topk(None, 12, out_host=torch.empty(3000, 12, dtype=torch.int64))   # not pinned
