@@ -886,13 +886,13 @@ rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ ite
 // so "k contenders above the cut" holds for the same users as before.
 constexpr int kRows2 = 16;                 // items per pass-2 round
 constexpr int kStride1 = 68;               // floats per staged fp32 row (16-byte aligned, LDS.128 conflict free)
-constexpr int kStride2 = 65;               // doubles per staged product row
+constexpr int kStride2 = 66;               // doubles per staged product row (16-byte aligned, LDS.128 conflict free)
 constexpr int kMaxSel = 128;               // pass-1 survivors a user may have (more: not certified)
 constexpr int kRescorePrefetch = 4096;     // users ahead whose inputs are pulled into the L2 (> users resident on the GPU)
-static_assert(32 * kStride1 * 4 <= kRows2 * kStride2 * 8 + 384, "tile union");
+static_assert(32 * kStride1 * 4 <= (kRows2 * kStride2 + 32) * 8, "tile union");
 
 struct __align__(16) RescoreSmem {
-  double tile[kRows2 * kStride2 + 48];     // pass 1: float [32][kStride1]; pass 2: double [16][kStride2]
+  double tile[kRows2 * kStride2 + 32];     // pass 1: float [32][kStride1]; pass 2: double [16][kStride2]
   double sc[kMaxContenders];               // contender scores
   float uf[kDim];
   int id[kMaxContenders];
@@ -951,15 +951,17 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   const float4 uf = ldg_f4(urow + sub * 4);
   if (half == 0) *reinterpret_cast<float4*>(sm.uf + sub * 4) = uf;
   const double ud0 = (double)uf.x, ud1 = (double)uf.y, ud2 = (double)uf.z, ud3 = (double)uf.w;
-  double un = 0.0, uc = 0.0, uc_abs = 0.0, cn = 0.0;
+  // u.c in fp64 (it enters the cut); the three quantities that only feed error bounds as fp32 upper bounds
+  double uc = 0.0;
+  float un2 = 0.f, uc_absf = 0.f, cn2 = 0.f;
   if (half == 0) {
-    un = fma(ud0, ud0, un); un = fma(ud1, ud1, un); un = fma(ud2, ud2, un); un = fma(ud3, ud3, un);
+    un2 = fmaf(uf.x, uf.x, fmaf(uf.y, uf.y, fmaf(uf.z, uf.z, uf.w * uf.w)));
     if (center) {
       const float4 cf = ldg_f4(center + sub * 4);
-      const double c0 = (double)cf.x, c1 = (double)cf.y, c2 = (double)cf.z, c3 = (double)cf.w;
-      uc = fma(ud0, c0, uc); uc = fma(ud1, c1, uc); uc = fma(ud2, c2, uc); uc = fma(ud3, c3, uc);
-      uc_abs = fabs(ud0 * c0) + fabs(ud1 * c1) + fabs(ud2 * c2) + fabs(ud3 * c3);
-      cn = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+      uc = fma(ud0, (double)cf.x, uc); uc = fma(ud1, (double)cf.y, uc);
+      uc = fma(ud2, (double)cf.z, uc); uc = fma(ud3, (double)cf.w, uc);
+      uc_absf = fabsf(uf.x * cf.x) + fabsf(uf.y * cf.y) + fabsf(uf.z * cf.z) + fabsf(uf.w * cf.w);
+      cn2 = fmaf(cf.x, cf.x, fmaf(cf.y, cf.y, fmaf(cf.z, cf.z, cf.w * cf.w)));
     }
   }
 
@@ -982,24 +984,23 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   groups = min(groups, kMaxGroups);
 
 #pragma unroll
-  for (int off = 8; off; off >>= 1) {          // the four sums live on lanes 0..15
-    un += __shfl_xor_sync(0xffffffffu, un, off);
+  for (int off = 16; off; off >>= 1) {         // lanes 16..31 contribute zeros
+    un2 += __shfl_xor_sync(0xffffffffu, un2, off);
     uc += __shfl_xor_sync(0xffffffffu, uc, off);
-    uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
-    cn += __shfl_xor_sync(0xffffffffu, cn, off);
+    uc_absf += __shfl_xor_sync(0xffffffffu, uc_absf, off);
+    cn2 += __shfl_xor_sync(0xffffffffu, cn2, off);
   }
-  un = __shfl_sync(0xffffffffu, un, 0);
-  uc = __shfl_sync(0xffffffffu, uc, 0);
-  uc_abs = __shfl_sync(0xffffffffu, uc_abs, 0);
-  cn = __shfl_sync(0xffffffffu, cn, 0);
-  un = sqrt(un);
+  // fp32 sums of 64 non-negative terms are within 64 * 2^-24 of the truth: 1.00002 makes them upper bounds
+  const double un = (double)(sqrtf(un2) * 1.00002f);
+  const double cn_norm = (double)(sqrtf(cn2) * 1.00002f);
+  const double uc_abs = (double)(uc_absf * 1.00002f);
   // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
   const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)kDim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
   const double cut = (double)thr * inv_scale + eps + uc;
   const float cutf = __double2float_rd(cut);                // a_j + rad <= cutf  =>  u.x_j <= cut
   // fp32 dot product radius: 2 gamma_64 ||u|| ||x_j||, ||x_j|| <= max ||x - c|| + ||c||; the absolute term
   // covers products that underflow in fp32
-  const float rad = __double2float_ru(7.62939453125e-6 * un * (max_item_norm + sqrt(cn)) * 1.0001 + 1e-36);
+  const float rad = __double2float_ru(7.62939453125e-6 * un * (max_item_norm + cn_norm) * 1.0001 + 1e-36);
   __syncwarp();
 
   // 2. g_(k) over (at most the first 32 of) the kept groups whose four items all exist and are not excluded
@@ -1050,15 +1051,14 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     if (it < num_cand_items) item = (int)sm.col[it / kGroup] + (it % kGroup);
     bool live = item >= 0 && item < num_items_local;        // columns past the catalog are zero padding
     if (live && ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)item)) live = false;
-    const int litem = live ? item : -1;
+    const int litem = live ? item : 0;                      // dead slots fetch row 0; their result is not used
 #pragma unroll
     for (int h0 = 0; h0 < 16; h0 += 8) {
       float4 v[8];
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         const int il = __shfl_sync(0xffffffffu, litem, 2 * (h0 + s) + half);
-        v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (il >= 0) v[s] = ldg_f4(item_emb + (size_t)il * kDim + sub * 4);
+        v[s] = ldg_f4(item_emb + (size_t)il * kDim + sub * 4);
       }
 #pragma unroll
       for (int s = 0; s < 8; ++s)
@@ -1095,25 +1095,19 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   for (int base = 0; base < nsel; base += kRows2) {
     {
       // all eight row loads of this half warp are issued before the first one is used
+      // (slots past the last survivor repeat it: no predicates, and nobody reads those rows)
       float4 v[kRows2 / 2];
 #pragma unroll
       for (int s = 0; s < kRows2 / 2; ++s) {
-        const int l = 2 * s + half;
-        v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (base + l < nsel) {
-          const int it = sm.sel[base + l];
-          const int item = (int)sm.col[it / kGroup] + (it % kGroup);
-          v[s] = ldg_f4(item_emb + (size_t)item * kDim + sub * 4);
-        }
+        const int it = sm.sel[min(base + 2 * s + half, nsel - 1)];
+        const int item = (int)sm.col[it / kGroup] + (it % kGroup);
+        v[s] = ldg_f4(item_emb + (size_t)item * kDim + sub * 4);
       }
 #pragma unroll
       for (int s = 0; s < kRows2 / 2; ++s) {
-        const int l = 2 * s + half;
-        if (base + l < nsel) {
-          double* t = sm.tile + l * kStride2 + sub * 4;
-          t[0] = ud0 * (double)v[s].x; t[1] = ud1 * (double)v[s].y; t[2] = ud2 * (double)v[s].z;
-          t[3] = ud3 * (double)v[s].w;
-        }
+        double2* t = reinterpret_cast<double2*>(sm.tile + (2 * s + half) * kStride2 + sub * 4);
+        t[0] = make_double2(ud0 * (double)v[s].x, ud1 * (double)v[s].y);
+        t[1] = make_double2(ud2 * (double)v[s].z, ud3 * (double)v[s].w);
       }
     }
     __syncwarp();
@@ -1123,9 +1117,13 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     if (mine2) {
       const int it = sm.sel[base + lane];
       item = (int)sm.col[it / kGroup] + (it % kGroup);
-      const double* t = sm.tile + lane * kStride2;
-#pragma unroll 16
-      for (int kk = 0; kk < kDim; ++kk) acc = __dadd_rn(t[kk], acc);   // == fma(u_k, x_k, acc): the product is exact
+      const double2* t = reinterpret_cast<const double2*>(sm.tile + lane * kStride2);
+#pragma unroll 8
+      for (int kk = 0; kk < kDim / 2; ++kk) {          // == fma(u_k, x_k, acc) for k = 0..63: the products are exact
+        const double2 pr = t[kk];
+        acc = __dadd_rn(pr.x, acc);
+        acc = __dadd_rn(pr.y, acc);
+      }
     }
     const bool c = mine2 && acc > cut;
     const unsigned mask = __ballot_sync(0xffffffffu, c);
@@ -1135,25 +1133,24 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     __syncwarp();
   }
   if (total <= 32) {
-    // the rule: one contender per lane, one warp-wide bitonic sort
-    double ms = lane < total ? sm.sc[lane] : -INFINITY;
-    int mi = lane < total ? sm.id[lane] : INT32_MAX;
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, ms, stride);
-        const int oi = __shfl_xor_sync(0xffffffffu, mi, stride);
-        const bool lower = (lane & stride) == 0;
-        const bool desc = (lane & size) == 0;
-        const bool other_first = before32(os, oi, ms, mi);
-        const bool take = (lower == desc) ? other_first : !other_first && !(os == ms && oi == mi);
-        if (take) { ms = os; mi = oi; }
-      }
+    // the rule: one contender per lane; its rank = how many contenders come before it (the (score, id) pairs
+    // are distinct), `total` broadcast rounds instead of a 15-step sorting network on doubles
+    const double ms = lane < total ? sm.sc[lane] : -INFINITY;
+    const int mi = lane < total ? sm.id[lane] : INT32_MAX;
+    int rank = 0;
+    for (int r = 0; r < total; ++r) {
+      const double os = __shfl_sync(0xffffffffu, ms, r);
+      const int oi = __shfl_sync(0xffffffffu, mi, r);
+      rank += before32(os, oi, ms, mi) ? 1 : 0;
     }
-    if (lane < k) {
-      out_ids[(size_t)b * k + lane] = mi == INT32_MAX ? INT64_MAX : item_begin + (int64_t)mi;
-      out_scores[(size_t)b * k + lane] = ms;
+    if (lane < total) {
+      if (rank < k) {
+        out_ids[(size_t)b * k + rank] = item_begin + (int64_t)mi;
+        out_scores[(size_t)b * k + rank] = ms;
+      }
+    } else if (lane < k) {                                    // fewer than k contenders: the user is not certified
+      out_ids[(size_t)b * k + lane] = INT64_MAX;
+      out_scores[(size_t)b * k + lane] = -INFINITY;
     }
   } else {
     // the exception (many near ties around the k-th score): k rounds of warp argmax over the list
