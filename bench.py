@@ -41,8 +41,10 @@ DIM = 64
 LAYERS = 3
 METRIC = "users/sec full-catalog top-12 (LightGCN 3-layer dim-64 propagate + score + top-12)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this very
-# command at N = 1 (profiles/r1_bench.md); not measured live -- a run under a profiler is never a bench run.
-NCU_DRAM_BYTES = {"fused": 0.29e9 + 0.99e9, "spmm_layer": 3.1e9 + 0.57e9}
+# command at N = 1 (profiles/r1b_top_kernels.tsv); not measured live -- a run under a profiler is never a bench
+# run.  spmm_layer = warp-per-row kernel (3.12 + 0.76 GB) + whole-CTA long-row kernel (1.37 + 0.01 GB); the
+# cluster kernel for the 457 longest rows was not in the capture.
+NCU_DRAM_BYTES = {"fused": 0.326e9 + 1.099e9, "spmm_layer": 3.118e9 + 0.760e9 + 1.375e9 + 0.007e9}
 
 
 def peaks():
@@ -276,7 +278,7 @@ def run_gpu(args):
         "data": "synthetic",
         "config": {"workload": name, "top_k": K_TOP, "embedding_init": "xavier_uniform seed 42",
                    "l2": "inputs larger than L2 (378 MB embedding table, 175 MB fp16 user operand); no explicit flush",
-                   "parallelism": "single GPU" if world == 1 else f"{sharded.mode}-sharded scoring + row-sharded propagation (all-gather per layer) x{world}"},
+                   "parallelism": "single GPU" if world == 1 else f"{sharded.mode}-sharded scoring + user-partitioned propagation (one 27 MB all-reduce of the item block per layer) x{world}"},
         "e2e": {"value": u / ms_e2e * 1e3, "unit": "users/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
         "gpu_launches": launches,
@@ -287,7 +289,7 @@ def run_gpu(args):
                      "traffic": NCU_DRAM_BYTES["fused"] if (world == 1 and args.config == "hm") else None,
                      "peak_source": pk["source"] + " (cuBLAS bf16 sustained; burst %.1f)" % pk["tflops_burst"],
                      "algorithmic_flops": flops / world, "ms": fused_ms},
-        "roofline_spmm": {"bound": "hbm", "kernel": "spmm_rows_kernel+spmm_heavy_kernel (one layer)",
+        "roofline_spmm": {"bound": "hbm", "kernel": "spmm_rows_kernel + spmm_heavy_kernel + spmm_huge_kernel (one layer)",
                           "achieved": spmm_alg_bytes / world / spmm_ms / 1e6 if spmm_ms else None,
                           "peak": pk["hbm_gbs"], "unit": "GB/s",
                           "frac": spmm_alg_bytes / world / spmm_ms / 1e6 / pk["hbm_gbs"] if spmm_ms else None,
