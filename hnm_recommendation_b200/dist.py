@@ -165,7 +165,11 @@ class ShardedLightGCN:
                 ue, ie = self.forward(all_rows=False)
                 u0, u1 = p.user_slices[p.rank]
                 ids, sc = self.backend.local_topk(self, ue[u0:u1], ie, 0, k)           # my users vs all items
-                out_ids = self.coll.allgather_slices(ids, p.user_slices, m.num_users)
+                if m.num_items < 2 ** 31:
+                    # item ids fit 32 bits: half the bytes on the wire (66 instead of 132 MB at the H&M shape)
+                    out_ids = self.coll.allgather_slices(ids.to(torch.int32), p.user_slices, m.num_users).long()
+                else:
+                    out_ids = self.coll.allgather_slices(ids, p.user_slices, m.num_users)
                 if return_scores:
                     return out_ids, self.coll.allgather_slices(sc, p.user_slices, m.num_users)
                 return out_ids
@@ -207,7 +211,8 @@ class CudaBackend:
             self._shard_key = key
 
         def allreduce(buf):
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=coll.group)
+            # asynchronous on NCCL: the caller overlaps it with the rank's own user rows and waits on the handle
+            return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=coll.group, async_op=coll.nccl)
 
         acc = engine.propagate_user_sharded(m.graph, self._shard, m.embeddings.weight, m.alpha, m.num_layers,
                                             m.num_users, allreduce)

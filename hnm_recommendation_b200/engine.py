@@ -374,14 +374,18 @@ def propagate_user_sharded(graph: Graph, shard: UserShard, e0: torch.Tensor, alp
         sh_heavy = ptr(shard.heavy_rows) if shard.heavy_rows.numel() else None
         for layer in range(1, num_layers + 1):
             last = layer == num_layers
+            call("hnm_lightgcn_partial", ptr(shard.seg_begin), ptr(shard.seg_end), ptr(graph.col), ptr(graph.w),
+                 ptr(cur), ptr(part), d, U, n, sh_heavy, int(shard.heavy_rows.numel()), shard.num_huge,
+                 graph.heavy_threshold, 0, s)
+            # the all-reduce may be asynchronous (it then returns a handle): this rank's user rows, which
+            # need neither `part` nor the other ranks, are gathered while the partial sums travel
+            pending = allreduce_items(part)
             if u1 > u0:
                 call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
                      None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, u0, u1, heavy, graph.num_heavy,
                      graph.num_huge, graph.heavy_threshold, s)
-            call("hnm_lightgcn_partial", ptr(shard.seg_begin), ptr(shard.seg_end), ptr(graph.col), ptr(graph.w),
-                 ptr(cur), ptr(part), d, U, n, sh_heavy, int(shard.heavy_rows.numel()), shard.num_huge,
-                 graph.heavy_threshold, 0, s)
-            allreduce_items(part)
+            if pending is not None:
+                pending.wait()
             call("hnm_lightgcn_finish", ptr(part), ptr(cur), ptr(graph.dis), float(alphas[layer]),
                  None if last else ptr(nxt), ptr(acc), U, I, d, s)
             if not last:

@@ -133,12 +133,14 @@ class FusedScorer:
                     sc2 = torch.empty(n_bad, k, dtype=torch.float64, device=dev)
                     cert2 = torch.empty(n_bad, dtype=torch.int32, device=dev)
                     self._launch(bad_uids, 0, n_bad, k, sel2, sub_excl, ids2, sc2, cert2, mark=False)
-                    ok2 = cert2 == 1
-                    ids[bad[ok2]] = ids2[ok2]
-                    sc[bad[ok2]] = sc2[ok2]
+                    # every tier-2 row is written back (the still uncertified ones are overwritten by tier 3):
+                    # two scatters and one host read instead of a mask, four gathers and two scatters
+                    ids.index_copy_(0, bad, ids2)
+                    sc.index_copy_(0, bad, sc2)
                     self.last_stats["tier2"] = n_bad
-                    bad = bad[~ok2]
-                    bad_uids = bad_uids[~ok2]
+                    rest = (cert2 != 1).nonzero().view(-1)
+                    bad = bad[rest]
+                    bad_uids = bad_uids[rest]
                     if bad.numel() and excl[0] is not None:
                         sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev)
                 if bad.numel():
