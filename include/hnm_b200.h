@@ -178,7 +178,12 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
  *              exact_kth > tau / (su*si) + eps + u.c,
  *              eps = 1.1 * 2^-10 * ||u|| * max_j ||x_j - c|| + dim * 2^-8 / (su*si)
  *          that no non-candidate can belong to the top-k given the fp16 rounding bound.
- * Users whose certificate fails are re-run through hnm_topk_exact by the caller.
+ *          Only items that can still be in the top-k get the fp64 chain: groups below the k-th best
+ *          nominated group (minus 2 eps) are dropped, then an fp32 dot product with a rigorous error
+ *          radius drops items below that same bound or below the cut.  The returned scores are the
+ *          bits of the fp64 chain (exact fp64 products added in the order k = 0..dim-1).
+ * Users whose certificate fails are re-run by the caller: the same three calls with a wider kth_sel,
+ * then hnm_topk_exact for what is left.
  * ---------------------------------------------------------------------- */
 #define HNM_FUSED_DIM 64            /* embedding dimension of the tensor-core path */
 #define HNM_FUSED_USER_TILE 128     /* users per accumulator (UMMA M); users_padded must be a multiple */
