@@ -6,6 +6,8 @@
 //   hnm_score_topk_fused        : TMA -> smem (128B swizzle) -> tcgen05.mma (fp16 x fp16 -> fp32
 //                                 accumulators in TMEM) -> tcgen05.ld epilogue that keeps, per user,
 //                                 every item whose approximate score beats a running threshold
+//   merge_split_kernel          : (inside hnm_score_topk_fused) one list + one threshold per user out of the
+//                                 per-slice lists of the user tiles whose item range was sliced over the CTAs
 //   hnm_rescore_topk            : exact fp64 scores of the survivors, canonical top-k, certificate
 //
 // Kernel shape (DESIGN.md "score_topk"): one persistent CTA per SM, 16 warps:
@@ -27,6 +29,9 @@
 // candidate list in global memory.  tau is refreshed (in-place sorting network over the bucket
 // registers) every time the number of item tiles seen has grown by 1/4.  The first kBootTiles item
 // tiles are run twice: once to seed the buckets, once to collect.
+//
+// Work distribution (SplitPlan below): whole passes of 3 user tiles x the whole catalog per CTA, and the
+// left-over tiles in triples whose item range is cut into slices, one (triple, slice) per CTA.
 #include <algorithm>
 #include <cuda.h>
 #include <cudaTypedefs.h>
