@@ -111,6 +111,16 @@ class Collectives:
         return out
 
     def allgather_slices(self, mine: torch.Tensor, slices: Sequence[Tuple[int, int]], total: int) -> torch.Tensor:
+        sizes = [b - a for a, b in slices]
+        if self.world > 1 and len(set(sizes)) > 1 and max(sizes) > 0:
+            # slices that differ by a row or two (1 371 980 users over 8 ranks): pad them to one size so that a
+            # single all-gather kernel does the exchange instead of 2 (G - 1) point-to-point operations per rank
+            rows = max(sizes)
+            padded = torch.empty((self.world, rows) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+            padded[self.rank, :sizes[self.rank]] = mine
+            dist.all_gather_into_tensor(padded.view((self.world * rows,) + tuple(mine.shape[1:])), padded[self.rank],
+                                        group=self.group)
+            return torch.cat([padded[r, :sizes[r]] for r in range(self.world)])
         out = torch.empty((total,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
         a, b = slices[self.rank]
         out[a:b] = mine
