@@ -133,3 +133,58 @@ def test_fused_work_plan_covers_every_tile_pair_once(hnm_lib, user_tiles, item_t
     need = triples * 3 * 128 * slices * (256 * 8 + 8) if slices > 1 else 0
     assert ws >= need and ws <= need + 4096
     assert hnm_lib.hnm_score_topk_fused_workspace_bytes(100, 128) < 0
+
+
+def _cpu_graph(num_users, num_items, edges, seed, extra=None):
+    """engine.Graph over CPU tensors built from the oracle's CSR (the host-side helpers are plain torch ops)."""
+    import oracle as O
+    from hnm_recommendation_b200 import engine
+    gen = torch.Generator().manual_seed(seed)
+    u = torch.randint(0, num_users, (edges,), generator=gen)
+    i = torch.randint(0, num_items, (edges,), generator=gen) + num_users
+    ei = torch.stack([torch.cat([u, i]), torch.cat([i, u])])
+    if extra is not None:
+        ei = torch.cat([ei, torch.tensor(extra, dtype=torch.long).t()], dim=1)
+    n = num_users + num_items
+    rowptr, col, _, dis = O.build_norm_adj(ei, None, n)
+    return engine.Graph(n, int(col.numel()), rowptr.to(torch.int32), col.to(torch.int32), None, dis,
+                        torch.zeros(0, dtype=torch.int32))
+
+
+def test_user_shards_and_item_chunks_partition_every_item_row():
+    """make_user_shard / make_item_chunks: for every item row the per-shard sub-ranges are contiguous, disjoint,
+    ordered, and together cover exactly the row's user entries (everything but the self loop)."""
+    from hnm_recommendation_b200 import engine
+    U, I = 157, 41
+    g = _cpu_graph(U, I, 900, seed=3)
+    assert engine.is_bipartite(g, U)
+    ic = engine.make_item_chunks(g, U, I, 64, num_chunks=5)
+    assert ic is not None and len(ic.chunks) == 5
+    assert [sh.u0 for sh in ic.chunks] == [0, 32, 64, 95, 126] and ic.chunks[-1].u1 == U
+    rp, col = g.rowptr.long(), g.col.long()
+    for r in range(I):
+        lo, hi = int(rp[U + r]), int(rp[U + r + 1])
+        assert int(col[hi - 1]) == U + r                                   # the self loop closes the row
+        pos = lo
+        for sh in ic.chunks:
+            b, e = int(sh.seg_begin[r]), int(sh.seg_end[r])
+            assert b == pos and b <= e
+            assert bool(((col[b:e] >= sh.u0) & (col[b:e] < sh.u1)).all())
+            pos = e
+        assert pos == hi - 1
+    assert engine.make_item_chunks(g, U, I, 64) is None                    # opt-in: nothing by default
+    assert engine.make_item_chunks(g, U, I, 64, num_chunks=1) is None
+    # heavy-row classification follows the SUB-range length
+    sh = engine.make_user_shard(g, U, I, 0, U)
+    lengths = (sh.seg_end - sh.seg_begin).long()
+    assert sh.heavy_rows.numel() == int((lengths > g.heavy_threshold).sum()) == 0
+
+
+def test_bipartite_check_sees_user_user_and_item_item_edges():
+    from hnm_recommendation_b200 import engine
+    U, I = 30, 20
+    assert engine.is_bipartite(_cpu_graph(U, I, 200, seed=1), U)
+    assert not engine.is_bipartite(_cpu_graph(U, I, 200, seed=1, extra=[(3, 7)]), U)              # user -> user
+    assert not engine.is_bipartite(_cpu_graph(U, I, 200, seed=1, extra=[(U + 2, U + 5)]), U)      # item -> item
+    g = _cpu_graph(U, I, 200, seed=1, extra=[(3, 7)])
+    assert engine.make_item_chunks(g, U, I, 64, num_chunks=4) is None
