@@ -127,6 +127,74 @@ def cuda_ms(fn, steps, warmup, barrier=None):
     return t0.elapsed_time(t1) / steps
 
 
+# ----------------------------------------------------------------------------------------- GPU comparators
+def gpu_comparators(model, sample_users: int = 65536, chunk: int = 8192):
+    """SURVEY.md 8(d) "on-box GPU comparators": the reference's own formulation in eager PyTorch on the SAME
+    GPU -- torch.sparse CSR @ dense (cuSPARSE SpMM) for the propagation, chunked torch.matmul + torch.topk for
+    the scoring (fp32, and with TF32 allowed).  Not the product path and outside every timed region of the
+    headline; a bounded sample of users, extrapolated linearly.  Any failure is reported, never raised."""
+    try:
+        g = model.graph
+        dev = g.rowptr.device
+        n, u_total = g.num_nodes, model.num_users
+        on_gpu = dev.type == "cuda"
+
+        def ms(fn, reps):
+            fn()
+            if on_gpu:
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    fn()
+                b.record()
+                torch.cuda.synchronize(dev)
+                return a.elapsed_time(b) / reps
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0) * 1e3 / reps
+
+        with torch.no_grad():
+            rowptr, col = g.rowptr.long(), g.col.long()
+            row = torch.repeat_interleave(torch.arange(n, device=dev), rowptr[1:] - rowptr[:-1])
+            val = g.dis[row] * g.dis[col] if g.w is None else g.dis[row] * g.w * g.dis[col]    # lightgcn.py:106
+            del row
+            adj = torch.sparse_csr_tensor(rowptr, col, val, size=(n, n))
+            x = model.embeddings.weight.detach()
+            alphas = [float(a) for a in model.alpha]
+
+            def forward():                                         # lightgcn.py:147-158
+                acc, cur = alphas[0] * x, x
+                for layer in range(1, model.num_layers + 1):
+                    cur = adj @ cur
+                    acc = acc + alphas[layer] * cur
+                return acc
+
+            t_fwd = ms(forward, 3)
+            final = forward()
+            ue, ie = final[:u_total], final[u_total:]
+            nu = min(sample_users, u_total)
+
+            def score():                                           # lightgcn.py:202,356 in 8192-user batches
+                for s0 in range(0, nu, chunk):
+                    torch.topk(ue[s0:s0 + chunk] @ ie.t(), min(K_TOP, ie.size(0)), dim=1)
+
+            out = {"kind": "eager PyTorch on the same GPU (torch.sparse CSR @ dense, torch.matmul + torch.topk); "
+                           "the reference's formulation, not the product path",
+                   "propagate_ms": t_fwd, "sample_users": nu, "chunk_users": chunk}
+            prev = torch.backends.cuda.matmul.allow_tf32
+            for name, flag in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = flag
+                t = ms(score, 2)
+                out[f"score_topk_ms_{name}"] = t * u_total / nu
+                out[f"users_per_s_{name}"] = u_total / (t_fwd + t * u_total / nu) * 1e3
+            torch.backends.cuda.matmul.allow_tf32 = prev
+            return out
+    except Exception as exc:  # noqa: BLE001
+        return {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+
 # ----------------------------------------------------------------------------------------- CPU arm
 class CpuArm:
     """The oracle (CPU restatement of the reference) on the host cores: graph built once, then every
@@ -299,6 +367,7 @@ def run_gpu(args):
         "stages_ms": stages,
     }
     if world == 1 and not args.no_cpu:
+        line["gpu_comparators"] = gpu_comparators(model)
         cpu = CpuArm(u, i, e, 4096 if args.config == "hm" else u).step()
         line["cpu_baseline"] = {
             "value": cpu["users_per_s"], "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",

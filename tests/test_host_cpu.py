@@ -188,3 +188,24 @@ def test_bipartite_check_sees_user_user_and_item_item_edges():
     assert not engine.is_bipartite(_cpu_graph(U, I, 200, seed=1, extra=[(U + 2, U + 5)]), U)      # item -> item
     g = _cpu_graph(U, I, 200, seed=1, extra=[(3, 7)])
     assert engine.make_item_chunks(g, U, I, 64, num_chunks=4) is None
+
+
+def test_bench_gpu_comparators_run_device_agnostic():
+    """bench.gpu_comparators (the eager-PyTorch restatement timed beside the kernels) is plain torch:
+    it must run on CPU tensors too, report both matmul modes, and never raise."""
+    import sys
+    from types import SimpleNamespace
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+    import oracle as O
+    U, I = 200, 90
+    g = _cpu_graph(U, I, 1500, seed=4)
+    model = SimpleNamespace(graph=g, num_users=U, num_items=I, num_layers=3, alpha=O.layer_weights(3),
+                            embeddings=SimpleNamespace(weight=torch.randn(U + I, 64) * 0.1))
+    out = bench.gpu_comparators(model, sample_users=128, chunk=64)
+    assert "error" not in out, out
+    assert out["sample_users"] == 128 and out["propagate_ms"] > 0
+    assert out["users_per_s_fp32"] > 0 and out["users_per_s_tf32"] > 0
+    broken = SimpleNamespace(graph=None)
+    assert "error" in bench.gpu_comparators(broken)
