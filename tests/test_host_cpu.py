@@ -209,3 +209,28 @@ def test_bench_gpu_comparators_run_device_agnostic():
     assert out["users_per_s_fp32"] > 0 and out["users_per_s_tf32"] > 0
     broken = SimpleNamespace(graph=None)
     assert "error" in bench.gpu_comparators(broken)
+
+
+@pytest.mark.timeout(180)
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores) prints ONE JSON line with the keys the
+    driver reads; under torchrun only rank 0 works."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "config1",
+           "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=170, env=dict(os.environ, RANK="0"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "users/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1"))
+    assert other.returncode == 0 and not other.stdout.strip()
