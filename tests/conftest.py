@@ -23,6 +23,11 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     if torch.cuda.is_available():
+        # a kernel that never returns must end the run, not hang the box: hard per-test limit for GPU tests
+        # (the "thread" method works even while the interpreter is blocked inside a CUDA call)
+        for item in items:
+            if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(300, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
