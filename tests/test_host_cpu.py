@@ -234,3 +234,21 @@ def test_bench_reference_arm_json_contract():
     assert "workload" in d["config"] and "model" not in d["config"]
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1"))
     assert other.returncode == 0 and not other.stdout.strip()
+
+
+def test_header_is_c99_and_library_links_from_c(hnm_lib, tmp_path):
+    """include/hnm_b200.h compiled by gcc as strict C99, linked against libhnm_b200.so, run without a GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "hnm_recommendation_b200")
+    exe = str(tmp_path / "abi_smoke")
+    build = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "tests", "abi_smoke.c"), "-o", exe, "-L", libdir, "-l:libhnm_b200.so",
+                            f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert run.returncode == 0, (run.returncode, run.stderr)
+    assert run.stdout.strip().startswith("ok|")
