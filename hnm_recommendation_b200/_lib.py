@@ -16,6 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libhnm_b200.so")
 
 _lib: Optional[C.CDLL] = None
+ABI_VERSION = 2
 
 P = C.c_void_p
 I64 = C.c_int64
@@ -37,12 +38,13 @@ _SIGNATURES = {
     "hnm_pair_scores": (C.c_int, [P, P, P, P, I64, I32, I64, I64, P, P]),
     "hnm_score_all_items": (C.c_int, [P, P, P, I64, I64, I32, P, P]),
     "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, I32, P, P, P]),
-    "hnm_score_pack": (C.c_int, [P, P, I64, I64, I32, P, F32, P, P, P]),
+    "hnm_score_pack_items": (C.c_int, [P, I64, I64, I32, P, P, P, P]),
+    "hnm_score_pack_users": (C.c_int, [P, P, I64, I64, I32, P, P, P]),
     "hnm_absmax": (C.c_int, [P, I64, P, I32, P, P]),
     "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, P, I32, P, P, P, I64, P]),
     "hnm_score_topk_fused_workspace_bytes": (C.c_int64, [I64, I64]),
     "hnm_score_topk_fused_plan": (C.c_int, [I64, I64, P]),
-    "hnm_rescore_topk": (C.c_int, [P, P, P, I64, I32, I64, I64, P, I32, P, P, F64, F64, P, P, P, I32, P, P, P, P]),
+    "hnm_rescore_topk": (C.c_int, [P, P, P, I64, I32, I64, I64, P, I32, P, P, P, P, P, P, P, I32, P, P, P, P]),
     "hnm_merge_topk": (C.c_int, [P, P, I32, I64, I32, P, P, P]),
     "hnm_ncf_precompute": (C.c_int, [P, I64, I32, P, I32, I32, I32, P, P, P]),
     "hnm_ncf_score_pairs": (C.c_int, [P, P, P, P, P, P, I32, P, F32, P, P, I64, I32, P, P]),
@@ -73,7 +75,7 @@ def load() -> C.CDLL:
                 continue
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.hnm_abi_version() != 1:
+        if lib.hnm_abi_version() != ABI_VERSION:
             raise RuntimeError("libhnm_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

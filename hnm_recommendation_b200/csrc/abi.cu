@@ -22,7 +22,8 @@ extern "C" const char* hnm_strerror(int code) {
 extern "C" int hnm_check_device(void) {
   int dev = 0;
   HNM_CUDA_TRY(cudaGetDevice(&dev));
-  int major = 0;
+  int major = 0, minor = 0;
   HNM_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-  return major == 10 ? HNM_OK : HNM_E_ARCH;
+  HNM_CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return (major == 10 && minor == 0) ? HNM_OK : HNM_E_ARCH;      // only sm_100a code is in the library
 }

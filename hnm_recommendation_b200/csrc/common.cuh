@@ -14,15 +14,25 @@
 
 static inline bool hnm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs).
 static inline int hnm_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n > 0 ? n : 148;
   }
-  return sms;
+  return sms[dev];
+}
+
+// Function attributes are per device and a process may drive several GPUs, so the dynamic shared-memory
+// limit is (re)set on every launch; the call is a host-side table update (well under a microsecond).
+template <typename K>
+static inline cudaError_t hnm_allow_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {

@@ -224,12 +224,7 @@ int launch_score(const float* gu, const float* gi, const float* pu, const float*
   } else {
     const size_t smem = sizeof(float) * (size_t)d.tail_floats;
     if (smem > 200 * 1024) return HNM_E_DIM;
-    static bool attr_set = false;
-    if (!attr_set) {
-      HNM_CUDA_TRY(cudaFuncSetAttribute(ncf_score_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        200 * 1024));
-      attr_set = true;
-    }
+    HNM_CUDA_TRY(hnm_allow_smem(ncf_score_generic_kernel, 200 * 1024));
     const int T = 128;
     const unsigned grid = (unsigned)std::min<int64_t>((total + T - 1) / T, (int64_t)hnm_num_sms() * 8);
     ncf_score_generic_kernel<<<grid, T, smem, stream>>>(gu, gi, pu, qi, tail, d, wp, bp, mf, user_ids, item_ids,
@@ -250,11 +245,7 @@ extern "C" int hnm_ncf_precompute(const float* mlp_emb, int64_t rows, int32_t h,
   if (rows < 0 || h < 1 || h1 < 1 || col_offset < 0 || col_offset + h > w1_cols) return HNM_E_RANGE;
   const size_t smem = sizeof(float) * (size_t)h * (h1 + 1);
   if (smem > 200 * 1024) return HNM_E_DIM;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HNM_CUDA_TRY(cudaFuncSetAttribute(ncf_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  HNM_CUDA_TRY(hnm_allow_smem(ncf_precompute_kernel, 200 * 1024));
   const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)hnm_num_sms() * 8);
   ncf_precompute_kernel<<<grid, 256, smem, stream>>>(mlp_emb, rows, h, w1, h1, w1_cols, col_offset, bias, out);
   HNM_LAUNCH_CHECK();

@@ -312,11 +312,7 @@ extern "C" int hnm_topk_exact(const float* user_emb, const float* item_emb, cons
   if (k <= 0 || k > XKMAX || k > item_end - item_begin) return HNM_E_RANGE;
   const size_t smem = sizeof(Cand) * XU * XCAP + sizeof(double) * XU * (size_t)dim;
   if (smem > 200 * 1024) return HNM_E_DIM;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HNM_CUDA_TRY(cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  HNM_CUDA_TRY(hnm_allow_smem(topk_exact_kernel, 200 * 1024));
   const unsigned grid = (unsigned)((batch + XU - 1) / XU);
   const int64_t items = item_end - item_begin;
   if (item_splits < 1 || item_splits > 64 || (item_splits > 1 && items / item_splits < std::max<int64_t>(k, 1)))

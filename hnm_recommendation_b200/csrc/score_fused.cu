@@ -2,7 +2,8 @@
 // Replaces the `torch.matmul(user_embeds, item_embeddings.t())` + `torch.topk` pair of
 // src/models/lightgcn.py:202,356 without ever writing the [users, items] score matrix.
 //
-//   hnm_absmax / hnm_score_pack : fp32 table -> power-of-two scaled fp16, zero padded
+//   hnm_absmax / hnm_score_pack_items / hnm_score_pack_users : fp32 table -> power-of-two scaled fp16, zero
+//                                 padded (one scale per item shard, one per user row; scales stay on the device)
 //   hnm_score_topk_fused        : TMA -> smem (128B swizzle) -> tcgen05.mma (fp16 x fp16 -> fp32
 //                                 accumulators in TMEM) -> tcgen05.ld epilogue that keeps, per user,
 //                                 every item whose approximate score beats a running threshold
@@ -44,26 +45,45 @@ namespace {
 
 constexpr int kDim = HNM_FUSED_DIM;         // 64 fp16 = one 128-byte swizzle row
 constexpr int kUserTile = 128;              // UMMA M
-constexpr int kMU = 3;                      // user tiles per CTA
-constexpr int kSlots = kMU;                 // one TMEM accumulator (128 columns) per user tile
-constexpr int kSuper = kUserTile * kMU;     // 384 users per CTA pass
 constexpr int kItemTile = 128;              // UMMA N
-constexpr int kStagesB = 6;
 constexpr int kBootTiles = 16;              // item tiles used to seed the bucket maxima (run twice)
-constexpr int kEpiWarps = 4 * kMU;
-constexpr int kThreads = (4 + kEpiWarps) * 32;   // 512
 constexpr int kTileBytes = kItemTile * kDim * 2; // 16384 (A tile and B tile have the same shape)
 constexpr int kNumBuckets = 32;
+constexpr uint32_t kWaitHintNs = 0;         // suspend-time hint of the control warps' mbarrier waits (0 = none)
+constexpr int kMaxStagesB = 8;
+constexpr int kMaxSlots = 4;                // TMEM: 512 columns = 4 accumulators of 128 columns
+
+// Two shapes of the persistent CTA, both compiled, chosen per launch (HNM_FUSED_SHAPE, default 2x2):
+//   MU = 3, BUF = 1   three user tiles, ONE accumulator each (384 TMEM columns), 12 epilogue warps -- round 1.
+//                     An accumulator is handed back to its MMA issuer only after the epilogue has pulled it
+//                     into registers, so MMA and drain of one user tile alternate; with the light select of
+//                     this round that chain (issue 4 MMAs -> complete -> wake -> 2 TMEM round trips -> arrive
+//                     -> wake) is the step time, not any pipe.
+//   MU = 2, BUF = 2   two user tiles, TWO accumulators each (all 512 columns), 8 epilogue warps: the tensor
+//                     pipe fills buffer 1 of a tile while its warpgroup drains buffer 0.
+template <int MU_, int BUF_>
+struct Shape {
+  static constexpr int MU = MU_;                       // user tiles per CTA pass
+  static constexpr int BUF = BUF_;                     // accumulators per user tile
+  static constexpr int kSlots = MU * BUF;
+  static constexpr int kStagesB = MU == 2 ? 8 : 6;
+  static constexpr int kThreads = (4 + 4 * MU) * 32;   // 4 control warps + one epilogue warpgroup per user tile
+  static constexpr bool kSetMaxNReg = MU == 3;         // 512 threads: control warps give registers to the epilogue
+  static_assert(kSlots <= kMaxSlots && kStagesB <= kMaxStagesB && MU <= 3, "shape");
+};
 
 static_assert(kUserTile == HNM_FUSED_USER_TILE && kItemTile == HNM_FUSED_ITEM_TILE, "header mismatch");
 
 struct __align__(8) Barriers {
   uint64_t a_full[2], a_empty[2];
-  uint64_t b_full[kStagesB], b_empty[kStagesB];
-  uint64_t t_full[kSlots], t_empty[kSlots];
+  uint64_t b_full[kMaxStagesB], b_empty[kMaxStagesB];
+  uint64_t t_full[kMaxSlots], t_empty[kMaxSlots];
   uint32_t tmem_base;
 };
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + 2 * kMU * kTileBytes + kStagesB * kTileBytes + sizeof(Barriers);
+template <class S>
+constexpr size_t smem_bytes() {
+  return 1024 /*align slack*/ + 2 * S::MU * kTileBytes + S::kStagesB * kTileBytes + sizeof(Barriers);
+}
 
 // ----------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,6 +107,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// The same wait with a suspend-time hint: the thread may stay descheduled for up to `ns` nanoseconds (it is
+// woken as soon as the phase completes).  The four control warps sit in these waits most of the time; with the
+// default (short) time limit their polling loops were 74 of the 170 warp instructions issued per 32-column
+// chunk (profiles/r1_fused_notes.md), competing with the epilogue warps of the same scheduler for issue slots.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (ns == 0) { mbar_wait(bar, parity); return; }
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns)
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -205,64 +242,90 @@ __device__ __forceinline__ float refresh_tau(float (&bm)[kNumBuckets], int kth) 
   return t;
 }
 
-// 32 accumulator columns of one user row = 8 groups of 4 columns.  A group is both a bucket of the
-// threshold estimator and the unit that gets nominated: when its maximum beats tau the pair
-// {maximum, first column} is appended and hnm_rescore_topk rescores its four items exactly.
-// The common case (nothing in the chunk beats tau) is ~30 straight-line instructions and one
-// branch; the rare case is 8 predicated stores.  Earlier versions branched per group and inlined a
-// per-element scan: the kernel then spent most of its time stalled on instruction fetch
-// (profiles/r1_fused_notes.md).
+// One nominated 32-column chunk of one user row: the chunk's eight group maxima (groups of 4 adjacent
+// items), each cut to its upper 16 bits (bf16, truncated toward zero; q.x = {low half: group 0, high half:
+// group 1}, ...), and the LOCAL index of the chunk's first item.  The two parts live in two arrays so that
+// an entry costs 20 bytes of DRAM traffic and both are read back coalesced.
+struct CandList {
+  uint4* q;           // [rows * cap]
+  uint32_t* col;      // [rows * cap]
+  __host__ __device__ CandList at(size_t off) const { return CandList{q + off, col + off}; }
+};
+static_assert(HNM_FUSED_CAND_BYTES == sizeof(uint4) + sizeof(uint32_t), "header mismatch");
+static inline CandList cand_list(void* base, size_t rows, int cap) {
+  return CandList{reinterpret_cast<uint4*>(base),
+                  reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(base) + rows * (size_t)cap * sizeof(uint4))};
+}
+
+// A stored 16-bit pattern t stands for the interval [lo, hi] that contains the group maximum q:
+// truncation toward zero gives t <= q < t + ulp for q >= 0 and t - ulp < q <= t for q < 0.
+__device__ __forceinline__ void cand_bounds(uint32_t h16, float& lo, float& hi) {
+  const float t = __uint_as_float(h16 << 16);
+  const float far = __uint_as_float((h16 + 1u) << 16);      // one bf16 step away from zero (may be +-inf)
+  const bool neg = (h16 & 0x8000u) != 0u;
+  lo = neg ? far : t;
+  hi = neg ? t : far;
+}
+
+// 32 accumulator columns of one user row = 8 groups of 4 columns.  The hot path is the 8 group maxima, the
+// chunk maximum and ONE compare-and-branch: 21 ALU-pipe instructions (FMNMX / FMNMX3 issue every other
+// cycle per scheduler).  Everything else happens only for the rows whose chunk beats their threshold tau:
+//   * the chunk's group maxima go into the 32 bucket maxima (bucket = position of the group inside an item
+//     tile).  Skipping the chunks at or below tau changes nothing: tau is the kth-largest bucket maximum,
+//     kth buckets already hold values >= tau, and a value <= tau cannot move the kth-largest upwards;
+//   * ONE 32-byte entry {8 truncated group maxima, first column} is appended to the row's candidate list.
+//     hnm_rescore_topk decides per group from the interval the 16 bits stand for.
+// Round 1 stored one {max, column} pair per group above tau with eight predicated store sequences and
+// updated the buckets on the hot path: ~96 warp instructions per chunk of which the hot path was a third
+// (tools/bench_select_epilogue.cu: 247 of ~780 cycles per accumulator quarter and scheduler).
 // The four group maxima pairs of a 32-column chunk; after this the 32 accumulator values are dead,
 // so their registers can take the next tcgen05.ld while the rest of the chunk is processed.
 __device__ __forceinline__ void group_max(const float (&v)[32], float (&q)[8]) {
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
     const float* x = v + 4 * h;
-    q[h] = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+    q[h] = fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]);
   }
 }
 
-// UPDATE = false on the second visit of the seed tiles: their items already sit in the buckets and an
-// item must never be counted in two buckets (tau would stop being a lower bound).
-template <bool UPDATE>
+enum { kSeed = 0, kCollectOnly = 1, kCollect = 2 };
+// kSeed: first visit of the seed tiles -- buckets only (tau is +inf).  kCollectOnly: their second visit --
+// their items already sit in the buckets, and after refresh_tau has permuted the bucket registers an item
+// must not be added to a second one (tau would stop being a lower bound).  kCollect: everything else.
+template <int MODE>
 __device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col0, RowState& st,
-                                         uint2* __restrict__ cand, int cap) {
-  if (UPDATE) {
+                                         const CandList cand, int cap) {
+  if (MODE == kSeed) {
 #pragma unroll
     for (int h = 0; h < 8; ++h) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
+    return;
   }
-  const float m32 = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7])));
+  const float m32 = fmaxf(fmaxf(fmaxf(fmaxf(q[0], q[1]), q[2]), fmaxf(fmaxf(q[3], q[4]), q[5])), fmaxf(q[6], q[7]));
   if (m32 > st.tau) {
-    if (st.cnt > cap - 8) {              // no room for a full chunk: stop collecting, flag the row
+    if (MODE == kCollect) {
+#pragma unroll
+      for (int h = 0; h < 8; ++h) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
+    }
+    if (st.cnt >= cap) {                 // no room: stop collecting, flag the row
       st.tau = INFINITY;
       st.cnt = cap + 1;
     } else {
-      // eight PREDICATED stores, no branches: ptxas turned the plain `if (q[h] > tau) cand[cnt++] = ...` into
-      // eight BSSY/BSYNC regions whose branch-resolving stalls made this path 40 % of the epilogue time
-      // (the block runs whenever any of the warp's 32 rows has a hit: 39 % of the chunks at the H&M shape)
-#pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            ".reg .u64 a;\n"
-            "setp.gt.f32 p, %2, %3;\n"
-            "mad.wide.s32 a, %0, 8, %1;\n"
-            "@p st.global.f32 [a], %2;\n"
-            "@p st.global.u32 [a + 4], %4;\n"
-            "@p add.s32 %0, %0, 1;\n"
-            "}\n"
-            : "+r"(st.cnt)
-            : "l"(cand), "f"(q[h]), "f"(st.tau), "r"(col0 + 4 * h));      // the list is write-only here
-      }
+      const uint32_t p0 = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x7632);
+      const uint32_t p1 = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x7632);
+      const uint32_t p2 = __byte_perm(__float_as_uint(q[4]), __float_as_uint(q[5]), 0x7632);
+      const uint32_t p3 = __byte_perm(__float_as_uint(q[6]), __float_as_uint(q[7]), 0x7632);
+      // the list is write-only here
+      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(cand.q + st.cnt), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+      asm volatile("st.global.b32 [%0], %1;" ::"l"(cand.col + st.cnt), "r"(col0) : "memory");
+      ++st.cnt;
     }
   }
 }
 
 // One 128-column accumulator of one user row.  Two 32-column loads are kept in flight: chunks 2 and 3
 // are fetched while chunks 0 and 1 are processed, so one TMEM round trip per tile is exposed, not four.
-template <bool UPDATE>
-__device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& st, uint2* __restrict__ cand,
+template <int MODE>
+__device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& st, const CandList cand,
                                            int cap, uint64_t* t_empty, int lane) {
   float va[32], vb[32], q0[8], q1[8];
   tmem_ld32(taddr, va);
@@ -272,8 +335,8 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& 
   tmem_ld32(taddr + 64, va);
   group_max(vb, q1);
   tmem_ld32(taddr + 96, vb);
-  finish32<UPDATE>(q0, 0, item0, st, cand, cap);
-  finish32<UPDATE>(q1, 1, item0 + 32, st, cand, cap);
+  finish32<MODE>(q0, 0, item0, st, cand, cap);
+  finish32<MODE>(q1, 1, item0 + 32, st, cand, cap);
   tmem_ld_wait(va, vb);
   // every column of this accumulator is in registers: hand it back to its MMA issuer
   tc_fence_before();
@@ -281,8 +344,8 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& 
   if (lane == 0) mbar_arrive(t_empty);
   group_max(va, q0);
   group_max(vb, q1);
-  finish32<UPDATE>(q0, 2, item0 + 64, st, cand, cap);
-  finish32<UPDATE>(q1, 3, item0 + 96, st, cand, cap);
+  finish32<MODE>(q0, 2, item0 + 64, st, cand, cap);
+  finish32<MODE>(q1, 3, item0 + 96, st, cand, cap);
 }
 
 // ----------------------------------------------------------------------------- work distribution
@@ -295,11 +358,12 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& 
 // merge_split_kernel then keeps the groups above the largest of the slice thresholds -- each slice's tau
 // is a lower bound on the kth_sel-th best score of a subset of the catalog, hence also of the catalog.
 struct SplitPlan {
-  int full_passes;      // passes of kMU tiles over the whole catalog, per CTA
-  int tile0;            // first left-over user tile (= gridDim.x * kMU * full_passes)
-  int triples;          // ceil(left-over tiles / kMU)
+  int mu;               // user tiles per pass (Shape::MU)
+  int full_passes;      // passes of mu tiles over the whole catalog, per CTA
+  int tile0;            // first left-over user tile (= gridDim.x * mu * full_passes)
+  int triples;          // ceil(left-over tiles / mu)
   int slices;           // item-range slices per triple; triples * slices <= gridDim.x
-  uint2* cand;          // [left-over users][slices][cap]
+  CandList cand;        // [left-over users][slices][cap]
   int cap;
   int32_t* count;       // [left-over users][slices]
   float* thresh;        // [left-over users][slices]
@@ -317,8 +381,8 @@ __device__ __forceinline__ bool pass_desc(int n, int num_user_tiles, int num_ite
                                           const SplitPlan& sp, PassDesc& p) {
   const int b = (int)blockIdx.x;
   if (n < sp.full_passes) {
-    p.t0 = (b * sp.full_passes + n) * kMU;
-    p.mc = kMU;
+    p.t0 = (b * sp.full_passes + n) * sp.mu;
+    p.mc = sp.mu;
     p.i0 = 0;
     p.ni = num_item_tiles;
     // every CTA sweeps the catalog from a different starting tile: otherwise all 148 SMs ask the L2 for
@@ -330,8 +394,8 @@ __device__ __forceinline__ bool pass_desc(int n, int num_user_tiles, int num_ite
   }
   if (n > sp.full_passes || b >= sp.triples * sp.slices) return false;
   const int j = b / sp.slices, sl = b - j * sp.slices;
-  p.t0 = sp.tile0 + j * kMU;
-  p.mc = min(kMU, num_user_tiles - p.t0);
+  p.t0 = sp.tile0 + j * sp.mu;
+  p.mc = min(sp.mu, num_user_tiles - p.t0);
   p.i0 = (int)(((long long)sl * num_item_tiles) / sp.slices);
   p.ni = (int)(((long long)(sl + 1) * num_item_tiles) / sp.slices) - p.i0;
   p.rot = 0;
@@ -358,14 +422,16 @@ __device__ __forceinline__ int pass_tile(const PassDesc& p, int it) {
 }
 
 // ----------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kThreads, 1)
+template <class S>
+__global__ void __launch_bounds__(S::kThreads, 1)
 score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                         int num_users, int num_user_tiles, int num_item_tiles, int kth_sel,
-                        uint2* __restrict__ cand, int cap, int32_t* __restrict__ cand_count,
+                        const CandList cand, int cap, int32_t* __restrict__ cand_count,
                         float* __restrict__ cand_thresh, int mode, int boot_tiles, int refresh_div,
-                        const SplitPlan sp) {
+                        uint32_t wait_hint_ns, const SplitPlan sp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kMU = S::MU, kBUF = S::BUF, kStagesB = S::kStagesB;
   uint8_t* smem_a = smem;                                   // [2][kMU][kTileBytes]
   uint8_t* smem_b = smem + 2 * kMU * kTileBytes;            // [kStagesB][kTileBytes]
   Barriers* bars = reinterpret_cast<Barriers*>(smem_b + kStagesB * kTileBytes);
@@ -379,7 +445,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     tma_prefetch_desc(&map_items);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], kMU); }
     for (int i = 0; i < kStagesB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], kMU); }
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
+    for (int i = 0; i < S::kSlots; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -395,7 +461,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
   if (warp < 4) {
   // The 4 control warps give registers back so the 12 epilogue warps can hold a whole 64-column
   // double buffer plus the 32 bucket maxima without spilling (40 * 128 + 152 * 384 <= 64 K).
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (S::kSetMaxNReg) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
@@ -403,7 +469,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
         const int mc = p.mc;
         const int abuf = n & 1;
-        mbar_wait(&bars->a_empty[abuf], ((n >> 1) & 1) ^ 1);
+        mbar_wait_hint(&bars->a_empty[abuf], ((n >> 1) & 1) ^ 1, wait_hint_ns);
         mbar_expect_tx(&bars->a_full[abuf], mc * kTileBytes);
         for (int m = 0; m < mc; ++m)
           tma_load_2d(smem_a + (abuf * kMU + m) * kTileBytes, &map_users, &bars->a_full[abuf], 0,
@@ -412,13 +478,13 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
         for (int it = 0; it < num_iters; ++it, ++g) {
           const int tile = pass_tile(p, it);
           const int stage = g % kStagesB;
-          mbar_wait(&bars->b_empty[stage], ((g / kStagesB) & 1) ^ 1);
+          mbar_wait_hint(&bars->b_empty[stage], ((g / kStagesB) & 1) ^ 1, wait_hint_ns);
           mbar_expect_tx(&bars->b_full[stage], kTileBytes);
           tma_load_2d(smem_b + stage * kTileBytes, &map_items, &bars->b_full[stage], 0, tile * kItemTile);
         }
       }
     }
-  } else {
+  } else if (warp <= kMU) {
     // ===================================================== MMA issuers: warp 1 + m serves user tile m
     // tcgen05.mma holds its issuing thread for about the duration of the MMA (tools/bench_mma.cu:
     // 73 cycles per M128 N128 K16), so with a single issuer every mbarrier wait / fence / commit adds
@@ -432,23 +498,24 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
         const int num_iters = p.ni + p.boot;
         const bool active = m < p.mc;
         const int abuf = n & 1;
-        mbar_wait(&bars->a_full[abuf], (n >> 1) & 1);
+        mbar_wait_hint(&bars->a_full[abuf], (n >> 1) & 1, wait_hint_ns);
         tc_fence_after();
         const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(smem_a + (abuf * kMU + m) * kTileBytes) >> 4) & 0x3FFF);
         for (int it = 0; it < num_iters; ++it, ++g) {
           const int stage = g % kStagesB;
-          mbar_wait(&bars->b_full[stage], (g / kStagesB) & 1);
+          mbar_wait_hint(&bars->b_full[stage], (g / kStagesB) & 1, wait_hint_ns);
           if (active) {
-            // accumulator m belongs to user tile m alone (its use counter is `uses`), so no issuer ever
+            // the accumulators of user tile m belong to it alone (use counter `uses`), so no issuer ever
             // has to order itself against another one
             const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(smem_b + stage * kTileBytes) >> 4) & 0x3FFF);
-            mbar_wait(&bars->t_empty[m], (uses & 1) ^ 1);
+            const int slot = m * kBUF + (int)(uses % kBUF);
+            mbar_wait_hint(&bars->t_empty[slot], ((uses / kBUF) & 1) ^ 1, wait_hint_ns);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + m * kItemTile;
+            const uint32_t d_tmem = tmem_base + slot * kItemTile;
 #pragma unroll
             for (int k = 0; k < kDim / 16; ++k)      // +32 bytes along K = +2 in the 16-byte address field
               umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, k > 0 ? 1u : 0u);
-            umma_commit(&bars->t_full[m]);
+            umma_commit(&bars->t_full[slot]);
             umma_commit(&bars->b_empty[stage]);
             ++uses;
           } else {
@@ -462,13 +529,11 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
   }
   } else {
     // ===================================================== epilogue: warpgroup m drains user tile m
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    if (S::kSetMaxNReg) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int m = (warp - 4) >> 2;
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t uses = 0;
-    const uint32_t taddr = lane_base + m * kItemTile;
-    uint64_t* t_empty = &bars->t_empty[m];
     for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
       if (m >= p.mc) continue;                                              // short pass: this warpgroup rests
       const int boot = p.boot;
@@ -477,7 +542,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       const uint32_t slot = out_slot(p, sp, m, q, lane);
       const bool real = (p.t0 + m) * kUserTile + q * 32 + lane < num_users;
       const int out_cap = p.slice < 0 ? cap : sp.cap;
-      uint2* my_cand = (p.slice < 0 ? cand : sp.cand) + (size_t)(real ? slot : 0) * out_cap;
+      const CandList my_cand = (p.slice < 0 ? cand : sp.cand).at((size_t)(real ? slot : 0) * out_cap);
       const int my_cap = real ? out_cap : 0;             // padded rows count but never store
       RowState rs;
       rs.tau = INFINITY;
@@ -499,7 +564,10 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
           const int seen = max(boot, it - boot);         // item tiles behind the current bucket maxima
           next_refresh = it + max(2, seen / refresh_div);
         }
-        mbar_wait(&bars->t_full[m], uses & 1);
+        const int slot_t = m * kBUF + (int)(uses % kBUF);
+        const uint32_t taddr = lane_base + slot_t * kItemTile;
+        uint64_t* t_empty = &bars->t_empty[slot_t];
+        mbar_wait(&bars->t_full[slot_t], (uses / kBUF) & 1);
         ++uses;
         tc_fence_after();
         if (mode == 1 || mode == 3 || mode == 4) {   // debug: drain only / handshake only / one load
@@ -511,10 +579,12 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
           __syncwarp();
           if (lane == 0) mbar_arrive(t_empty);
           rs.bm[0] += acc;
-        } else if (it >= boot && it < 2 * boot) {      // second visit of a seed tile: collect only
-          drain_tile<false>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
+        } else if (it < boot) {                        // first visit of a seed tile: buckets only
+          drain_tile<kSeed>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
+        } else if (it < 2 * boot) {                    // second visit of a seed tile: collect only
+          drain_tile<kCollectOnly>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
         } else {
-          drain_tile<true>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
+          drain_tile<kCollect>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
         }
       }
       if (mode == 0) rs.tau = refresh_tau(rs.bm, kth_sel);
@@ -548,8 +618,13 @@ __device__ __forceinline__ void cmpx_lane(float& v, int lane, int stride, bool d
   v = (lower == desc) ? fmaxf(v, o) : fminf(v, o);    // best-first block: the lower lane keeps the larger value
 }
 
+__device__ __forceinline__ uint32_t cand_half(const uint4& q, int h) {     // 16-bit pattern of group h
+  const uint32_t w = h < 2 ? q.x : (h < 4 ? q.y : (h < 6 ? q.z : q.w));
+  return (h & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
 __global__ void __launch_bounds__(128)
-merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, uint2* __restrict__ cand, int cap,
+merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand, int cap,
                    int32_t* __restrict__ cand_count, float* __restrict__ cand_thresh) {
   const int lane = threadIdx.x & 31;
   const int lu = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -572,44 +647,64 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, uint2* __restrict__
     }
     return;
   }
-  // kth_sel-th largest stored group maximum: running top 32 over all slice lists, lane i = (i+1)-th largest
+  // kth_sel-th largest stored group maximum (its lower bound: the stored 16 bits are a truncation):
+  // running top 32 over all slice lists, lane i = (i+1)-th largest
   float top = -INFINITY;
   for (int s = 0; s < sp.slices; ++s) {
     const int cnt = sp.count[base + s];
-    const uint2* in = sp.cand + (base + s) * sp.cap;
+    const CandList in = sp.cand.at((base + s) * sp.cap);
     for (int i0 = 0; i0 < cnt; i0 += 32) {
-      float v = i0 + lane < cnt ? __uint_as_float(in[i0 + lane].x) : -INFINITY;
-      if (!__any_sync(0xffffffffu, v > thr)) continue;          // nothing here can move a threshold above thr0
+      const bool have = i0 + lane < cnt;
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if (have) q = in.q[i0 + lane];
+#pragma unroll 1
+      for (int h = 0; h < 8; ++h) {
+        float lo, hi;
+        cand_bounds(cand_half(q, h), lo, hi);
+        float v = have ? lo : -INFINITY;
+        if (!__any_sync(0xffffffffu, v > thr)) continue;        // nothing here can move a threshold above thr0
 #pragma unroll
-      for (int size = 2; size <= 32; size <<= 1) {
+        for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_lane(v, lane, stride, (lane & size) == 0);
+          for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_lane(v, lane, stride, (lane & size) == 0);
+        }
+        top = fmaxf(top, __shfl_sync(0xffffffffu, v, 31 - lane));
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) cmpx_lane(top, lane, stride, true);
       }
-      top = fmaxf(top, __shfl_sync(0xffffffffu, v, 31 - lane));
-#pragma unroll
-      for (int stride = 16; stride > 0; stride >>= 1) cmpx_lane(top, lane, stride, true);
     }
   }
   // An unsliced row's tau is the kth_sel-th largest of 32 BUCKET maxima, which sits near the (kth_sel + 4)-th
   // best score because good items share buckets.  Taking the exact kth_sel-th best group here would leave less
   // room between the k-th score and the threshold, and 30x more sliced users failed their certificate.
   thr = fmaxf(thr, __shfl_sync(0xffffffffu, top, min(kth_sel + 4, 32) - 1));
-  uint2* out = cand + (size_t)row * cap;
+  // gather the chunks that still hold a group above thr (judged by the upper end of its interval)
+  const CandList out = cand.at((size_t)row * cap);
   int total = 0;
   for (int s = 0; s < sp.slices; ++s) {
     const int cnt = sp.count[base + s];
-    const uint2* in = sp.cand + (base + s) * sp.cap;
+    const CandList in = sp.cand.at((base + s) * sp.cap);
     for (int i0 = 0; i0 < cnt; i0 += 32) {
       const int i = i0 + lane;
-      uint2 c = make_uint2(0u, 0u);
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t col = 0u;
       bool keep = false;
       if (i < cnt) {
-        c = in[i];
-        keep = __uint_as_float(c.x) > thr;
+        q = in.q[i];
+        col = in.col[i];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          float lo, hi;
+          cand_bounds(cand_half(q, h), lo, hi);
+          keep |= hi > thr;
+        }
       }
       const unsigned mask = __ballot_sync(0xffffffffu, keep);
       const int pos = total + __popc(mask & ((1u << lane) - 1u));
-      if (keep && pos < cap) out[pos] = c;
+      if (keep && pos < cap) {
+        out.q[pos] = q;
+        out.col[pos] = col;
+      }
       total += __popc(mask);
     }
   }
@@ -630,14 +725,29 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, const floa
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // m >= 0
 }
 
-// one 8-lane group per row of 64: lane handles 8 consecutive floats -> one 16-byte store
+// Power of two s with absmax * s in [2^14, 2^15): fp16 keeps 11 significant bits and cannot overflow.
+// Built from the exponent field, clamped to 2^+-100; 1 for a zero / non-finite absmax.
+__device__ __forceinline__ float pow2_scale(float absmax) {
+  const int e = (int)((__float_as_uint(absmax) >> 23) & 0xFFu);        // biased exponent; absmax >= 0
+  if (e == 0 || e == 255) return 1.f;
+  const int se = min(227, max(27, 268 - e));                            // 2^(14 - (e - 127)), biased
+  return __uint_as_float((uint32_t)se << 23);
+}
+
+// One 8-lane group per row of 64: a lane handles 8 consecutive floats -> one 16-byte store.
+// PER_ROW = false (item shard): one scale for the table, derived from the device-resident absmax
+//   (params[0]); the kernel also publishes params[1] = scale and params[2] = max_j ||x_j - c||^2.
+// PER_ROW = true (users): every row gets its own power of two -- the ranking of the items for a fixed
+//   user does not depend on that user's scale, so a table with a heavy-tailed norm distribution keeps
+//   11 significant bits in every row; 1/scale goes to row_inv_scale[r] for hnm_rescore_topk.
+template <bool PER_ROW>
 __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __restrict__ row_ids, int64_t num_rows,
-                            int64_t rows_padded, const float* __restrict__ center, float scale,
-                            __half* __restrict__ out, float* __restrict__ sumsq) {
+                            int64_t rows_padded, const float* __restrict__ center, float* __restrict__ params,
+                            __half* __restrict__ out, float* __restrict__ row_inv_scale) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t r = t >> 3;
   const int sub = (int)(t & 7);
-  if (r >= rows_padded) return;
+  if (r >= rows_padded) return;                                          // whole 8-lane groups leave together
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
   if (r < num_rows) {
     const int64_t src = row_ids ? row_ids[r] : r;
@@ -650,18 +760,33 @@ __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __rest
       b = make_float4(__fsub_rn(b.x, cb.x), __fsub_rn(b.y, cb.y), __fsub_rn(b.z, cb.z), __fsub_rn(b.w, cb.w));
     }
   }
+  // the 8 lanes of a row are 8 consecutive lanes of one warp: xor-shuffles 1, 2, 4 stay inside the row
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  float scale;
+  if (PER_ROW) {
+    float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                    fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+    m = fmaxf(m, __shfl_xor_sync(gmask, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(gmask, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(gmask, m, 4));
+    scale = pow2_scale(m);
+    if (sub == 0 && r < num_rows) row_inv_scale[r] = 1.f / scale;       // exact: a power of two
+  } else {
+    scale = pow2_scale(params[0]);
+    if (t == 0) params[1] = scale;
+  }
   __half2 h[4];
   h[0] = __floats2half2_rn(a.x * scale, a.y * scale);
   h[1] = __floats2half2_rn(a.z * scale, a.w * scale);
   h[2] = __floats2half2_rn(b.x * scale, b.y * scale);
   h[3] = __floats2half2_rn(b.z * scale, b.w * scale);
   *reinterpret_cast<uint4*>(out + (size_t)r * kDim + sub * 8) = *reinterpret_cast<uint4*>(h);
-  if (sumsq) {
-    float s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (sub == 0 && r < num_rows) sumsq[r] = s;
+  if (!PER_ROW) {
+    float sq = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    sq += __shfl_xor_sync(gmask, sq, 1);
+    sq += __shfl_xor_sync(gmask, sq, 2);
+    sq += __shfl_xor_sync(gmask, sq, 4);
+    if (sub == 0 && r < num_rows) atomicMax(reinterpret_cast<int*>(params + 2), __float_as_int(sq));   // sq >= 0
   }
 }
 
@@ -671,7 +796,6 @@ constexpr int kGroup = 4;        // items per nominated group (select32)
 constexpr int kMaxGroups = 64;   // surviving groups hnm_rescore_topk can take per user
 constexpr int kMaxContenders = 128;  // rescored items above the cut it can rank per user
 constexpr int kRescoreWarps = 4;     // one user per warp
-constexpr int kTileStride = 65;      // floats per staged item row (64 + 1: conflict-free column walks)
 
 __device__ __forceinline__ bool in_sorted(const int64_t* __restrict__ a, int64_t lo, int64_t hi, int64_t x) {
   while (lo < hi) {
@@ -686,188 +810,6 @@ __device__ __forceinline__ bool in_sorted(const int64_t* __restrict__ a, int64_t
 // (score desc, id asc) with 32-bit ids; used by the warp-wide sort below
 __device__ __forceinline__ bool before32(double sa, int ia, double sb, int ib) {
   return sa > sb || (sa == sb && ia < ib);
-}
-
-__global__ void __launch_bounds__(kRescoreWarps * 32)
-rescore_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
-               const int64_t* __restrict__ user_ids, int64_t batch, int dim, int64_t item_begin, int num_items_local,
-               const uint2* __restrict__ cand, int cap, const int32_t* __restrict__ cand_count,
-               const float* __restrict__ cand_thresh, double inv_scale, double max_item_norm,
-               const float* __restrict__ center, const int64_t* __restrict__ excl_ptr,
-               const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
-               double* __restrict__ out_scores, int32_t* __restrict__ certified) {
-  __shared__ uint32_t s_col[kRescoreWarps][kMaxGroups];
-  __shared__ float s_tile[kRescoreWarps][32 * kTileStride];
-  __shared__ double s_sc[kRescoreWarps][kMaxContenders];
-  __shared__ int s_id[kRescoreWarps][kMaxContenders];
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  if (b >= batch) return;
-  const int64_t uid = user_ids ? user_ids[b] : b;
-  const float* urow = user_emb + (size_t)uid * dim;
-  const int raw = cand_count[b];
-  const int n = min(raw, cap);
-  const float thr = cand_thresh[b];
-  const uint2* mine = cand + (size_t)b * cap;
-  int64_t ex_lo = 0, ex_hi = 0;
-  if (excl_ptr) { ex_lo = excl_ptr[b]; ex_hi = excl_ptr[b + 1]; }
-
-  // 1. keep the groups whose maximum ended above the final threshold (the others are covered by
-  //    the certificate bound) and compact them: lane j takes kept group j
-  int groups = 0;
-#pragma unroll
-  for (int e = 0; e < kMaxPerLane; ++e) {
-    const int idx = lane + 32 * e;
-    uint2 c = make_uint2(0u, 0u);
-    bool keep = false;
-    if (idx < n) {
-      c = mine[idx];
-      keep = __uint_as_float(c.x) > thr;
-    }
-    const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    const int pos = groups + __popc(mask & ((1u << lane) - 1u));
-    if (keep && pos < kMaxGroups) s_col[wib][pos] = c.y;
-    groups += __popc(mask);
-  }
-  __syncwarp();
-  const bool too_many = groups > kMaxGroups;
-  groups = min(groups, kMaxGroups);
-  int total = 0;                                            // contenders found so far
-  // ||u||_2, u.c and sum |u_k c_k| for the bound, each k on one lane
-  double un = 0.0, uc = 0.0, uc_abs = 0.0;
-  for (int kk = 4 * lane; kk < dim; kk += 128) {
-    const float4 uf = ldg_f4(urow + kk);
-    const double u0 = (double)uf.x, u1 = (double)uf.y, u2 = (double)uf.z, u3 = (double)uf.w;
-    un = fma(u0, u0, un); un = fma(u1, u1, un); un = fma(u2, u2, un); un = fma(u3, u3, un);
-    if (center) {
-      const float4 cf = ldg_f4(center + kk);
-      const double c0 = (double)cf.x, c1 = (double)cf.y, c2 = (double)cf.z, c3 = (double)cf.w;
-      uc = fma(u0, c0, uc); uc = fma(u1, c1, uc); uc = fma(u2, c2, uc); uc = fma(u3, c3, uc);
-      uc_abs += fabs(u0 * c0) + fabs(u1 * c1) + fabs(u2 * c2) + fabs(u3 * c3);
-    }
-  }
-#pragma unroll
-  for (int off = 16; off; off >>= 1) {
-    un += __shfl_xor_sync(0xffffffffu, un, off);
-    uc += __shfl_xor_sync(0xffffffffu, uc, off);
-    uc_abs += __shfl_xor_sync(0xffffffffu, uc_abs, off);
-  }
-  un = sqrt(un);
-  // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
-  const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)dim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
-  const double cut = (double)thr * inv_scale + eps + uc;
-
-  // 2. exact fp64 scores (k = 0..dim-1 fma chain per item) of the items of the kept groups, 32 items
-  //    per round: the rows are fetched by half warps (one coalesced 256-byte request per row) into a
-  //    padded shared-memory tile, then lane j runs the chain of item j out of the tile.
-  // 3. contenders = rescored items strictly above the cut, appended to the warp's list.
-  float* tile = s_tile[wib];
-  const int half = lane >> 4, sub = lane & 15;
-  const int num_cand_items = groups * kGroup;
-  for (int base = 0; base < num_cand_items || base == 0; base += 32) {
-    const int it = base + lane;
-    int item = -1;
-    if (it < num_cand_items) item = (int)s_col[wib][it / kGroup] + (it % kGroup);
-    bool live = item >= 0 && item < num_items_local;        // columns past the catalog are zero padding
-    if (live && ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)item)) live = false;
-    if (dim == kDim) {
-#pragma unroll 4
-      for (int step = 0; step < 16; ++step) {
-        const int l = 2 * step + half;
-        const int il = __shfl_sync(0xffffffffu, live ? item : -1, l);
-        if (il >= 0) {
-          const float4 v = ldg_f4(item_emb + (size_t)il * kDim + sub * 4);
-          float* t = tile + l * kTileStride + sub * 4;
-          t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
-        }
-      }
-      __syncwarp();
-    }
-    double acc = 0.0;
-    if (live) {
-      if (dim == kDim) {
-        const float* t = tile + lane * kTileStride;
-#pragma unroll 4
-        for (int kk = 0; kk < kDim; kk += 4) {
-          const float4 uf = ldg_f4(urow + kk);
-          acc = fma((double)uf.x, (double)t[kk], acc);
-          acc = fma((double)uf.y, (double)t[kk + 1], acc);
-          acc = fma((double)uf.z, (double)t[kk + 2], acc);
-          acc = fma((double)uf.w, (double)t[kk + 3], acc);
-        }
-      } else {
-        const float* irow = item_emb + (size_t)item * dim;
-        for (int kk = 0; kk < dim; kk += 4) {
-          const float4 uf = ldg_f4(urow + kk), v = ldg_f4(irow + kk);
-          acc = fma((double)uf.x, (double)v.x, acc);
-          acc = fma((double)uf.y, (double)v.y, acc);
-          acc = fma((double)uf.z, (double)v.z, acc);
-          acc = fma((double)uf.w, (double)v.w, acc);
-        }
-      }
-    }
-    const bool c = live && acc > cut;
-    const unsigned mask = __ballot_sync(0xffffffffu, c);
-    const int pos = total + __popc(mask & ((1u << lane) - 1u));
-    if (c && pos < kMaxContenders) { s_sc[wib][pos] = acc; s_id[wib][pos] = item; }
-    total += __popc(mask);
-    __syncwarp();
-  }
-  __syncwarp();
-  if (total <= 32) {
-    // the rule: one contender per lane, one warp-wide bitonic sort
-    double ms = lane < total ? s_sc[wib][lane] : -INFINITY;
-    int mi = lane < total ? s_id[wib][lane] : INT32_MAX;
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, ms, stride);
-        const int oi = __shfl_xor_sync(0xffffffffu, mi, stride);
-        const bool lower = (lane & stride) == 0;                 // lower lane of the pair
-        const bool desc = (lane & size) == 0;                    // this block sorts best-first
-        const bool other_first = before32(os, oi, ms, mi);
-        // the lower lane keeps the better entry in a best-first block, the worse one otherwise
-        const bool take = (lower == desc) ? other_first : !other_first && !(os == ms && oi == mi);
-        if (take) { ms = os; mi = oi; }
-      }
-    }
-    if (lane < k) {
-      out_ids[(size_t)b * k + lane] = mi == INT32_MAX ? INT64_MAX : item_begin + (int64_t)mi;
-      out_scores[(size_t)b * k + lane] = ms;
-    }
-  } else if (total <= kMaxContenders) {
-    // the exception (tau ended far below the k-th score): k rounds of warp argmax over the list
-    for (int t = 0; t < k; ++t) {
-      double bs = -INFINITY;
-      int bi = INT32_MAX, bp = -1;
-      for (int p = lane; p < total; p += 32) {
-        const double x = s_sc[wib][p];
-        const int xi = s_id[wib][p];
-        if (before32(x, xi, bs, bi)) { bs = x; bi = xi; bp = p; }
-      }
-      double ws = bs;
-      int wi = bi;
-#pragma unroll
-      for (int off = 16; off; off >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, ws, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
-        if (before32(os, oi, ws, wi)) { ws = os; wi = oi; }
-      }
-      if (bp >= 0 && wi == bi && ws == bs) { s_sc[wib][bp] = -INFINITY; s_id[wib][bp] = INT32_MAX; }
-      __syncwarp();
-      if (lane == 0) {
-        out_ids[(size_t)b * k + t] = item_begin + (int64_t)wi;
-        out_scores[(size_t)b * k + t] = ws;
-      }
-    }
-  }
-  if (lane == 0) {
-    // bit 0: provably exact; bits 1.. say why not (list overflow, > 32 groups, < k contenders, > 32 contenders)
-    const int why = (raw > cap ? 2 : 0) | (too_many ? 4 : 0) | (total < k ? 8 : 0) | (total > kMaxContenders ? 16 : 0);
-    certified[b] = why == 0 ? 1 : why;
-  }
 }
 
 // ----------------------------------------------------------------------------- rescoring, dim = 64
@@ -902,7 +844,8 @@ struct __align__(16) RescoreSmem {
   float uf[kDim];
   int id[kMaxContenders];
   uint32_t col[kMaxGroups];
-  float gmax[kMaxGroups];
+  float glo[kMaxGroups];                   // interval of the group's tensor-core maximum
+  float ghi[kMaxGroups];
   uint8_t sel[kMaxSel];
 };
 
@@ -916,8 +859,9 @@ __device__ __forceinline__ void cmpx_desc(float& v, int lane, int stride, bool d
 __global__ void __launch_bounds__(kRescoreWarps * 32, 5)
 rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
                  const int64_t* __restrict__ user_ids, int64_t batch, int64_t item_begin, int num_items_local,
-                 const uint2* __restrict__ cand, int cap, const int32_t* __restrict__ cand_count,
-                 const float* __restrict__ cand_thresh, double inv_scale, double max_item_norm,
+                 const CandList cand, int cap, const int32_t* __restrict__ cand_count,
+                 const float* __restrict__ cand_thresh, const float* __restrict__ user_inv_scale,
+                 const float* __restrict__ item_params,
                  const float* __restrict__ center, const int64_t* __restrict__ excl_ptr,
                  const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
                  double* __restrict__ out_scores, int32_t* __restrict__ certified) {
@@ -933,17 +877,25 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   const int raw = cand_count[b];
   const int n = min(raw, cap);
   const float thr = cand_thresh[b];
-  const uint2* mine = cand + (size_t)b * cap;
+  const CandList mine = cand.at((size_t)b * cap);
   int64_t ex_lo = 0, ex_hi = 0;
   if (excl_ptr) { ex_lo = excl_ptr[b]; ex_hi = excl_ptr[b + 1]; }
   const int half = lane >> 4, sub = lane & 15;
+  // scales are powers of two (exact in any format): 1 / (su * si) with su per user, si per item shard;
+  // item_params = {absmax, scale, max_j ||x_j - c||^2} as left on the device by hnm_absmax / hnm_score_pack_items
+  const double inv_scale = (double)user_inv_scale[b] / (double)item_params[1];
+  const double max_item_norm = sqrt((double)item_params[2]) * (1.0 + 1e-6);   // a hair above the fp32 sum
   {
     // The kernel is a chain of dependent loads per user (count -> list -> item rows), so warm the L2 for a user
     // that a later CTA will take: its list head (lane i: 32 bytes), count, threshold and embedding row.
     const int64_t pb = b + kRescorePrefetch;
     if (pb < batch) {
-      const char* pa = reinterpret_cast<const char*>(cand + (size_t)pb * cap) + lane * 32;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+      if (4 * lane + 3 < cap) {      // the first 128 entries: 64 bytes of maxima per lane, 512 bytes of columns
+        const char* pa = reinterpret_cast<const char*>(cand.q + (size_t)pb * cap) + lane * 64;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 32));
+        if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(cand.col + (size_t)pb * cap) + lane * 32));
+      }
       const char* pm = nullptr;
       if (lane == 0) pm = reinterpret_cast<const char*>(cand_count + pb);
       else if (lane == 1) pm = reinterpret_cast<const char*>(cand_thresh + pb);
@@ -970,20 +922,41 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     }
   }
 
-  // 1. keep the groups whose maximum ended above the final threshold, compacted: slot j = kept group j
+  // 1. keep the groups that may have ended above the final threshold (upper end of the interval the stored
+  //    16 bits stand for), compacted: slot j = kept group j with the interval of its maximum
   int groups = 0;
   for (int e0 = 0; e0 < n; e0 += 32) {
     const int idx = e0 + lane;
-    uint2 c = make_uint2(0u, 0u);
-    bool keep = false;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t col0 = 0u;
     if (idx < n) {
-      c = mine[idx];
-      keep = __uint_as_float(c.x) > thr;
+      q = __ldg(mine.q + idx);
+      col0 = __ldg(mine.col + idx);
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    const int pos = groups + __popc(mask & ((1u << lane) - 1u));
-    if (keep && pos < kMaxGroups) { sm.col[pos] = c.y; sm.gmax[pos] = __uint_as_float(c.x); }
-    groups += __popc(mask);
+    float lo[8], hi[8];
+    uint32_t kmask = 0u;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      cand_bounds(cand_half(q, h), lo[h], hi[h]);
+      if (idx < n && hi[h] > thr) kmask |= 1u << h;
+    }
+    // exclusive prefix sum of the per-lane counts
+    const int mine_cnt = __popc(kmask);
+    int incl = mine_cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    int pos = groups + incl - mine_cnt;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      if (kmask & (1u << h)) {
+        if (pos < kMaxGroups) { sm.col[pos] = col0 + 4u * h; sm.glo[pos] = lo[h]; sm.ghi[pos] = hi[h]; }
+        ++pos;
+      }
+    }
+    groups += __shfl_sync(0xffffffffu, incl, 31);
   }
   const bool too_many = groups > kMaxGroups;
   groups = min(groups, kMaxGroups);
@@ -1016,7 +989,7 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     if (ok && ex_lo < ex_hi) {
       for (int j = 0; j < kGroup; ++j) ok = ok && !in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)(c0 + j));
     }
-    if (ok) gv = sm.gmax[lane];
+    if (ok) gv = sm.glo[lane];
   }
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
@@ -1036,7 +1009,7 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
       bool keep = false;
       if (gi < groups) {
         c = sm.col[gi];
-        keep = sm.gmax[gi] >= gmin;
+        keep = sm.ghi[gi] >= gmin;
       }
       const unsigned mask = __ballot_sync(0xffffffffu, keep);
       __syncwarp();
@@ -1223,29 +1196,51 @@ extern "C" int hnm_absmax(const float* emb, int64_t count, const float* center, 
   return HNM_OK;
 }
 
-extern "C" int hnm_score_pack(const float* emb, const int64_t* row_ids, int64_t num_rows, int64_t rows_padded,
-                              int32_t dim, const float* center, float scale, void* out_f16, float* out_sumsq,
-                              void* stream_) {
+extern "C" int hnm_score_pack_items(const float* emb, int64_t num_rows, int64_t rows_padded, int32_t dim,
+                                    const float* center, float* params, void* out_f16, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!emb || !out_f16) return HNM_E_NULL;
+  if (!emb || !out_f16 || !params) return HNM_E_NULL;
   if (dim != kDim) return HNM_E_DIM;
   if (num_rows < 0 || rows_padded < num_rows || rows_padded <= 0) return HNM_E_RANGE;
   if (!hnm_aligned16(emb) || !hnm_aligned16(out_f16) || (center && !hnm_aligned16(center))) return HNM_E_ALIGN;
   const int T = 256;
   const int64_t threads = rows_padded * 8;
-  pack_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(emb, row_ids, num_rows, rows_padded, center, scale,
-                                                                  (__half*)out_f16, out_sumsq);
+  pack_kernel<false><<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(emb, nullptr, num_rows, rows_padded, center,
+                                                                         params, (__half*)out_f16, nullptr);
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
+}
+
+extern "C" int hnm_score_pack_users(const float* emb, const int64_t* row_ids, int64_t num_rows, int64_t rows_padded,
+                                    int32_t dim, void* out_f16, float* out_inv_scale, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!emb || !out_f16 || !out_inv_scale) return HNM_E_NULL;
+  if (dim != kDim) return HNM_E_DIM;
+  if (num_rows < 0 || rows_padded < num_rows || rows_padded <= 0) return HNM_E_RANGE;
+  if (!hnm_aligned16(emb) || !hnm_aligned16(out_f16)) return HNM_E_ALIGN;
+  const int T = 256;
+  const int64_t threads = rows_padded * 8;
+  pack_kernel<true><<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(emb, row_ids, num_rows, rows_padded, nullptr,
+                                                                        nullptr, (__half*)out_f16, out_inv_scale);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
 
 namespace {
-constexpr int kSplitCap = 256;      // candidate entries per (sliced user, item slice)
+constexpr int kSplitCap = 128;      // candidate entries (32-column chunks) per (sliced user, item slice)
 constexpr int kMinSliceTiles = 32;  // an item slice is at least this many item tiles
+
+// user tiles per CTA pass of the shape in use: HNM_FUSED_SHAPE=3 selects round 1's 3 x 1 shape
+int fused_mu() {
+  static const int mu = (getenv("HNM_FUSED_SHAPE") && atoi(getenv("HNM_FUSED_SHAPE")) == 3) ? 3 : 2;
+  return mu;
+}
 
 // The work distribution of one launch (see SplitPlan); pointers are filled in by the caller.
 SplitPlan make_plan(int num_user_tiles, int num_item_tiles, int grid) {
+  const int kMU = fused_mu();
   SplitPlan sp{};
+  sp.mu = kMU;
   static const bool no_split = getenv("HNM_FUSED_NOSPLIT") != nullptr;      // A/B switch for profiling
   sp.full_passes = num_user_tiles / (grid * kMU);
   sp.tile0 = grid * kMU * sp.full_passes;
@@ -1261,6 +1256,7 @@ SplitPlan make_plan(int num_user_tiles, int num_item_tiles, int grid) {
 }
 
 int fused_grid(int num_user_tiles) {
+  const int kMU = fused_mu();
   static const bool no_split = getenv("HNM_FUSED_NOSPLIT") != nullptr;
   if (no_split) return std::min((num_user_tiles + kMU - 1) / kMU, hnm_num_sms());
   return hnm_num_sms();
@@ -1268,8 +1264,8 @@ int fused_grid(int num_user_tiles) {
 
 size_t split_bytes(const SplitPlan& sp, size_t* off_count, size_t* off_thresh) {
   if (sp.slices <= 1) { *off_count = *off_thresh = 0; return 0; }
-  const size_t slots = (size_t)sp.triples * kMU * kUserTile * sp.slices;
-  *off_count = slots * kSplitCap * sizeof(uint2);
+  const size_t slots = (size_t)sp.triples * sp.mu * kUserTile * sp.slices;
+  *off_count = slots * kSplitCap * (sizeof(uint4) + sizeof(uint32_t));
   *off_thresh = *off_count + slots * sizeof(int32_t);
   return *off_thresh + slots * sizeof(float);
 }
@@ -1284,15 +1280,16 @@ extern "C" int64_t hnm_score_topk_fused_workspace_bytes(int64_t users_padded, in
   return (int64_t)split_bytes(make_plan(tiles, (int)(items_padded / kItemTile), fused_grid(tiles)), &a, &b) + 256;
 }
 
-extern "C" int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_padded, int32_t* out5) {
-  if (!out5) return HNM_E_NULL;
+extern "C" int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_padded, int32_t* out6) {
+  if (!out6) return HNM_E_NULL;
   if (users_padded <= 0 || items_padded <= 0 || users_padded % kUserTile || items_padded % kItemTile ||
       users_padded > INT32_MAX || items_padded > INT32_MAX)
     return HNM_E_RANGE;
   const int tiles = (int)(users_padded / kUserTile);
   const int grid = fused_grid(tiles);
   const SplitPlan sp = make_plan(tiles, (int)(items_padded / kItemTile), grid);
-  out5[0] = grid; out5[1] = sp.full_passes; out5[2] = sp.tile0; out5[3] = sp.triples; out5[4] = sp.slices;
+  out6[0] = grid; out6[1] = sp.full_passes; out6[2] = sp.tile0; out6[3] = sp.triples; out6[4] = sp.slices;
+  out6[5] = sp.mu;
   return HNM_OK;
 }
 
@@ -1312,15 +1309,10 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   CUtensorMap map_u, map_i;
   if ((rc = make_map(&map_u, users_f16, users_padded)) != HNM_OK) return rc;
   if ((rc = make_map(&map_i, items_f16, items_padded)) != HNM_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HNM_CUDA_TRY(cudaFuncSetAttribute(score_topk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kSmemBytes));
-    attr_set = true;
-  }
   static const int debug_mode = getenv("HNM_FUSED_DEBUG") ? atoi(getenv("HNM_FUSED_DEBUG")) : 0;
   static const int boot_tiles = getenv("HNM_FUSED_BOOT") ? std::max(1, atoi(getenv("HNM_FUSED_BOOT"))) : kBootTiles;
   static const int refresh_div = getenv("HNM_FUSED_REFRESH") ? std::max(1, atoi(getenv("HNM_FUSED_REFRESH"))) : 4;
+  static const uint32_t wait_hint = getenv("HNM_FUSED_WAIT_NS") ? (uint32_t)atoi(getenv("HNM_FUSED_WAIT_NS")) : kWaitHintNs;
   const int num_user_tiles = (int)(users_padded / kUserTile);
   const int num_tiles = (int)(items_padded / kItemTile);
   const int grid = fused_grid(num_user_tiles);
@@ -1331,20 +1323,29 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
     if (!workspace) return HNM_E_NULL;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     if ((int64_t)(need + (size_t)(ws - reinterpret_cast<uint8_t*>(workspace))) > workspace_bytes) return HNM_E_WORKSPACE;
-    sp.cand = reinterpret_cast<uint2*>(ws);
+    sp.cand = cand_list(ws, (size_t)sp.triples * sp.mu * kUserTile * sp.slices, kSplitCap);
     sp.count = reinterpret_cast<int32_t*>(ws + off_count);
     sp.thresh = reinterpret_cast<float*>(ws + off_thresh);
   }
-  score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_u, map_i, (int)num_users, num_user_tiles,
-                                                                  num_tiles, kth_sel, (uint2*)cand,
-                                                                  cand_cap, cand_count, cand_thresh, debug_mode, boot_tiles,
-                                                                  refresh_div, sp);
+  if (sp.mu == 3) {
+    using S = Shape<3, 1>;
+    HNM_CUDA_TRY(hnm_allow_smem(score_topk_fused_kernel<S>, (int)smem_bytes<S>()));
+    score_topk_fused_kernel<S><<<grid, S::kThreads, smem_bytes<S>(), stream>>>(
+        map_u, map_i, (int)num_users, num_user_tiles, num_tiles, kth_sel, cand_list(cand, (size_t)num_users, cand_cap), cand_cap, cand_count,
+        cand_thresh, debug_mode, boot_tiles, refresh_div, wait_hint, sp);
+  } else {
+    using S = Shape<2, 2>;
+    HNM_CUDA_TRY(hnm_allow_smem(score_topk_fused_kernel<S>, (int)smem_bytes<S>()));
+    score_topk_fused_kernel<S><<<grid, S::kThreads, smem_bytes<S>(), stream>>>(
+        map_u, map_i, (int)num_users, num_user_tiles, num_tiles, kth_sel, cand_list(cand, (size_t)num_users, cand_cap), cand_cap, cand_count,
+        cand_thresh, debug_mode, boot_tiles, refresh_div, wait_hint, sp);
+  }
   HNM_LAUNCH_CHECK();
   if (need > 0 && debug_mode == 0) {
-    const int64_t split_users = std::min<int64_t>((int64_t)sp.triples * kMU * kUserTile,
+    const int64_t split_users = std::min<int64_t>((int64_t)sp.triples * sp.mu * kUserTile,
                                                   num_users - (int64_t)sp.tile0 * kUserTile);
     if (split_users > 0) {
-      merge_split_kernel<<<(unsigned)((split_users + 3) / 4), 128, 0, stream>>>(sp, (int)num_users, kth_sel, (uint2*)cand, cand_cap,
+      merge_split_kernel<<<(unsigned)((split_users + 3) / 4), 128, 0, stream>>>(sp, (int)num_users, kth_sel, cand_list(cand, (size_t)num_users, cand_cap), cand_cap,
                                                                                 cand_count, cand_thresh);
       HNM_LAUNCH_CHECK();
     }
@@ -1354,34 +1355,27 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
 
 extern "C" int hnm_rescore_topk(const float* user_emb, const float* item_emb, const int64_t* user_ids, int64_t batch,
                                 int32_t dim, int64_t item_begin, int64_t num_items_local, const void* cand,
-                                int32_t cand_cap,
-                                const int32_t* cand_count, const float* cand_thresh, double inv_scale_product,
-                                double max_item_norm, const float* center, const int64_t* excl_ptr,
-                                const int64_t* excl_items, int32_t k, int64_t* out_ids, double* out_scores,
-                                int32_t* out_certified, void* stream_) {
+                                int32_t cand_cap, const int32_t* cand_count, const float* cand_thresh,
+                                const float* user_inv_scale, const float* item_params, const float* center,
+                                const int64_t* excl_ptr, const int64_t* excl_items, int32_t k, int64_t* out_ids,
+                                double* out_scores, int32_t* out_certified, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (batch == 0) return HNM_OK;
-  if (!user_emb || !item_emb || !cand || !cand_count || !cand_thresh || !out_ids || !out_scores || !out_certified)
+  if (!user_emb || !item_emb || !cand || !cand_count || !cand_thresh || !user_inv_scale || !item_params || !out_ids ||
+      !out_scores || !out_certified)
     return HNM_E_NULL;
   if ((excl_ptr != nullptr) != (excl_items != nullptr)) return HNM_E_NULL;
-  if (batch < 0 || dim <= 0 || dim % 4 != 0 || k < 1 || k > 32 || cand_cap < 1 || cand_cap > 32 * kMaxPerLane ||
-      num_items_local < 1 || num_items_local > INT32_MAX)
+  if (dim != kDim) return HNM_E_DIM;
+  if (batch < 0 || k < 1 || k > 32 || cand_cap < 1 || cand_cap > 32 * kMaxPerLane || num_items_local < 1 ||
+      num_items_local > INT32_MAX)
     return HNM_E_RANGE;
+  if (!hnm_aligned16(user_emb) || !hnm_aligned16(item_emb) || !hnm_aligned16(cand) || (center && !hnm_aligned16(center)))
+    return HNM_E_ALIGN;
   const int wpc = kRescoreWarps;
-  static const bool generic = getenv("HNM_RESCORE_GENERIC") != nullptr;     // A/B switch for profiling
-  if (dim == kDim && !generic && hnm_aligned16(user_emb) && hnm_aligned16(item_emb) &&
-      (!center || hnm_aligned16(center))) {
-    rescore64_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
-        user_emb, item_emb, user_ids, batch, item_begin, (int)num_items_local, (const uint2*)cand, cand_cap,
-        cand_count, cand_thresh, inv_scale_product, max_item_norm, center, excl_ptr, excl_items, k, out_ids,
-        out_scores, out_certified);
-    HNM_LAUNCH_CHECK();
-    return HNM_OK;
-  }
-  rescore_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
-      user_emb, item_emb, user_ids, batch, dim, item_begin, (int)num_items_local, (const uint2*)cand, cand_cap,
-      cand_count, cand_thresh,
-      inv_scale_product, max_item_norm, center, excl_ptr, excl_items, k, out_ids, out_scores, out_certified);
+  rescore64_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
+      user_emb, item_emb, user_ids, batch, item_begin, (int)num_items_local, cand_list(const_cast<void*>(cand), (size_t)batch, cand_cap), cand_cap,
+      cand_count, cand_thresh, user_inv_scale, item_params, center, excl_ptr, excl_items, k, out_ids, out_scores,
+      out_certified);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }

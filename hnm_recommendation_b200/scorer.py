@@ -8,7 +8,6 @@ recomputed by the exact SIMT kernel (hnm_topk_exact).
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -18,19 +17,12 @@ from ._lib import call, ptr, stream
 
 USER_BLOCK = 128
 ITEM_TILE = 128
-CAND_CAP = 256
+CAND_CAP = 192                 # candidate entries (32-column chunks) per user; ~100 on average at the H&M shape
+CAND_WORDS = 5                 # HNM_FUSED_CAND_BYTES / 4 (16 bytes of group maxima + 4 bytes of column per entry)
 K_MAX = 16
 SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maximum
 MAX_USERS_PER_LAUNCH = 1 << 21
 TIER2_MIN_USERS = 32
-
-
-def _pow2_scale(absmax: float) -> float:
-    """Power of two s with absmax * s in [2^14, 2^15): fp16 keeps 11 significant bits, no overflow."""
-    if not (absmax > 0.0) or math.isinf(absmax) or math.isnan(absmax):
-        return 1.0
-    e = 14 - math.floor(math.log2(absmax))
-    return 2.0 ** max(-100, min(100, e))
 
 
 class FusedScorer:
@@ -53,19 +45,14 @@ class FusedScorer:
         with torch.cuda.device(dev):
             # any fp32 vector is a valid centre; the mean row is the one that shrinks the items most
             self.center = self.item_emb.mean(dim=0, dtype=torch.float64).float().contiguous() if center else None
-            amax = torch.zeros(2, dtype=torch.float32, device=dev)
-            call("hnm_absmax", ptr(self.user_emb), self.user_emb.numel(), None, 64, amax[0:1].data_ptr(), stream())
+            # {absmax, scale, max ||x - c||^2, -} of the shard: produced and consumed on the device, so the
+            # set-up needs no host synchronisation (two .tolist()/.max() round trips in round 1)
+            self.item_params = torch.zeros(4, dtype=torch.float32, device=dev)
             call("hnm_absmax", ptr(self.item_emb), self.item_emb.numel(), ptr(self.center), 64,
-                 amax[1:2].data_ptr(), stream())
-            au, ai = amax.tolist()
-            self.user_scale, self.item_scale = _pow2_scale(au), _pow2_scale(ai)
+                 self.item_params.data_ptr(), stream())
             self.items_f16 = torch.empty(self.items_padded, 64, dtype=torch.float16, device=dev)
-            sumsq = torch.empty(self.num_items, dtype=torch.float32, device=dev)
-            call("hnm_score_pack", ptr(self.item_emb), None, self.num_items, self.items_padded, 64,
-                 ptr(self.center), self.item_scale, ptr(self.items_f16), ptr(sumsq), stream())
-            # a hair above the fp32 value so the bound stays an upper bound
-            self.max_item_norm = math.sqrt(float(sumsq.max())) * (1.0 + 1e-6)
-        self.inv_scale = 1.0 / (self.user_scale * self.item_scale)
+            call("hnm_score_pack_items", ptr(self.item_emb), self.num_items, self.items_padded, 64,
+                 ptr(self.center), ptr(self.item_params), ptr(self.items_f16), stream())
         self.last_stats: Dict[str, int] = {}
         self.profile = False                       # record CUDA events around each stage of topk()
         self.stage_ms: Dict[str, float] = {}
@@ -190,18 +177,19 @@ class FusedScorer:
         with torch.cuda.device(dev):
             s = stream()
             users_f16 = torch.empty(padded, 64, dtype=torch.float16, device=dev)
+            inv_scale = torch.empty(n, dtype=torch.float32, device=dev)      # 1 / (the row's own power of two)
             note("pack_begin")
             if uids is None:
                 src = self.user_emb[b0:b1]
-                call("hnm_score_pack", ptr(src), None, n, padded, 64, None, self.user_scale, ptr(users_f16), None, s)
+                call("hnm_score_pack_users", ptr(src), None, n, padded, 64, ptr(users_f16), ptr(inv_scale), s)
                 rid = None
                 user_base = src
             else:
                 rid = uids[b0:b1]
-                call("hnm_score_pack", ptr(self.user_emb), ptr(rid), n, padded, 64, None, self.user_scale,
-                     ptr(users_f16), None, s)
+                call("hnm_score_pack_users", ptr(self.user_emb), ptr(rid), n, padded, 64, ptr(users_f16),
+                     ptr(inv_scale), s)
                 user_base = self.user_emb
-            cand = torch.empty(n, CAND_CAP, 2, dtype=torch.int32, device=dev)
+            cand = torch.empty(n * CAND_CAP * CAND_WORDS, dtype=torch.int32, device=dev)
             count = torch.empty(n, dtype=torch.int32, device=dev)
             thresh = torch.empty(n, dtype=torch.float32, device=dev)
             ws_bytes = int(_lib.load().hnm_score_topk_fused_workspace_bytes(padded, self.items_padded))
@@ -216,7 +204,7 @@ class FusedScorer:
             ex_ptr = excl[0][b0:b1 + 1] if excl[0] is not None else None
             note("rescore_begin")
             call("hnm_rescore_topk", ptr(user_base), ptr(self.item_emb), ptr(rid), n, 64, self.item_begin,
-                 self.num_items, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), self.inv_scale, self.max_item_norm,
+                 self.num_items, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(inv_scale), ptr(self.item_params),
                  ptr(self.center), ptr(ex_ptr), ptr(excl[1]), k, ptr(ids[b0:b1]), ptr(sc[b0:b1]), ptr(cert[b0:b1]), s)
             note("rescore_end")
         if mark:

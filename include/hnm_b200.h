@@ -34,7 +34,7 @@ extern "C" {
 #define HNM_API
 #endif
 
-#define HNM_ABI_VERSION 1
+#define HNM_ABI_VERSION 2
 
 #define HNM_OK 0
 #define HNM_E_NULL (-1)      /* required pointer is NULL */
@@ -160,20 +160,24 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
 /* ------------------------------------------------------------------------
  * Fused full-catalog score + top-k (tensor cores)   replaces lightgcn.py:202 + :356
  *
- * Stage 1  hnm_absmax + hnm_score_pack: fp32 rows -> fp16 rows scaled by a power of
- *          two (row-major [rows_padded, 64], zero padded), plus sum of squares per row.
+ * Stage 1  hnm_absmax + hnm_score_pack_items / hnm_score_pack_users: fp32 rows -> fp16 rows scaled by a
+ *          power of two (row-major [rows_padded, 64], zero padded).  The item shard is centred on a common
+ *          vector and gets ONE scale; every user row gets its OWN scale (the ranking of the items for a
+ *          fixed user does not depend on that user's scale, so heavy-tailed row norms cost no precision).
+ *          All scales stay on the device: no host synchronisation anywhere in the set-up.
  * Stage 2  hnm_score_topk_fused: TMA-fed tcgen05.mma (fp16 x fp16 -> fp32 in TMEM);
- *          the epilogue keeps, per user, every item whose approximate score beats a
- *          running threshold tau (the kth_sel-th largest of 32 disjoint bucket
- *          maxima, a lower bound on the kth_sel-th best score).  The [users, items]
- *          score matrix never exists in memory.  The unit of nomination is a group
- *          of 4 adjacent items: per user the kernel emits cand_count entries
- *          {fp32 bits of the group's best approx score, LOCAL index of its first
- *          item} (cand_count may exceed cand_cap: overflow, the user is then not
- *          certifiable) and the final tau: every item outside the stored groups
- *          scored <= tau.
- * Stage 3  hnm_rescore_topk: exact fp64 scores (k = 0..dim-1 fma chain) of the items
- *          of the groups that ended above tau, optional exclusion (lightgcn.py:349-353), canonical
+ *          the epilogue keeps, per user, every 32-column chunk that holds an approximate score above a
+ *          running threshold tau (the kth_sel-th largest of 32 disjoint bucket maxima, a lower bound on
+ *          the kth_sel-th best score).  The [users, items] score matrix never exists in memory.  Per user
+ *          the kernel emits cand_count entries; `cand` is two arrays back to back,
+ *              uint32 q[num_users * cand_cap][4]   the chunk's 8 group maxima (groups of 4 adjacent items), each
+ *                            cut to its upper 16 bits (bf16 truncated toward zero), group 2j in the low half of q[j]
+ *              uint32 col[num_users * cand_cap]    LOCAL index of the chunk's first item
+ *          i.e. HNM_FUSED_CAND_BYTES bytes per entry, the entries of user r at index r * cand_cap of both arrays
+ *          (cand_count may exceed cand_cap: overflow, the user is then not certifiable) and the final tau:
+ *          every item outside the stored chunks scored <= tau.
+ * Stage 3  hnm_rescore_topk: exact fp64 scores (k = 0..dim-1 fma chain) of the items of the groups that may
+ *          have ended above tau, optional exclusion (lightgcn.py:349-353), canonical
  *          (score desc, id asc) top-k, and a per-user certificate
  *              exact_kth > tau / (su*si) + eps + u.c,
  *              eps = 1.1 * 2^-10 * ||u|| * max_j ||x_j - c|| + dim * 2^-8 / (su*si)
@@ -188,41 +192,49 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
 #define HNM_FUSED_DIM 64            /* embedding dimension of the tensor-core path */
 #define HNM_FUSED_USER_TILE 128     /* users per accumulator (UMMA M); users_padded must be a multiple */
 #define HNM_FUSED_ITEM_TILE 128     /* items per MMA tile (UMMA N); items_padded must be a multiple */
-#define HNM_FUSED_CAND_MAX 256      /* largest cand_cap */
+#define HNM_FUSED_CAND_MAX 256      /* largest cand_cap (entries per user) */
+#define HNM_FUSED_CAND_BYTES 20     /* bytes per candidate entry (16 in the q array + 4 in the col array) */
 
 /* max |x - center[col]| over `count` floats of a [rows, dim] table -> *out_absmax (device float,
  * zeroed by the caller).  center NULL = no centring. */
 HNM_API int hnm_absmax(const float* emb, int64_t count, const float* center, int32_t dim, float* out_absmax,
                void* stream);
-/* out = fp16((emb[row] - center) * scale).  Item tables are centred on their mean row: for a fixed
- * user, u.x and u.(x - c) rank items identically, and the smaller magnitudes tighten the bound. */
-HNM_API int hnm_score_pack(const float* emb, const int64_t* row_ids /* NULL = identity */, int64_t num_rows,
-                   int64_t rows_padded, int32_t dim, const float* center /* [dim] or NULL */,
-                   float scale /* power of two */,
-                   void* out_f16 /* [rows_padded, dim] __half */, float* out_sumsq /* [num_rows] or NULL */,
-                   void* stream);
+/* Item shard: out = fp16((emb[row] - center) * s), s = the power of two that puts params[0] (the absmax left
+ * there by hnm_absmax) into [2^14, 2^15).  Item tables are centred on their mean row: for a fixed user, u.x
+ * and u.(x - c) rank items identically, and the smaller magnitudes tighten the bound.
+ * params (device float[4], params[2] zeroed by the caller): in [0] absmax; out [1] = s, [2] = max_j ||x_j - c||^2. */
+HNM_API int hnm_score_pack_items(const float* emb, int64_t num_rows, int64_t rows_padded, int32_t dim,
+                         const float* center /* [dim] or NULL */, float* params /* device float[4] */,
+                         void* out_f16 /* [rows_padded, dim] __half */, void* stream);
+/* Users: out[r] = fp16(emb[row_ids[r]] * s_r) with s_r the power of two that puts the row's own absmax into
+ * [2^14, 2^15); out_inv_scale[r] = 1 / s_r. */
+HNM_API int hnm_score_pack_users(const float* emb, const int64_t* row_ids /* NULL = identity */, int64_t num_rows,
+                         int64_t rows_padded, int32_t dim, void* out_f16 /* [rows_padded, dim] __half */,
+                         float* out_inv_scale /* [num_rows] */, void* stream);
 HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */, int64_t num_users, int64_t users_padded,
                          const void* items_f16 /* [items_padded, 64] */, int64_t num_items, int64_t items_padded,
                          int32_t kth_sel /* 1..32 */,
-                         void* cand /* [num_users, cand_cap] x {uint32 score bits, uint32 local item} */,
+                         void* cand /* num_users * cand_cap * HNM_FUSED_CAND_BYTES bytes, 16-byte aligned (layout above) */,
                          int32_t cand_cap, int32_t* cand_count /* [num_users] */,
                          float* cand_thresh /* [num_users] final tau (scaled units) */,
                          void* workspace /* hnm_score_topk_fused_workspace_bytes(), may be NULL when that is 0 */,
                          int64_t workspace_bytes, void* stream);
 /* Scratch for the user tiles that do not fill a whole pass of the persistent grid: their item range is cut
  * into slices handled by different CTAs, with one candidate list per (user, slice) that a second kernel
- * merges into `cand` (at most ~30 MB).  < 0 on bad sizes. */
+ * merges into `cand` (at most ~240 MB at the H&M catalog).  < 0 on bad sizes. */
 HNM_API int64_t hnm_score_topk_fused_workspace_bytes(int64_t users_padded, int64_t items_padded);
-/* Host only: how the launch distributes its work.  out5 = {grid, full passes per CTA (3 user tiles x whole
- * catalog each), first left-over user tile, left-over triples, item slices per triple}. */
-HNM_API int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_padded, int32_t* out5);
+/* Host only: how the launch distributes its work.  out6 = {grid, full passes per CTA (T user tiles x whole
+ * catalog each), first left-over user tile, left-over groups of T tiles, item slices per group, T}. */
+HNM_API int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_padded, int32_t* out6);
 HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb /* local shard rows */,
-                     const int64_t* user_ids /* NULL = identity */, int64_t batch, int32_t dim, int64_t item_begin,
+                     const int64_t* user_ids /* NULL = identity */, int64_t batch, int32_t dim /* 64 */,
+                     int64_t item_begin,
                      int64_t num_items_local /* rows of item_emb; columns past it are zero padding */,
-                     const void* cand, int32_t cand_cap, const int32_t* cand_count, const float* cand_thresh,
-                     double inv_scale_product /* 1/(user_scale*item_scale) */,
-                     double max_item_norm /* max ||x_j - center|| over the shard */,
-                     const float* center /* the item centre used by hnm_score_pack, or NULL */,
+                     const void* cand /* as written by hnm_score_topk_fused for num_users = batch */, int32_t cand_cap,
+                     const int32_t* cand_count, const float* cand_thresh,
+                     const float* user_inv_scale /* [batch], from hnm_score_pack_users */,
+                     const float* item_params /* device float[4], from hnm_absmax + hnm_score_pack_items */,
+                     const float* center /* the item centre used by hnm_score_pack_items, or NULL */,
                      const int64_t* excl_ptr, const int64_t* excl_items /* GLOBAL ids, sorted per user */,
                      int32_t k, int64_t* out_ids /* [batch,k] GLOBAL item ids */, double* out_scores /* [batch,k] */,
                      int32_t* out_certified /* [batch] 1 = provably exact; else reason bits: 2 list overflow,

@@ -8,7 +8,7 @@ int main(void) {
   int32_t plan[5];
   int rc = hnm_score_topk_fused_plan(10719 * 128, 825 * 128, plan);
   if (rc != 0) return 10;
-  if (hnm_abi_version() != 1) return 11;
+  if (hnm_abi_version() != HNM_ABI_VERSION) return 11;
   if (hnm_score_topk_fused_plan(100, 128, plan) != HNM_E_RANGE) return 12;        /* users_padded not a multiple of 128 */
   if (hnm_score_topk_fused_plan(128, 128, (int32_t*)0) != HNM_E_NULL) return 13;
   if (hnm_score_topk_fused_workspace_bytes(10719 * 128, 825 * 128) <= 0) return 14;

@@ -57,17 +57,21 @@ def test_fused_subset_filter_and_shard(hnm_lib):
     assert torch.equal(ids.cpu(), w_ids + 1000) and torch.equal(s.cpu(), w_s)
 
 
-@pytest.mark.parametrize("u,i,kind", [(300, 16500, "randn"), (1000, 33000, "small"), (57000, 8300, "randn")])
+@pytest.mark.parametrize("u,i,kind", [(300, 16500, "randn"), (1000, 33000, "small"), (-9, 8300, "randn")])
 def test_fused_sliced_left_over_tiles_bit_exact(hnm_lib, u, i, kind):
     """User tiles that do not fill a whole pass of the persistent grid have their item range sliced over
-    the CTAs (one candidate list per slice, merged under a recomputed threshold): same lists, bit for bit."""
+    the CTAs (one candidate list per slice, merged under a recomputed threshold): same lists, bit for bit.
+    u < 0: one whole pass on every CTA plus -u left-over tiles (the count depends on the CTA shape in use)."""
     import ctypes as C
     from hnm_recommendation_b200 import engine
     from hnm_recommendation_b200.scorer import FusedScorer
-    plan = (C.c_int32 * 5)()
+    plan = (C.c_int32 * 6)()
     pad = lambda x: (x + 127) // 128 * 128
+    if u < 0:
+        assert hnm_lib.hnm_score_topk_fused_plan(128, pad(i), plan) == 0
+        u = (plan[0] * plan[5] - u) * 128 - 50
     assert hnm_lib.hnm_score_topk_fused_plan(pad(u), pad(i), plan) == 0
-    grid, full, tile0, triples, slices = list(plan)
+    grid, full, tile0, triples, slices, mu = list(plan)
     assert triples > 0 and slices > 1, list(plan)                  # the case under test
     ue, ie = _emb(u, i, seed=u + i, kind=kind)
     ue, ie = ue.cuda(), ie.cuda()

@@ -35,7 +35,7 @@ def test_ctypes_signatures_match_header_arity():
 
 
 def test_abi_version_and_strerror(hnm_lib):
-    assert hnm_lib.hnm_abi_version() == 1
+    assert hnm_lib.hnm_abi_version() == 2
     assert hnm_lib.hnm_strerror(0) == b"ok"
     assert b"NULL" in hnm_lib.hnm_strerror(-1)
     assert hnm_lib.hnm_strerror(-3) != hnm_lib.hnm_strerror(-2)
@@ -107,30 +107,31 @@ def test_metrics_standin():
 @pytest.mark.parametrize("user_tiles,item_tiles", [(1, 2), (8, 825), (63, 40), (444, 825), (1340, 825),
                                                    (10719, 825), (2680, 825), (445, 9), (7, 3)])
 def test_fused_work_plan_covers_every_tile_pair_once(hnm_lib, user_tiles, item_tiles):
-    """hnm_score_topk_fused_plan: whole-catalog passes of 3 user tiles per CTA, the left-over tiles in triples
+    """hnm_score_topk_fused_plan: whole-catalog passes of `mu` user tiles per CTA, the left-over tiles in groups of `mu`
     whose item range is sliced over the CTAs -- every (user tile, item tile) pair belongs to exactly one CTA."""
     import ctypes as C
-    out = (C.c_int32 * 5)()
+    out = (C.c_int32 * 6)()
     assert hnm_lib.hnm_score_topk_fused_plan(user_tiles * 128, item_tiles * 128, out) == 0
-    grid, full, tile0, triples, slices = list(out)
-    assert grid >= 1 and tile0 == grid * 3 * full and 0 <= user_tiles - tile0 < 3 * grid
-    assert triples == -(-(user_tiles - tile0) // 3)
+    grid, full, tile0, triples, slices, mu = list(out)
+    assert mu in (2, 3)
+    assert grid >= 1 and tile0 == grid * mu * full and 0 <= user_tiles - tile0 < mu * grid
+    assert triples == -(-(user_tiles - tile0) // mu)
     if triples:
         assert 1 <= slices and triples * slices <= grid
     seen = np.zeros((user_tiles, item_tiles), dtype=np.int32)
     for b in range(grid):
-        for n in range(full):                       # CTA b, pass n: tiles (b*full + n)*3 .. +3, all items
-            t0 = (b * full + n) * 3
-            seen[t0:t0 + 3, :] += 1
+        for n in range(full):                       # CTA b, pass n: tiles (b*full + n)*mu .. +mu, all items
+            t0 = (b * full + n) * mu
+            seen[t0:t0 + mu, :] += 1
         if b < triples * slices:
             j, sl = divmod(b, slices)
-            t0 = tile0 + 3 * j
+            t0 = tile0 + mu * j
             i0, i1 = sl * item_tiles // slices, (sl + 1) * item_tiles // slices
             assert i1 > i0
-            seen[t0:min(t0 + 3, user_tiles), i0:i1] += 1
+            seen[t0:min(t0 + mu, user_tiles), i0:i1] += 1
     assert (seen == 1).all()
     ws = hnm_lib.hnm_score_topk_fused_workspace_bytes(user_tiles * 128, item_tiles * 128)
-    need = triples * 3 * 128 * slices * (256 * 8 + 8) if slices > 1 else 0
+    need = triples * mu * 128 * slices * (128 * 20 + 8) if slices > 1 else 0    # 128 entries of 20 B + count + tau
     assert ws >= need and ws <= need + 4096
     assert hnm_lib.hnm_score_topk_fused_workspace_bytes(100, 128) < 0
 
