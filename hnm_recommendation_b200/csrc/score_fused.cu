@@ -50,40 +50,43 @@ constexpr int kBootTiles = 16;              // item tiles used to seed the bucke
 constexpr int kTileBytes = kItemTile * kDim * 2; // 16384 (A tile and B tile have the same shape)
 constexpr int kNumBuckets = 32;
 constexpr uint32_t kWaitHintNs = 0;         // suspend-time hint of the control warps' mbarrier waits (0 = none)
-constexpr int kMaxStagesB = 8;
-constexpr int kMaxSlots = 4;                // TMEM: 512 columns = 4 accumulators of 128 columns
 
-// Two shapes of the persistent CTA, both compiled, chosen per launch (HNM_FUSED_SHAPE, default 2x2):
-//   MU = 3, BUF = 1   three user tiles, ONE accumulator each (384 TMEM columns), 12 epilogue warps -- round 1.
-//                     An accumulator is handed back to its MMA issuer only after the epilogue has pulled it
-//                     into registers, so MMA and drain of one user tile alternate; with the light select of
-//                     this round that chain (issue 4 MMAs -> complete -> wake -> 2 TMEM round trips -> arrive
-//                     -> wake) is the step time, not any pipe.
-//   MU = 2, BUF = 2   two user tiles, TWO accumulators each (all 512 columns), 8 epilogue warps: the tensor
-//                     pipe fills buffer 1 of a tile while its warpgroup drains buffer 0.
-template <int MU_, int BUF_>
-struct Shape {
-  static constexpr int MU = MU_;                       // user tiles per CTA pass
-  static constexpr int BUF = BUF_;                     // accumulators per user tile
-  static constexpr int kSlots = MU * BUF;
-  static constexpr int kStagesB = MU == 2 ? 8 : 6;
-  static constexpr int kThreads = (4 + 4 * MU) * 32;   // 4 control warps + one epilogue warpgroup per user tile
-  static constexpr bool kSetMaxNReg = MU == 3;         // 512 threads: control warps give registers to the epilogue
-  static_assert(kSlots <= kMaxSlots && kStagesB <= kMaxStagesB && MU <= 3, "shape");
-};
+// Shape of the persistent CTA (round 2):
+//   2 user tiles per pass, 2 accumulators (128 TMEM columns) each = all 512 columns: the tensor pipe fills one
+//   buffer of a user tile while the other one is drained (round 1: 3 tiles x 1 accumulator, where the chain
+//   issue 4 MMAs -> complete -> wake -> 2 TMEM round trips -> arrive -> wake set the step time);
+//   2 threads per user row, each draining 64 of an accumulator's 128 columns: 16 epilogue warps = 4 per
+//   scheduler.  ncu of the one-thread-per-row form: ALU pipe 62 % busy, half of the epilogue's stall samples
+//   fixed-latency waits with 2 warps per scheduler to hide them behind.
+constexpr int kMU = 2;                      // user tiles per CTA pass
+constexpr int kBUF = 2;                     // accumulators per user tile
+constexpr int kHalves = 2;                  // threads per user row (column halves of an accumulator)
+constexpr int kSlots = kMU * kBUF;
+constexpr int kStagesB = 6;
+constexpr int kEpiWarps = 4 * kMU * kHalves;      // 16
+constexpr int kThreads = (4 + kEpiWarps) * 32;    // 640
+constexpr int kHalfBuckets = kNumBuckets / kHalves;
+constexpr int kCtlRegs = 32, kEpiRegs = 112;      // setmaxnreg: the CTA is launched with 96 registers x 640 threads = 61 440, and
+                                                  // 128 * 32 + 512 * 112 must not exceed THAT (not 64 K): a warpgroup whose
+                                                  // setmaxnreg.inc cannot be served waits forever
+static_assert(128 * kCtlRegs + 512 * kEpiRegs <= 96 * kThreads, "register pool");
 
 static_assert(kUserTile == HNM_FUSED_USER_TILE && kItemTile == HNM_FUSED_ITEM_TILE, "header mismatch");
+static_assert(kSlots * kItemTile <= 512, "TMEM columns");
 
 struct __align__(8) Barriers {
   uint64_t a_full[2], a_empty[2];
-  uint64_t b_full[kMaxStagesB], b_empty[kMaxStagesB];
-  uint64_t t_full[kMaxSlots], t_empty[kMaxSlots];
+  uint64_t b_full[kStagesB], b_empty[kStagesB];
+  uint64_t t_full[kSlots], t_empty[kSlots];
   uint32_t tmem_base;
 };
-template <class S>
-constexpr size_t smem_bytes() {
-  return 1024 /*align slack*/ + 2 * S::MU * kTileBytes + S::kStagesB * kTileBytes + sizeof(Barriers);
-}
+// bucket exchange between the two threads of a row: [user tile][quarter][bucket][lane] + the agreed tau
+struct PairXchg {
+  float bm[kMU][4][kHalfBuckets][32];
+  float tau[kMU][4][32];
+};
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + 2 * kMU * kTileBytes + kStagesB * kTileBytes + sizeof(PairXchg) +
+                              sizeof(Barriers);
 
 // ----------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,10 +208,11 @@ __device__ __forceinline__ void tmem_ld_wait(float (&a)[32], float (&b)[32]) {
 #undef HNM_F8
 
 // ----------------------------------------------------------------------------- select state
+// One of the two threads of a user row: it sees columns [64 h, 64 h + 64) of every item tile.
 struct RowState {
-  float tau;                  // collect threshold (+inf while seeding)
-  int cnt;                    // candidates appended so far (may exceed the capacity: overflow)
-  float bm[kNumBuckets];      // bucket maxima (an unordered multiset: see refresh_tau)
+  float tau;                  // collect threshold (+inf while seeding), common to both threads of the row
+  int cnt;                    // chunks this thread appended so far (may exceed its capacity: overflow)
+  float bm[kHalfBuckets];     // bucket maxima; bucket = position of the 4-column group inside the item tile
 };
 
 __device__ __forceinline__ void cmpx(float& a, float& b) {   // a <- max, b <- min
@@ -217,11 +221,8 @@ __device__ __forceinline__ void cmpx(float& a, float& b) {   // a <- max, b <- m
   b = lo;
 }
 
-// Bitonic sorting network (descending, 240 comparators) over the 32 bucket registers, then
-// tau = bm[kth-1].  Sorting in place is legal: after any permutation register r still holds the
-// maximum of some item set S_r, the S_r stay pairwise disjoint, and later updates add each new item
-// to exactly one S_r.
-__device__ __forceinline__ float refresh_tau(float (&bm)[kNumBuckets], int kth) {
+// kth largest of 32 values: bitonic sorting network (descending, 240 comparators) on a scratch copy.
+__device__ __forceinline__ float kth_largest32(float (&t)[kNumBuckets], int kth) {
 #pragma unroll
   for (int k = 2; k <= kNumBuckets; k <<= 1) {
 #pragma unroll
@@ -230,16 +231,43 @@ __device__ __forceinline__ float refresh_tau(float (&bm)[kNumBuckets], int kth) 
       for (int i = 0; i < kNumBuckets; ++i) {
         const int l = i ^ j;
         if (l > i) {
-          if ((i & k) == 0) cmpx(bm[i], bm[l]);
-          else cmpx(bm[l], bm[i]);
+          if ((i & k) == 0) cmpx(t[i], t[l]);
+          else cmpx(t[l], t[i]);
         }
       }
     }
   }
-  float t = bm[0];
+  float r = t[0];
 #pragma unroll
-  for (int i = 1; i < kNumBuckets; ++i) t = (i < kth) ? bm[i] : t;
-  return t;
+  for (int i = 1; i < kNumBuckets; ++i) r = (i < kth) ? t[i] : r;
+  return r;
+}
+
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// tau = the kth largest of the row's 32 bucket maxima.  The buckets hold disjoint item sets, so tau is a
+// lower bound on the kth best score seen.  Thread h = 1 of the row hands its 16 maxima to thread h = 0
+// through shared memory, h = 0 sorts a copy of all 32 and hands tau back; the two warps meet at a 64-thread
+// named barrier (the schedule of refreshes is the same function of the pass for both).  The bucket
+// registers themselves are never permuted, so revisiting an item (the seed tiles are swept twice) is
+// idempotent.
+__device__ __forceinline__ float refresh_tau(const RowState& st, int h, float* xb /* [16][32] */, float* xt /* [32] */,
+                                             int bar_id, int kth, int lane) {
+  if (h == 1) {
+#pragma unroll
+    for (int i = 0; i < kHalfBuckets; ++i) xb[i * 32 + lane] = st.bm[i];
+    pair_bar(bar_id);
+    pair_bar(bar_id);
+    return xt[lane];
+  }
+  pair_bar(bar_id);
+  float t[kNumBuckets];
+#pragma unroll
+  for (int i = 0; i < kHalfBuckets; ++i) { t[i] = st.bm[i]; t[kHalfBuckets + i] = xb[i * 32 + lane]; }
+  const float tau = kth_largest32(t, kth);
+  xt[lane] = tau;
+  pair_bar(bar_id);
+  return tau;
 }
 
 // One nominated 32-column chunk of one user row: the chunk's eight group maxima (groups of 4 adjacent
@@ -288,10 +316,8 @@ __device__ __forceinline__ void group_max(const float (&v)[32], float (&q)[8]) {
   }
 }
 
-enum { kSeed = 0, kCollectOnly = 1, kCollect = 2 };
-// kSeed: first visit of the seed tiles -- buckets only (tau is +inf).  kCollectOnly: their second visit --
-// their items already sit in the buckets, and after refresh_tau has permuted the bucket registers an item
-// must not be added to a second one (tau would stop being a lower bound).  kCollect: everything else.
+enum { kSeed = 0, kCollect = 1 };
+// kSeed: first visit of the seed tiles -- buckets only (tau is +inf).  kCollect: everything else.
 template <int MODE>
 __device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col0, RowState& st,
                                          const CandList cand, int cap) {
@@ -302,10 +328,8 @@ __device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col
   }
   const float m32 = fmaxf(fmaxf(fmaxf(fmaxf(q[0], q[1]), q[2]), fmaxf(fmaxf(q[3], q[4]), q[5])), fmaxf(q[6], q[7]));
   if (m32 > st.tau) {
-    if (MODE == kCollect) {
 #pragma unroll
-      for (int h = 0; h < 8; ++h) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
-    }
+    for (int h = 0; h < 8; ++h) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
     if (st.cnt >= cap) {                 // no room: stop collecting, flag the row
       st.tau = INFINITY;
       st.cnt = cap + 1;
@@ -322,30 +346,22 @@ __device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col
   }
 }
 
-// One 128-column accumulator of one user row.  Two 32-column loads are kept in flight: chunks 2 and 3
-// are fetched while chunks 0 and 1 are processed, so one TMEM round trip per tile is exposed, not four.
+// This thread's 64 columns of one accumulator: both 32-column loads are issued together, and the
+// accumulator goes back to its MMA issuer as soon as they have landed (the 8 warps of the user tile arrive).
 template <int MODE>
-__device__ __forceinline__ void drain_tile(uint32_t taddr, int item0, RowState& st, const CandList cand,
-                                           int cap, uint64_t* t_empty, int lane) {
-  float va[32], vb[32], q0[8], q1[8];
+__device__ __forceinline__ void drain_half(uint32_t taddr, int col0, RowState& st, const CandList cand, int cap,
+                                           uint64_t* t_empty, int lane) {
+  float va[32], vb[32], q[8];
   tmem_ld32(taddr, va);
   tmem_ld32(taddr + 32, vb);
   tmem_ld_wait(va, vb);
-  group_max(va, q0);
-  tmem_ld32(taddr + 64, va);
-  group_max(vb, q1);
-  tmem_ld32(taddr + 96, vb);
-  finish32<MODE>(q0, 0, item0, st, cand, cap);
-  finish32<MODE>(q1, 1, item0 + 32, st, cand, cap);
-  tmem_ld_wait(va, vb);
-  // every column of this accumulator is in registers: hand it back to its MMA issuer
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(t_empty);
-  group_max(va, q0);
-  group_max(vb, q1);
-  finish32<MODE>(q0, 2, item0 + 64, st, cand, cap);
-  finish32<MODE>(q1, 3, item0 + 96, st, cand, cap);
+  group_max(va, q);
+  finish32<MODE>(q, 0, col0, st, cand, cap);
+  group_max(vb, q);
+  finish32<MODE>(q, 1, col0 + 32, st, cand, cap);
 }
 
 // ----------------------------------------------------------------------------- work distribution
@@ -409,7 +425,7 @@ __device__ __forceinline__ bool pass_desc(int n, int num_user_tiles, int num_ite
   return true;
 }
 
-// index of a row's {list, count, tau}: the row itself, or (left-over row, slice)
+// index of a row's {lists, counts, tau}: the row itself, or (left-over row, slice)
 __device__ __forceinline__ uint32_t out_slot(const PassDesc& p, const SplitPlan& sp, int m, int q, int lane) {
   const int row = (p.t0 + m) * kUserTile + q * 32 + lane;
   return p.slice < 0 ? (uint32_t)row : (uint32_t)((row - sp.tile0 * kUserTile) * sp.slices + p.slice);
@@ -422,8 +438,9 @@ __device__ __forceinline__ int pass_tile(const PassDesc& p, int it) {
 }
 
 // ----------------------------------------------------------------------------- the kernel
-template <class S>
-__global__ void __launch_bounds__(S::kThreads, 1)
+// Candidate storage of a row: `cap` entries, the first cap/2 for thread h = 0 (columns 0..63 of every item
+// tile), the rest for h = 1; cand_count[2 row + h] entries are valid in each half.
+__global__ void __launch_bounds__(kThreads, 1)
 score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                         int num_users, int num_user_tiles, int num_item_tiles, int kth_sel,
                         const CandList cand, int cap, int32_t* __restrict__ cand_count,
@@ -431,10 +448,10 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
                         uint32_t wait_hint_ns, const SplitPlan sp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kMU = S::MU, kBUF = S::BUF, kStagesB = S::kStagesB;
   uint8_t* smem_a = smem;                                   // [2][kMU][kTileBytes]
   uint8_t* smem_b = smem + 2 * kMU * kTileBytes;            // [kStagesB][kTileBytes]
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_b + kStagesB * kTileBytes);
+  PairXchg* xchg = reinterpret_cast<PairXchg*>(smem_b + kStagesB * kTileBytes);
+  Barriers* bars = reinterpret_cast<Barriers*>(xchg + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -445,7 +462,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     tma_prefetch_desc(&map_items);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], kMU); }
     for (int i = 0; i < kStagesB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], kMU); }
-    for (int i = 0; i < S::kSlots; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
+    for (int i = 0; i < kSlots; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4 * kHalves); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -459,9 +476,9 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp < 4) {
-  // The 4 control warps give registers back so the 12 epilogue warps can hold a whole 64-column
-  // double buffer plus the 32 bucket maxima without spilling (40 * 128 + 152 * 384 <= 64 K).
-  if (S::kSetMaxNReg) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  // The control warpgroup gives registers back so that the 16 epilogue warps can hold two 32-column loads,
+  // their 16 bucket maxima and the 32-value scratch of the threshold refresh without spilling.
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
@@ -488,8 +505,7 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     // ===================================================== MMA issuers: warp 1 + m serves user tile m
     // tcgen05.mma holds its issuing thread for about the duration of the MMA (tools/bench_mma.cu:
     // 73 cycles per M128 N128 K16), so with a single issuer every mbarrier wait / fence / commit adds
-    // to the tensor pipe's critical path (measured: 562 cycles per accumulator instead of 292).  Three
-    // issuing threads, one per user tile, overlap each other's bookkeeping with MMA issue.
+    // to the tensor pipe's critical path.  One issuing thread per user tile.
     const int m = warp - 1;
     if (lane == 0) {
       uint32_t g = 0, uses = 0;
@@ -528,71 +544,84 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     }
   }
   } else {
-    // ===================================================== epilogue: warpgroup m drains user tile m
-    if (S::kSetMaxNReg) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-    const int m = (warp - 4) >> 2;
+    // ===================================================== epilogue: 2 warpgroups (column halves) per user tile
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+    const int e = warp - 4;
+    const int m = e >> 3;                          // user tile
+    const int h = (e >> 2) & 1;                    // column half
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + h * (kItemTile / kHalves);
+    float* xb = &xchg->bm[m][q][0][0];
+    float* xt = &xchg->tau[m][q][0];
+    const int bar_id = 1 + m * 4 + q;              // barrier 0 is __syncthreads
     uint32_t uses = 0;
     for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
-      if (m >= p.mc) continue;                                              // short pass: this warpgroup rests
+      if (m >= p.mc) continue;                                              // short pass: these warpgroups rest
       const int boot = p.boot;
       const int num_iters = p.ni + boot;
-      // where this row's candidates go: its own list, or its list for this item slice
+      // where this thread's candidates go: its half of the row's list, or of the row's list for this item slice
       const uint32_t slot = out_slot(p, sp, m, q, lane);
       const bool real = (p.t0 + m) * kUserTile + q * 32 + lane < num_users;
       const int out_cap = p.slice < 0 ? cap : sp.cap;
-      const CandList my_cand = (p.slice < 0 ? cand : sp.cand).at((size_t)(real ? slot : 0) * out_cap);
-      const int my_cap = real ? out_cap : 0;             // padded rows count but never store
+      const int half_cap = out_cap / kHalves;
+      const CandList my_cand = (p.slice < 0 ? cand : sp.cand).at((size_t)(real ? slot : 0) * out_cap + h * half_cap);
+      const int my_cap = real ? half_cap : 0;            // padded rows count but never store
+      int32_t* out_count = (p.slice < 0 ? cand_count : sp.count) + (size_t)slot * kHalves + h;
+      float* out_thresh = (p.slice < 0 ? cand_thresh : sp.thresh) + slot;
       RowState rs;
       rs.tau = INFINITY;
       rs.cnt = 0;
 #pragma unroll
-      for (int i = 0; i < kNumBuckets; ++i) rs.bm[i] = -INFINITY;
-      int next_refresh = boot;
+      for (int i = 0; i < kHalfBuckets; ++i) rs.bm[i] = -INFINITY;
       // item tile of this iteration.  Only whole-catalog passes are rotated, so the sweep wraps at the end of
       // the catalog in both kinds of pass (a slice never gets there before its last iteration).
       const int restart = p.i0 + p.rot;
       int cur = restart;
-      for (int it = 0; it < num_iters; ++it) {
-        if (it == boot) cur = restart;                   // the seed tiles are visited a second time
-        const int tile = cur;
-        if (++cur == num_item_tiles) cur = 0;
-        if (it == next_refresh && mode == 0) {
-          // it == boot: the seed pass is over, collecting starts (again from tile 0)
-          rs.tau = refresh_tau(rs.bm, kth_sel);
-          const int seen = max(boot, it - boot);         // item tiles behind the current bucket maxima
-          next_refresh = it + max(2, seen / refresh_div);
-        }
-        const int slot_t = m * kBUF + (int)(uses % kBUF);
-        const uint32_t taddr = lane_base + slot_t * kItemTile;
-        uint64_t* t_empty = &bars->t_empty[slot_t];
-        mbar_wait(&bars->t_full[slot_t], (uses / kBUF) & 1);
-        ++uses;
-        tc_fence_after();
-        if (mode == 1 || mode == 3 || mode == 4) {   // debug: drain only / handshake only / one load
+      int it = 0;
+      // one accumulator: wait for it, drain this thread's half
+#define HNM_TILE_STEP(MODE)                                                                        \
+      {                                                                                            \
+        const int col0 = cur * kItemTile + h * (kItemTile / kHalves);                              \
+        if (++cur == num_item_tiles) cur = 0;                                                      \
+        const int slot_t = m * kBUF + (int)(uses & 1u);                                            \
+        mbar_wait(&bars->t_full[slot_t], (uses >> 1) & 1u);                                        \
+        ++uses;                                                                                    \
+        tc_fence_after();                                                                          \
+        drain_half<MODE>(lane_base + slot_t * kItemTile, col0, rs, my_cand, my_cap,                \
+                         &bars->t_empty[slot_t], lane);                                            \
+      }
+      if (mode != 0) {
+        // debug shapes of the pipeline: 3 = handshakes only, 4 = one load, 1 = both loads, 2 = + the hot path
+        for (; it < num_iters; ++it) {
+          const int slot_t = m * kBUF + (int)(uses & 1u);
+          if (mode == 2) { HNM_TILE_STEP(kSeed) continue; }
+          mbar_wait(&bars->t_full[slot_t], (uses >> 1) & 1u);
+          ++uses;
+          tc_fence_after();
           float va[32];
           float acc = 0.f;
-          const int nld = mode == 1 ? 4 : (mode == 4 ? 1 : 0);
-          for (int c = 0; c < nld; ++c) { tmem_ld32(taddr + c * 32, va); tmem_ld_wait(va); acc += va[c]; }
+          const int nld = mode == 1 ? 2 : (mode == 4 ? 1 : 0);
+          for (int c = 0; c < nld; ++c) { tmem_ld32(lane_base + slot_t * kItemTile + c * 32, va); tmem_ld_wait(va); acc += va[c]; }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty);
+          if (lane == 0) mbar_arrive(&bars->t_empty[slot_t]);
           rs.bm[0] += acc;
-        } else if (it < boot) {                        // first visit of a seed tile: buckets only
-          drain_tile<kSeed>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
-        } else if (it < 2 * boot) {                    // second visit of a seed tile: collect only
-          drain_tile<kCollectOnly>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
-        } else {
-          drain_tile<kCollect>(taddr, tile * kItemTile, rs, my_cand, my_cap, t_empty, lane);
         }
+      } else {
+        for (; it < boot; ++it) HNM_TILE_STEP(kSeed)     // the seed tiles: buckets only
+        cur = restart;                                    // ... and they are swept a second time, collecting
+        while (it < num_iters) {
+          rs.tau = refresh_tau(rs, h, xb, xt, bar_id, kth_sel, lane);
+          const int seen = max(boot, it - boot);         // item tiles behind the current bucket maxima
+          const int stop = min(num_iters, it + max(2, seen / refresh_div));
+          for (; it < stop; ++it) HNM_TILE_STEP(kCollect)
+        }
+        rs.tau = refresh_tau(rs, h, xb, xt, bar_id, kth_sel, lane);
       }
-      if (mode == 0) rs.tau = refresh_tau(rs.bm, kth_sel);
-      pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p);      // recomputed: not kept live in the loop
-      if ((p.t0 + m) * kUserTile + q * 32 + lane < num_users) {
-        const uint32_t slot2 = out_slot(p, sp, m, q, lane);
-        (p.slice < 0 ? cand_count : sp.count)[slot2] = rs.cnt;
-        (p.slice < 0 ? cand_thresh : sp.thresh)[slot2] = rs.tau;
+#undef HNM_TILE_STEP
+      if (real) {
+        *out_count = rs.cnt;
+        if (h == 0) *out_thresh = rs.tau;
       }
     }
   }
@@ -631,28 +660,29 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand
   const int row = sp.tile0 * kUserTile + lu;
   if (row >= num_users) return;
   const size_t base = (size_t)lu * sp.slices;
+  const int half_cap = sp.cap / kHalves;
+  const int lists = sp.slices * kHalves;             // sub-list l = (slice l / 2, column half l % 2)
   float thr = -INFINITY;
   bool over = false;
-  for (int s = lane; s < sp.slices; s += 32) {
-    thr = fmaxf(thr, sp.thresh[base + s]);
-    over |= sp.count[base + s] > sp.cap;
-  }
+  for (int s = lane; s < sp.slices; s += 32) thr = fmaxf(thr, sp.thresh[base + s]);
+  for (int l = lane; l < lists; l += 32) over |= sp.count[base * kHalves + l] > half_cap;
 #pragma unroll
   for (int off = 16; off; off >>= 1) thr = fmaxf(thr, __shfl_xor_sync(0xffffffffu, thr, off));
   over = __any_sync(0xffffffffu, over);
   if (over) {                      // a slice ran out of room: the user is not certifiable from these lists
     if (lane == 0) {
-      cand_count[row] = cap + 1;
+      cand_count[(size_t)row * kHalves] = cap + 1;
+      cand_count[(size_t)row * kHalves + 1] = 0;
       cand_thresh[row] = INFINITY;
     }
     return;
   }
   // kth_sel-th largest stored group maximum (its lower bound: the stored 16 bits are a truncation):
-  // running top 32 over all slice lists, lane i = (i+1)-th largest
+  // running top 32 over all sub-lists, lane i = (i+1)-th largest
   float top = -INFINITY;
-  for (int s = 0; s < sp.slices; ++s) {
-    const int cnt = sp.count[base + s];
-    const CandList in = sp.cand.at((base + s) * sp.cap);
+  for (int l = 0; l < lists; ++l) {
+    const int cnt = sp.count[base * kHalves + l];
+    const CandList in = sp.cand.at((base + (l >> 1)) * sp.cap + (l & 1) * half_cap);
     for (int i0 = 0; i0 < cnt; i0 += 32) {
       const bool have = i0 + lane < cnt;
       uint4 q = make_uint4(0u, 0u, 0u, 0u);
@@ -678,12 +708,13 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand
   // best score because good items share buckets.  Taking the exact kth_sel-th best group here would leave less
   // room between the k-th score and the threshold, and 30x more sliced users failed their certificate.
   thr = fmaxf(thr, __shfl_sync(0xffffffffu, top, min(kth_sel + 4, 32) - 1));
-  // gather the chunks that still hold a group above thr (judged by the upper end of its interval)
+  // gather the chunks that still hold a group above thr (judged by the upper end of its interval) into the
+  // row's ordinary storage as ONE list: all `cap` entries belong to the first half, the second stays empty
   const CandList out = cand.at((size_t)row * cap);
   int total = 0;
-  for (int s = 0; s < sp.slices; ++s) {
-    const int cnt = sp.count[base + s];
-    const CandList in = sp.cand.at((base + s) * sp.cap);
+  for (int l = 0; l < lists; ++l) {
+    const int cnt = sp.count[base * kHalves + l];
+    const CandList in = sp.cand.at((base + (l >> 1)) * sp.cap + (l & 1) * half_cap);
     for (int i0 = 0; i0 < cnt; i0 += 32) {
       const int i = i0 + lane;
       uint4 q = make_uint4(0u, 0u, 0u, 0u);
@@ -709,7 +740,8 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand
     }
   }
   if (lane == 0) {
-    cand_count[row] = total;       // > cap: overflow, flagged by hnm_rescore_topk
+    cand_count[(size_t)row * kHalves] = total;       // > cap: overflow, flagged by hnm_rescore_topk
+    cand_count[(size_t)row * kHalves + 1] = 0;
     cand_thresh[row] = total > cap ? INFINITY : thr;
   }
 }
@@ -874,8 +906,12 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   float* tile1 = reinterpret_cast<float*>(sm.tile);
   const int64_t uid = user_ids ? user_ids[b] : b;
   const float* urow = user_emb + (size_t)uid * kDim;
-  const int raw = cand_count[b];
-  const int n = min(raw, cap);
+  // the row's storage: cap entries; list 0 starts at entry 0, list 1 at cap / 2 (the two threads of the row in
+  // the fused kernel); a lone list 0 (merge_split_kernel) may use all of it
+  const int raw0 = cand_count[2 * b], raw1 = cand_count[2 * b + 1];
+  const int cap0 = raw1 > 0 ? cap / 2 : cap;
+  const bool list_overflow = raw0 > cap0 || raw1 > cap / 2;
+  const int n0 = min(raw0, cap0), n1 = min(raw1, cap / 2);
   const float thr = cand_thresh[b];
   const CandList mine = cand.at((size_t)b * cap);
   int64_t ex_lo = 0, ex_hi = 0;
@@ -890,14 +926,15 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     // that a later CTA will take: its list head (lane i: 32 bytes), count, threshold and embedding row.
     const int64_t pb = b + kRescorePrefetch;
     if (pb < batch) {
-      if (4 * lane + 3 < cap) {      // the first 128 entries: 64 bytes of maxima per lane, 512 bytes of columns
-        const char* pa = reinterpret_cast<const char*>(cand.q + (size_t)pb * cap) + lane * 64;
+      if (4 * lane + 3 < cap) {      // 64 entries of each list: 64 bytes of maxima per lane, 256 bytes of columns
+        const int pe = (lane < 16 ? 0 : cap / 2 - 64) + 4 * lane;
+        const char* pa = reinterpret_cast<const char*>(cand.q + (size_t)pb * cap + pe);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 32));
-        if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(cand.col + (size_t)pb * cap) + lane * 32));
+        if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(cand.col + (size_t)pb * cap + pe)));
       }
       const char* pm = nullptr;
-      if (lane == 0) pm = reinterpret_cast<const char*>(cand_count + pb);
+      if (lane == 0) pm = reinterpret_cast<const char*>(cand_count + 2 * pb);
       else if (lane == 1) pm = reinterpret_cast<const char*>(cand_thresh + pb);
       else if (lane < 10 && !user_ids) pm = reinterpret_cast<const char*>(user_emb + (size_t)pb * kDim) + (lane - 2) * 32;
       if (pm) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm));
@@ -925,11 +962,14 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   // 1. keep the groups that may have ended above the final threshold (upper end of the interval the stored
   //    16 bits stand for), compacted: slot j = kept group j with the interval of its maximum
   int groups = 0;
-  for (int e0 = 0; e0 < n; e0 += 32) {
-    const int idx = e0 + lane;
+  // one sweep over both lists: entry e < n0 comes from list 0, the others from list 1
+  for (int e0 = 0; e0 < n0 + n1; e0 += 32) {
+    const int e = e0 + lane;
+    const int idx = e < n0 ? e : cap / 2 + (e - n0);
+    const bool have = e < n0 + n1;
     uint4 q = make_uint4(0u, 0u, 0u, 0u);
     uint32_t col0 = 0u;
-    if (idx < n) {
+    if (have) {
       q = __ldg(mine.q + idx);
       col0 = __ldg(mine.col + idx);
     }
@@ -938,7 +978,7 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       cand_bounds(cand_half(q, h), lo[h], hi[h]);
-      if (idx < n && hi[h] > thr) kmask |= 1u << h;
+      if (have && hi[h] > thr) kmask |= 1u << h;
     }
     // exclusive prefix sum of the per-lane counts
     const int mine_cnt = __popc(kmask);
@@ -1158,7 +1198,7 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   }
   if (lane == 0) {
     // bit 0: provably exact; bits 1.. say why not (list overflow, > 64 groups, < k contenders, > 128 survivors)
-    const int why = (raw > cap ? 2 : 0) | (too_many ? 4 : 0) | (total < k ? 8 : 0) | (sel_overflow ? 16 : 0);
+    const int why = (list_overflow ? 2 : 0) | (too_many ? 4 : 0) | (total < k ? 8 : 0) | (sel_overflow ? 16 : 0);
     certified[b] = why == 0 ? 1 : why;
   }
 }
@@ -1230,11 +1270,7 @@ namespace {
 constexpr int kSplitCap = 128;      // candidate entries (32-column chunks) per (sliced user, item slice)
 constexpr int kMinSliceTiles = 32;  // an item slice is at least this many item tiles
 
-// user tiles per CTA pass of the shape in use: HNM_FUSED_SHAPE=3 selects round 1's 3 x 1 shape
-int fused_mu() {
-  static const int mu = (getenv("HNM_FUSED_SHAPE") && atoi(getenv("HNM_FUSED_SHAPE")) == 3) ? 3 : 2;
-  return mu;
-}
+int fused_mu() { return kMU; }
 
 // The work distribution of one launch (see SplitPlan); pointers are filled in by the caller.
 SplitPlan make_plan(int num_user_tiles, int num_item_tiles, int grid) {
@@ -1266,7 +1302,7 @@ size_t split_bytes(const SplitPlan& sp, size_t* off_count, size_t* off_thresh) {
   if (sp.slices <= 1) { *off_count = *off_thresh = 0; return 0; }
   const size_t slots = (size_t)sp.triples * sp.mu * kUserTile * sp.slices;
   *off_count = slots * kSplitCap * (sizeof(uint4) + sizeof(uint32_t));
-  *off_thresh = *off_count + slots * sizeof(int32_t);
+  *off_thresh = *off_count + slots * kHalves * sizeof(int32_t);
   return *off_thresh + slots * sizeof(float);
 }
 }  // namespace
@@ -1302,7 +1338,7 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   if (num_users <= 0 || num_items <= 0 || users_padded < num_users || items_padded < num_items) return HNM_E_RANGE;
   if (users_padded % kUserTile != 0 || items_padded % kItemTile != 0) return HNM_E_RANGE;
   if (users_padded > INT32_MAX || items_padded > INT32_MAX) return HNM_E_RANGE;
-  if (kth_sel < 1 || kth_sel > kNumBuckets || cand_cap < 1 || cand_cap > 32 * kMaxPerLane) return HNM_E_RANGE;
+  if (kth_sel < 1 || kth_sel > kNumBuckets || cand_cap < 2 || cand_cap % 2 || cand_cap > 32 * kMaxPerLane) return HNM_E_RANGE;
   if ((reinterpret_cast<uintptr_t>(users_f16) & 127) || (reinterpret_cast<uintptr_t>(items_f16) & 127)) return HNM_E_ALIGN;
   int rc = hnm_check_device();
   if (rc != HNM_OK) return rc;
@@ -1327,21 +1363,12 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
     sp.count = reinterpret_cast<int32_t*>(ws + off_count);
     sp.thresh = reinterpret_cast<float*>(ws + off_thresh);
   }
-  if (sp.mu == 3) {
-    using S = Shape<3, 1>;
-    HNM_CUDA_TRY(hnm_allow_smem(score_topk_fused_kernel<S>, (int)smem_bytes<S>()));
-    score_topk_fused_kernel<S><<<grid, S::kThreads, smem_bytes<S>(), stream>>>(
-        map_u, map_i, (int)num_users, num_user_tiles, num_tiles, kth_sel, cand_list(cand, (size_t)num_users, cand_cap), cand_cap, cand_count,
-        cand_thresh, debug_mode, boot_tiles, refresh_div, wait_hint, sp);
-  } else {
-    using S = Shape<2, 2>;
-    HNM_CUDA_TRY(hnm_allow_smem(score_topk_fused_kernel<S>, (int)smem_bytes<S>()));
-    score_topk_fused_kernel<S><<<grid, S::kThreads, smem_bytes<S>(), stream>>>(
-        map_u, map_i, (int)num_users, num_user_tiles, num_tiles, kth_sel, cand_list(cand, (size_t)num_users, cand_cap), cand_cap, cand_count,
-        cand_thresh, debug_mode, boot_tiles, refresh_div, wait_hint, sp);
-  }
+  HNM_CUDA_TRY(hnm_allow_smem(score_topk_fused_kernel, (int)kSmemBytes));
+  score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(
+      map_u, map_i, (int)num_users, num_user_tiles, num_tiles, kth_sel, cand_list(cand, (size_t)num_users, cand_cap),
+      cand_cap, cand_count, cand_thresh, debug_mode, boot_tiles, refresh_div, wait_hint, sp);
   HNM_LAUNCH_CHECK();
-  if (need > 0 && debug_mode == 0) {
+  if (need > 0) {
     const int64_t split_users = std::min<int64_t>((int64_t)sp.triples * sp.mu * kUserTile,
                                                   num_users - (int64_t)sp.tile0 * kUserTile);
     if (split_users > 0) {
@@ -1366,7 +1393,7 @@ extern "C" int hnm_rescore_topk(const float* user_emb, const float* item_emb, co
     return HNM_E_NULL;
   if ((excl_ptr != nullptr) != (excl_items != nullptr)) return HNM_E_NULL;
   if (dim != kDim) return HNM_E_DIM;
-  if (batch < 0 || k < 1 || k > 32 || cand_cap < 1 || cand_cap > 32 * kMaxPerLane || num_items_local < 1 ||
+  if (batch < 0 || k < 1 || k > 32 || cand_cap < 2 || cand_cap % 2 || cand_cap > 32 * kMaxPerLane || num_items_local < 1 ||
       num_items_local > INT32_MAX)
     return HNM_E_RANGE;
   if (!hnm_aligned16(user_emb) || !hnm_aligned16(item_emb) || !hnm_aligned16(cand) || (center && !hnm_aligned16(center)))

@@ -190,7 +190,7 @@ class FusedScorer:
                      ptr(inv_scale), s)
                 user_base = self.user_emb
             cand = torch.empty(n * CAND_CAP * CAND_WORDS, dtype=torch.int32, device=dev)
-            count = torch.empty(n, dtype=torch.int32, device=dev)
+            count = torch.empty(n, 2, dtype=torch.int32, device=dev)     # one list per thread of the row
             thresh = torch.empty(n, dtype=torch.float32, device=dev)
             ws_bytes = int(_lib.load().hnm_score_topk_fused_workspace_bytes(padded, self.items_padded))
             if ws_bytes < 0:

@@ -169,13 +169,16 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
  *          the epilogue keeps, per user, every 32-column chunk that holds an approximate score above a
  *          running threshold tau (the kth_sel-th largest of 32 disjoint bucket maxima, a lower bound on
  *          the kth_sel-th best score).  The [users, items] score matrix never exists in memory.  Per user
- *          the kernel emits cand_count entries; `cand` is two arrays back to back,
+ *          the kernel emits its nominations into `cand`, two arrays back to back,
  *              uint32 q[num_users * cand_cap][4]   the chunk's 8 group maxima (groups of 4 adjacent items), each
  *                            cut to its upper 16 bits (bf16 truncated toward zero), group 2j in the low half of q[j]
  *              uint32 col[num_users * cand_cap]    LOCAL index of the chunk's first item
- *          i.e. HNM_FUSED_CAND_BYTES bytes per entry, the entries of user r at index r * cand_cap of both arrays
- *          (cand_count may exceed cand_cap: overflow, the user is then not certifiable) and the final tau:
- *          every item outside the stored chunks scored <= tau.
+ *          i.e. HNM_FUSED_CAND_BYTES bytes per entry.  User r owns entries [r * cand_cap, (r + 1) * cand_cap) of
+ *          both arrays, as TWO lists (a row is drained by two threads, one per 64-column half of an item tile):
+ *          list 0 starts at entry 0 and holds cand_count[2 r] entries, list 1 starts at cand_cap / 2 and holds
+ *          cand_count[2 r + 1]; a count above cand_cap / 2 means overflow (the user is then not certifiable).
+ *          When list 1 is empty list 0 may use the whole storage (the merged lists of sliced user tiles).
+ *          cand_thresh[r] is the final tau: every item outside the stored chunks scored <= tau.
  * Stage 3  hnm_rescore_topk: exact fp64 scores (k = 0..dim-1 fma chain) of the items of the groups that may
  *          have ended above tau, optional exclusion (lightgcn.py:349-353), canonical
  *          (score desc, id asc) top-k, and a per-user certificate
@@ -215,7 +218,7 @@ HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */,
                          const void* items_f16 /* [items_padded, 64] */, int64_t num_items, int64_t items_padded,
                          int32_t kth_sel /* 1..32 */,
                          void* cand /* num_users * cand_cap * HNM_FUSED_CAND_BYTES bytes, 16-byte aligned (layout above) */,
-                         int32_t cand_cap, int32_t* cand_count /* [num_users] */,
+                         int32_t cand_cap /* even */, int32_t* cand_count /* [num_users][2] */,
                          float* cand_thresh /* [num_users] final tau (scaled units) */,
                          void* workspace /* hnm_score_topk_fused_workspace_bytes(), may be NULL when that is 0 */,
                          int64_t workspace_bytes, void* stream);

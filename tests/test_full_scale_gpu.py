@@ -96,3 +96,59 @@ def test_recommend_all_properties_and_spot_check(hm_model):
     # single-user API path agrees with the all-users path
     some = uids[:257]
     assert torch.equal(m.recommend(some), ids[some])
+
+
+def test_hm_shape_forward_and_topk_match_oracle(hm_model):
+    """configs[1] against the oracle itself (not only invariants): the CPU restatement of set_graph +
+    forward() runs at the full H&M shape in a few seconds of host time (sort of 65 M triplets + 3 SpMMs).
+      P1  forward() embeddings, rtol 1e-5 (atol 1e-6 of the largest magnitude);
+      P2  fed with the ORACLE's embeddings, the fused scorer returns ids and fp64 scores bit-identical to
+          oracle.recommend_exact for 1 024 users;
+      P3  end to end (CUDA embeddings), recommend() equals the oracle's lists up to near-ties (1e-6 rel)."""
+    import oracle as O
+    from conftest import assert_close, assert_topk_matches_scores
+    from hnm_recommendation_b200 import synth
+    from hnm_recommendation_b200.scorer import FusedScorer
+    m = hm_model
+    U, I = m.num_users, m.num_items
+    data = synth.interactions(U, I, synth.HM_EDGES, seed=42)
+    w = m.embeddings.weight.detach().cpu()
+    rowptr, col, val, dis = O.build_norm_adj(data.edge_index(), None, U + I)
+    g = m.graph
+    assert torch.equal(g.rowptr.cpu().long(), rowptr) and torch.equal(g.col.cpu().long(), col)      # the CSR itself
+    assert torch.allclose(g.dis.cpu(), dis, rtol=2e-7, atol=0)
+    o_ue, o_ie = O.forward(w, rowptr, col, val, U, m.num_layers, O.layer_weights(m.num_layers))
+    ue, ie = m.forward()
+    assert_close(ue, o_ue, what="user embeddings at the H&M shape")                                 # P1
+    assert_close(ie, o_ie, what="item embeddings at the H&M shape")
+    uids = torch.randperm(U, generator=torch.Generator().manual_seed(7))[:1024]
+    want_ids, want_sc = O.recommend_exact(o_ue, o_ie, uids, 12)
+    sc = FusedScorer(o_ue.cuda(), o_ie.cuda())
+    ids, s = sc.topk(uids.cuda(), 12)
+    assert torch.equal(ids.cpu(), want_ids) and torch.equal(s.cpu(), want_sc)                        # P2
+    got = m.recommend(uids.cuda())                                                                  # P3
+    ref_scores = O.exact_scores_fp64(o_ue, o_ie, uids)
+    differ = assert_topk_matches_scores(got, ref_scores, 12)
+    assert differ <= 20, differ
+
+
+def test_validation_step_feeds_metrics_with_the_oracle_lists(hm_model):
+    """LightGCN.validation_step (src/models/lightgcn.py:267-284): recommend() for the batch's users, metrics
+    updated with the lists -- the same numbers as feeding the metrics with the brute-force lists."""
+    from hnm_recommendation_b200 import engine
+    from hnm_recommendation_b200.metrics import RecommendationMetrics
+    m = hm_model
+    uids = torch.arange(1000, 1000 + 777, device="cuda")
+    ue, ie = m.forward()
+    w_ids, _ = engine.topk_exact(ue, ie, uids, 12)
+    truth = [[int(w_ids[r, 0]), int(w_ids[r, 5]), (r * 31) % m.num_items] for r in range(uids.numel())]
+    m.metrics.reset()
+    out = m.validation_step({"user_ids": uids, "ground_truth": truth}, 0)
+    assert out is None
+    got = m.metrics.compute()
+    ref = RecommendationMetrics(top_k=12)
+    ref.update(w_ids.cpu(), truth)
+    want = ref.compute()
+    assert got == want and got["recall_at_k"] > 0.6
+    m.on_validation_epoch_end()                              # logs and resets (lightgcn.py:286-292)
+    assert m.metrics.compute()["map_at_k"] == 0.0

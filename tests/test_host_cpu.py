@@ -131,7 +131,7 @@ def test_fused_work_plan_covers_every_tile_pair_once(hnm_lib, user_tiles, item_t
             seen[t0:min(t0 + mu, user_tiles), i0:i1] += 1
     assert (seen == 1).all()
     ws = hnm_lib.hnm_score_topk_fused_workspace_bytes(user_tiles * 128, item_tiles * 128)
-    need = triples * mu * 128 * slices * (128 * 20 + 8) if slices > 1 else 0    # 128 entries of 20 B + count + tau
+    need = triples * mu * 128 * slices * (128 * 20 + 12) if slices > 1 else 0    # 128 entries of 20 B + 2 counts + tau
     assert ws >= need and ws <= need + 4096
     assert hnm_lib.hnm_score_topk_fused_workspace_bytes(100, 128) < 0
 

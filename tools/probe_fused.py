@@ -23,7 +23,7 @@ for margin in [int(x) for x in os.environ.get('PROBE_MARGINS', '2,3,4').split(',
         ids, s = sc.topk(None, 12)
         torch.cuda.synchronize(); dt = time.time() - t
     cnt, thr = sc._debug
-    print(f"margin {margin}: wall {dt*1e3:.1f} ms  stages {sc.stage_ms}  stats {sc.last_stats}  cand mean {float(cnt.float().mean()):.1f} max {int(cnt.max())}", flush=True)
+    print(f"margin {margin}: wall {dt*1e3:.1f} ms  stages {sc.stage_ms}  stats {sc.last_stats}  cand mean {float(cnt.float().sum(1).mean()):.1f} max half {int(cnt.max())}", flush=True)
     f = 2.0 * U * I * 64
     print(f"   fused TFLOP/s {f/sc.stage_ms['fused']/1e9:.1f}", flush=True)
 # spot check vs exact kernel

@@ -12,4 +12,4 @@ for rep in range(3):
     sc.topk(None, 12, fallback=False)
 cnt, thr = sc._debug
 print("mode", os.environ.get("HNM_FUSED_DEBUG", "0"), "users", U, "fused ms", round(sc.stage_ms["fused"], 2),
-      "TFLOP/s", round(2.0 * U * I * 64 / sc.stage_ms["fused"] / 1e9, 1), "cand mean", round(float(cnt.float().mean()), 1), flush=True)
+      "TFLOP/s", round(2.0 * U * I * 64 / sc.stage_ms["fused"] / 1e9, 1), "cand mean", round(float(cnt.float().sum(1).mean()), 1), flush=True)
