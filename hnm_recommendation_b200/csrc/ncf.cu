@@ -8,6 +8,7 @@
 // The tail weights sit in shared memory and are read as warp-wide broadcasts; see the two kernels
 // for the thread mapping.
 #include <algorithm>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -136,6 +137,205 @@ ncf_score_default_kernel(const float* __restrict__ gu, const float* __restrict__
   }
 }
 
+// ----------------------------------------------------------------------------- tensor-core fast path
+// Same default architecture, layer 2 ([pairs, 64] x [64, 32]) on the tensor cores with a 3xTF32 split
+//     h1 W2^T  ~=  hi(h1) hi(W2)^T + hi(h1) lo(W2)^T + lo(h1) hi(W2)^T        (error ~2^-21 per product,
+// inside the 1e-5 tolerance of P4; a plain TF32 product would be 2^-11), warp-level mma.sync m16n8k8.
+// A warp takes 32 pairs = two 16-row MMA tiles.  The MMA's A fragment gives the 4 lanes of a quad the same
+// two rows and lane c of the quad 2 of every 8 K-columns; since the contraction does not care about the
+// order of K, lane c is given the 16-byte chunks [16 v + 4 c, 16 v + 4 c + 4), v = 0..3, of its rows (so a
+// quad reads 64 contiguous bytes per request: full sectors) and K step j = 2 v + p pairs slot c with column
+// 16 v + 4 c + 2 p and slot c + 4 with the next one.  W2 is laid out to match, once per CTA, in shared memory
+// as {hi(b0), hi(b1), lo(b0), lo(b1)} per (K step, N tile, lane): one conflict-free LDS.128 per 3 MMAs.
+// h1 = relu(P[u] + Q[i]) never leaves registers (round 1 staged it through shared memory and ran layer 2 as
+// 2 048 FFMA per pair: 285 ms at configs[3], 3.4x the FMA floor).
+// CANDS = true (candidate / all-items form): a warp owns a contiguous range of 32-candidate tiles, so the
+// user's slices of P[u] and gw[u] = gu[u] * wp[:64] stay in registers for the ~31 tiles of a user;
+// CANDS = false (pair form): every row brings its own user.
+constexpr int kTcWarps = 8;
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool CANDS>
+__global__ void __launch_bounds__(kTcWarps * 32)
+ncf_score_tc_kernel(const float* __restrict__ gu, const float* __restrict__ gi, const float* __restrict__ pu,
+                    const float* __restrict__ qi, const float* __restrict__ tail, const float* __restrict__ wp,
+                    float bp, const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids,
+                    const int32_t* __restrict__ cand_items, int cand_per_user, int64_t num_rows, int64_t total,
+                    float* __restrict__ out) {
+  constexpr int MF = 64, H1 = 64, H2 = 32;
+  __shared__ __align__(16) float4 s_b[8][4][32];       // [K step][N tile][lane] = {hi b0, hi b1, lo b0, lo b1}
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  for (int t = threadIdx.x; t < 8 * 4 * 32; t += blockDim.x) {
+    const int l = t & 31, nt = (t >> 5) & 3, j = t >> 7;
+    const int v = j >> 1, p = j & 1, lc = l & 3, lg = l >> 2;
+    const int col = 16 * v + 4 * lc + 2 * p, n = 8 * nt + lg;
+    const float b0 = tail[n * H1 + col], b1 = tail[n * H1 + col + 1];
+    const uint32_t h0 = tf32_hi(b0), h1 = tf32_hi(b1);
+    s_b[j][nt][l] = make_float4(__uint_as_float(h0), __uint_as_float(h1), b0 - __uint_as_float(h0),
+                                b1 - __uint_as_float(h1));
+  }
+  __syncthreads();
+  // this lane's 8 output columns of layer 2 (N tile nt: columns 8 nt + 2 c, + 1): bias and prediction weights
+  float b2r[8], wpr[8];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      b2r[2 * nt + e] = tail[H2 * H1 + 8 * nt + 2 * c + e];
+      wpr[2 * nt + e] = wp[MF + 8 * nt + 2 * c + e];
+    }
+  }
+  float4 wg[4];                                         // wp[:64] on this lane's 16 GMF columns
+#pragma unroll
+  for (int v = 0; v < 4; ++v) wg[v] = ldg_f4(wp + 16 * v + 4 * c);
+
+  const int64_t warp_global = (int64_t)blockIdx.x * kTcWarps + (threadIdx.x >> 5);
+  const int64_t warp_count = (int64_t)gridDim.x * kTcWarps;
+  const int tiles_per_row = CANDS ? (cand_per_user + 31) / 32 : 1;
+  const int64_t num_tiles = CANDS ? num_rows * tiles_per_row : (total + 31) / 32;
+  // contiguous tile ranges: consecutive tiles of a warp belong to the same user
+  const int64_t t_begin = num_tiles * warp_global / warp_count, t_end = num_tiles * (warp_global + 1) / warp_count;
+  int64_t cur_row = -1;
+  float4 pr[4], gw[4];                                  // CANDS: this lane's slices of P[u] and gu[u] * wp
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    // ---- ids of the warp's 32 pairs (lane = pair), then of this lane's four rows g, g + 8, g + 16, g + 24
+    int64_t my_u = 0, my_i = 0, my_out = -1;
+    if (CANDS) {
+      const int64_t r = tile / tiles_per_row;
+      const int cpos = (int)(tile - r * tiles_per_row) * 32 + lane;
+      if (r != cur_row) {
+        cur_row = r;
+        const int64_t u = user_ids ? user_ids[r] : r;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          pr[v] = ldg_f4(pu + (size_t)u * H1 + 16 * v + 4 * c);
+          const float4 x = ldg_f4(gu + (size_t)u * MF + 16 * v + 4 * c);
+          gw[v] = make_float4(wg[v].x * x.x, wg[v].y * x.y, wg[v].z * x.z, wg[v].w * x.w);
+        }
+      }
+      if (cpos < cand_per_user) {
+        my_out = r * cand_per_user + cpos;
+        my_i = cand_items ? (int64_t)cand_items[my_out] : cpos;
+      }
+    } else {
+      const int64_t t = tile * 32 + lane;
+      if (t < total) { my_out = t; my_u = user_ids[t]; my_i = item_ids[t]; }
+    }
+    int64_t it[4], ut[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      it[r] = __shfl_sync(0xffffffffu, my_i, g + 8 * r);
+      if (!CANDS) ut[r] = __shfl_sync(0xffffffffu, my_u, g + 8 * r);
+    }
+    // ---- gather: 16 columns of Q[i] (and P[u]) per row -> h1 = relu(P + Q); 16 columns of the GMF product
+    float h1[4][16];
+    float gsum[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float4 qv[4], zv[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        qv[v] = ldg_f4(qi + (size_t)it[r] * H1 + 16 * v + 4 * c);
+        zv[v] = ldg_f4(gi + (size_t)it[r] * MF + 16 * v + 4 * c);
+      }
+      float gs = 0.f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float4 pv = CANDS ? pr[v] : ldg_f4(pu + (size_t)ut[r] * H1 + 16 * v + 4 * c);
+        float4 wv;
+        if (CANDS) {
+          wv = gw[v];
+        } else {
+          const float4 x = ldg_f4(gu + (size_t)ut[r] * MF + 16 * v + 4 * c);
+          wv = make_float4(wg[v].x * x.x, wg[v].y * x.y, wg[v].z * x.z, wg[v].w * x.w);
+        }
+        h1[r][4 * v + 0] = fmaxf(pv.x + qv[v].x, 0.f);
+        h1[r][4 * v + 1] = fmaxf(pv.y + qv[v].y, 0.f);
+        h1[r][4 * v + 2] = fmaxf(pv.z + qv[v].z, 0.f);
+        h1[r][4 * v + 3] = fmaxf(pv.w + qv[v].w, 0.f);
+        gs = fmaf(wv.x, zv[v].x, gs);
+        gs = fmaf(wv.y, zv[v].y, gs);
+        gs = fmaf(wv.z, zv[v].z, gs);
+        gs = fmaf(wv.w, zv[v].w, gs);
+      }
+      gsum[r] = gs;
+    }
+    // ---- layer 2 on the tensor cores: two M tiles (rows {g, g+8} and {g+16, g+24}) x four N tiles
+    float acc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k0 = 4 * (j >> 1) + 2 * (j & 1);        // index of slot c's column inside this lane's 16
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float a0 = h1[2 * mt][k0], a1 = h1[2 * mt + 1][k0], a2 = h1[2 * mt][k0 + 1], a3 = h1[2 * mt + 1][k0 + 1];
+        ah[mt][0] = tf32_hi(a0); ah[mt][1] = tf32_hi(a1); ah[mt][2] = tf32_hi(a2); ah[mt][3] = tf32_hi(a3);
+        al[mt][0] = __float_as_uint(a0 - __uint_as_float(ah[mt][0]));
+        al[mt][1] = __float_as_uint(a1 - __uint_as_float(ah[mt][1]));
+        al[mt][2] = __float_as_uint(a2 - __uint_as_float(ah[mt][2]));
+        al[mt][3] = __float_as_uint(a3 - __uint_as_float(ah[mt][3]));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float4 b = s_b[j][nt][lane];
+        const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
+        const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_tf32(acc[mt][nt], al[mt], bh0, bh1);      // small terms first
+          mma_tf32(acc[mt][nt], ah[mt], bl0, bl1);
+          mma_tf32(acc[mt][nt], ah[mt], bh0, bh1);
+        }
+      }
+    }
+    // ---- tail: relu(+ b2), prediction weights, sum over the 32 outputs (8 here, the rest across the quad)
+    float y[4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float s_lo = 0.f, s_hi = 0.f;                      // rows g + 16 mt and g + 16 mt + 8
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        s_lo = fmaf(wpr[2 * nt], fmaxf(acc[mt][nt][0] + b2r[2 * nt], 0.f), s_lo);
+        s_lo = fmaf(wpr[2 * nt + 1], fmaxf(acc[mt][nt][1] + b2r[2 * nt + 1], 0.f), s_lo);
+        s_hi = fmaf(wpr[2 * nt], fmaxf(acc[mt][nt][2] + b2r[2 * nt], 0.f), s_hi);
+        s_hi = fmaf(wpr[2 * nt + 1], fmaxf(acc[mt][nt][3] + b2r[2 * nt + 1], 0.f), s_hi);
+      }
+      y[2 * mt] = s_lo + gsum[2 * mt];
+      y[2 * mt + 1] = s_hi + gsum[2 * mt + 1];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      y[r] += __shfl_xor_sync(0xffffffffu, y[r], 1);
+      y[r] += __shfl_xor_sync(0xffffffffu, y[r], 2);
+    }
+    // row g + 8 r lives in every lane of quad g; hand it to lane (g + 8 r) so that the store is coalesced
+    float mine = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float v = __shfl_sync(0xffffffffu, y[r], 4 * (lane & 7));
+      if ((lane >> 3) == r) mine = v;
+    }
+    if (my_out >= 0) out[my_out] = mine + bp;
+  }
+}
+
 // Any depth / width up to kMaxWidth: activations ping-pong through local memory.
 __global__ void __launch_bounds__(128)
 ncf_score_generic_kernel(const float* __restrict__ gu, const float* __restrict__ gi, const float* __restrict__ pu,
@@ -209,15 +409,23 @@ int launch_score(const float* gu, const float* gi, const float* pu, const float*
   if (mf < 1 || total < 0) return HNM_E_RANGE;
   const bool is_default = num_layers == 2 && mf == 64 && d.width[0] == 64 && d.width[1] == 32 &&
                           hnm_aligned16(gu) && hnm_aligned16(gi) && hnm_aligned16(pu) && hnm_aligned16(qi);
-  if (is_default) {
+  static const bool simt = getenv("HNM_NCF_SIMT") != nullptr;          // A/B switch: round 1's FFMA kernel
+  if (is_default && !simt && hnm_aligned16(wp)) {
+    const int T = kTcWarps * 32;
+    const int64_t rows = cand_per_user > 0 ? total / cand_per_user : 0;
+    const int64_t tiles = cand_per_user > 0 ? rows * ((cand_per_user + 31) / 32) : (total + 31) / 32;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + kTcWarps - 1) / kTcWarps,
+                                                                           (int64_t)hnm_num_sms() * 2));
+    if (cand_per_user > 0)
+      ncf_score_tc_kernel<true><<<grid, T, 0, stream>>>(gu, gi, pu, qi, tail, wp, bp, user_ids, item_ids, cand_items,
+                                                        cand_per_user, rows, total, out);
+    else
+      ncf_score_tc_kernel<false><<<grid, T, 0, stream>>>(gu, gi, pu, qi, tail, wp, bp, user_ids, item_ids, cand_items,
+                                                         0, 0, total, out);
+  } else if (is_default) {
     const int T = kNcfWarps * 32;
     const size_t smem = sizeof(float) * (64 * 32 + 32 + 64 + 32 + kNcfWarps * (32 * kNcfStride + 32));
-    static bool attr_default = false;
-    if (!attr_default) {
-      HNM_CUDA_TRY(cudaFuncSetAttribute(ncf_score_default_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-      attr_default = true;
-    }
+    HNM_CUDA_TRY(hnm_allow_smem(ncf_score_default_kernel, (int)smem));
     const unsigned grid = (unsigned)std::min<int64_t>((total + T - 1) / T, (int64_t)hnm_num_sms() * 6);
     ncf_score_default_kernel<<<grid, T, smem, stream>>>(gu, gi, pu, qi, tail, wp, bp, user_ids, item_ids, cand_items,
                                                        cand_per_user, total, out);

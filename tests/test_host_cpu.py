@@ -253,3 +253,26 @@ def test_header_is_c99_and_library_links_from_c(hnm_lib, tmp_path):
     run = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert run.returncode == 0, (run.returncode, run.stderr)
     assert run.stdout.strip().startswith("ok|")
+
+
+def test_interaction_data_contract_roundtrip(tmp_path):
+    """data.InteractionData: processed/train.parquet (customer_idx, article_idx; scripts/serve.py:174-177) ->
+    get_graph() in the layout set_graph takes (scripts/train.py:221), the serving filter dict and its CSR form."""
+    from hnm_recommendation_b200 import synth
+    from hnm_recommendation_b200.data import InteractionData
+    d = InteractionData.synthetic(300, 120, 2500, seed=3)
+    path = d.to_parquet(str(tmp_path))
+    assert path.endswith(os.path.join("processed", "train.parquet"))
+    back = InteractionData.from_parquet(str(tmp_path), num_users=300, num_items=120)
+    ei, ew = back.get_graph()
+    assert ew is None and torch.equal(ei, synth.interactions(300, 120, 2500, seed=3).edge_index())
+    assert ei.dtype == torch.int64 and int(ei[0, :2500].max()) < 300 and int(ei[1, :2500].min()) >= 300
+    hist = back.user_history()
+    assert set(hist) == set(range(300))                                   # every synthetic user buys at least once
+    ptr, items = back.history_csr()
+    assert ptr.numel() == 301 and int(ptr[-1]) == items.numel() == sum(len(v) for v in hist.values())
+    for u in (0, 17, 299):
+        row = items[int(ptr[u]):int(ptr[u + 1])].tolist()
+        assert row == sorted(hist[u])
+    with pytest.raises(ValueError):
+        InteractionData.from_arrays([0, 5], [1, 2], num_users=3)
