@@ -46,6 +46,7 @@ _SIGNATURES = {
     "hnm_score_topk_fused_plan": (C.c_int, [I64, I64, P]),
     "hnm_rescore_topk": (C.c_int, [P, P, P, I64, I32, I64, I64, P, I32, P, P, P, P, P, P, P, I32, P, P, P, P]),
     "hnm_merge_topk": (C.c_int, [P, P, I32, I64, I32, P, P, P]),
+    "hnm_topk_dense": (C.c_int, [P, I64, I64, P, P, I32, P, P, P]),
     "hnm_ncf_precompute": (C.c_int, [P, I64, I32, P, I32, I32, I32, P, P, P]),
     "hnm_ncf_score_pairs": (C.c_int, [P, P, P, P, P, P, I32, P, F32, P, P, I64, I32, P, P]),
     "hnm_ncf_score_candidates": (C.c_int, [P, P, P, P, P, P, I32, P, F32, P, I64, P, I32, I32, P, P]),

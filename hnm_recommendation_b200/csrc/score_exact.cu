@@ -237,6 +237,49 @@ topk_exact_kernel(const float* __restrict__ ue, const float* __restrict__ ie, co
   }
 }
 
+// ------------------------------------------------------------------ top-k of materialised score rows
+// NeuralCF.recommend (src/models/neural_cf.py:300-326): the logits of a pair are an MLP, not a dot product,
+// so the [batch, items] fp32 matrix exists (predict_all_items); this kernel is the `scores[i, filter] = -inf`
+// + `torch.topk` tail with the canonical (score desc, id asc) order.  One CTA per row, the same candidate
+// buffer + block-wide bitonic compaction as the exact kernel above.
+__global__ void __launch_bounds__(XT)
+topk_dense_kernel(const float* __restrict__ scores, int64_t num_items, const int64_t* __restrict__ excl_ptr,
+                  const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
+                  float* __restrict__ out_scores) {
+  __shared__ Cand cands[XCAP];
+  __shared__ int count;
+  __shared__ double thr_s;
+  __shared__ int64_t thr_id;
+  const int64_t b = blockIdx.x;
+  const float* row = scores + (size_t)b * num_items;
+  int64_t ex_lo = 0, ex_hi = 0;
+  if (excl_ptr) { ex_lo = excl_ptr[b]; ex_hi = excl_ptr[b + 1]; }
+  if (threadIdx.x == 0) { count = 0; thr_s = -INFINITY; thr_id = INT64_MAX; }
+  __syncthreads();
+  for (int64_t base = 0; base < num_items; base += XT) {
+    const int64_t j = base + threadIdx.x;
+    if (j < num_items) {
+      double s = (double)__ldg(row + j);
+      if (s != s) s = -INFINITY;                                  // NaN logits rank last (torch.topk ranks them first)
+      if (ex_lo < ex_hi && excluded(excl_items, ex_lo, ex_hi, j)) s = -INFINITY;
+      if (hnm_before(s, j, thr_s, thr_id)) cands[atomicAdd(&count, 1)] = Cand{s, j};
+    }
+    __syncthreads();
+    if (count > XCAP - XT) {                                      // block-uniform
+      for (int t = count + threadIdx.x; t < XCAP; t += XT) cands[t] = Cand{-INFINITY, INT64_MAX};
+      sort_cands(cands);
+      if (threadIdx.x == 0) { count = k; thr_s = cands[k - 1].s; thr_id = cands[k - 1].id; }
+      __syncthreads();
+    }
+  }
+  for (int t = count + threadIdx.x; t < XCAP; t += XT) cands[t] = Cand{-INFINITY, INT64_MAX};
+  sort_cands(cands);
+  for (int t = threadIdx.x; t < k; t += XT) {
+    out_ids[(size_t)b * k + t] = cands[t].id;
+    if (out_scores) out_scores[(size_t)b * k + t] = (float)cands[t].s;
+  }
+}
+
 // ------------------------------------------------------------------ merge of sorted per-shard lists
 __global__ void merge_topk_kernel(const int64_t* __restrict__ in_ids, const double* __restrict__ in_s, int shards,
                                   int64_t batch, int k, int64_t* __restrict__ out_ids,
@@ -332,6 +375,19 @@ extern "C" int hnm_merge_topk(const int64_t* in_ids, const double* in_scores, in
   if (num_shards <= 0 || num_shards > 16 || batch < 0 || k <= 0) return HNM_E_RANGE;
   merge_topk_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(in_ids, in_scores, num_shards, batch, k,
                                                                        out_ids, out_scores);
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
+}
+
+extern "C" int hnm_topk_dense(const float* scores, int64_t batch, int64_t num_items, const int64_t* excl_ptr,
+                              const int64_t* excl_items, int32_t k, int64_t* out_ids, float* out_scores,
+                              void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (batch == 0) return HNM_OK;
+  if (!scores || !out_ids) return HNM_E_NULL;
+  if ((excl_ptr != nullptr) != (excl_items != nullptr)) return HNM_E_NULL;
+  if (batch < 0 || batch > INT32_MAX || num_items < 1 || k < 1 || k > XKMAX || k > num_items) return HNM_E_RANGE;
+  topk_dense_kernel<<<(unsigned)batch, XT, 0, stream>>>(scores, num_items, excl_ptr, excl_items, k, out_ids, out_scores);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }

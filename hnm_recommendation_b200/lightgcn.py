@@ -12,12 +12,17 @@ Differences from the reference, all deliberate:
     ``torch.topk`` order is unspecified; BASELINE.json fixes this rule);
   * ``recommend`` ranks by the exact (fp64-accumulated) dot products of the fp32
     embeddings, i.e. the ordering the reference's fp32 sgemm approximates;
-  * ``forward()`` is cached until the weights or the graph change
-    (the reference recomputes it on every call, SURVEY.md F7) -- results are identical;
-  * ``forward()`` returns detached, cached tensors; the differentiable form is
-    ``forward_with_grad()`` (what ``bpr_loss`` / ``training_step`` use, lightgcn.py:206-265):
+  * in eval mode ``forward()`` is cached until the weights or the graph change
+    (the reference recomputes it on every call) -- results are identical.  The cache key is
+    the parameter's storage and version counter: a write through ``.data`` bumps neither, so call
+    ``invalidate()`` after one (``load_state_dict`` and ``.to()`` / ``.cuda()`` do it themselves), or set
+    ``cache_embeddings = "verify"`` to have every hit confirmed by a device-side checksum of the table.
+    In train mode nothing is cached;
+  * in train mode, when autograd is recording and the table requires grad, ``forward()`` IS ``forward_with_grad()``
+    (differentiable as in the reference; what ``bpr_loss`` / ``training_step`` use, lightgcn.py:206-265):
     its backward pass is the same propagate kernels on the transposed adjacency,
-    ``dL/dE0 = sum_l alpha_l (A_hat^T)^l dL/dfinal``;
+    ``dL/dE0 = sum_l alpha_l (A_hat^T)^l dL/dfinal``, and ``predict`` / ``predict_all_items`` then score with
+    plain differentiable torch ops; under ``no_grad`` or in eval mode the kernels and the cached buffer serve;
   * ``recommend(user_ids, filter_items=None, k=None)`` accepts ``k`` (README.md:131).
 """
 from __future__ import annotations
@@ -96,7 +101,9 @@ class LightGCN(ModelBase):
         self._graph_t = None
         self._cache_key = None
         self._cache_val: Optional[torch.Tensor] = None
+        self._cache_sum = None
         self._scorer = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # ------------------------------------------------------------------ graph
     def set_graph(self, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor] = None) -> None:
@@ -126,6 +133,18 @@ class LightGCN(ModelBase):
         return self._graph_t
 
     # ---------------------------------------------------------------- forward
+    def invalidate(self) -> None:
+        """Drop the cached propagated embeddings and the packed scorer tables.  Needed after a write to the
+        parameters that autograd's version counter does not see (``weight.data.copy_(...)``)."""
+        self._cache_key = None
+        self._cache_val = None
+        self._cache_sum = None
+        self._scorer = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
     def _final_embeddings(self) -> torch.Tensor:
         if self.graph is None:
             raise RuntimeError("Graph not set. Call set_graph() first.")
@@ -133,18 +152,29 @@ class LightGCN(ModelBase):
         if self.graph.rowptr.device != w.device:
             raise RuntimeError("graph and parameters are on different devices; call set_graph() after .to(device)")
         key = (w.data_ptr(), w._version, id(self.graph), tuple(self.alpha), self.num_layers)
-        if self.cache_embeddings and self._cache_key == key and self._cache_val is not None:
-            return self._cache_val
+        use_cache = bool(self.cache_embeddings) and not self.training
+        if use_cache and self._cache_key == key and self._cache_val is not None:
+            if self.cache_embeddings != "verify" or float(w.detach().sum(dtype=torch.float64)) == self._cache_sum:
+                return self._cache_val
         final = engine.propagate(self.graph, w, self.alpha, self.num_layers,
                                  item_chunks=getattr(self, "_item_chunks", None))
-        self._cache_key, self._cache_val = key, final
+        self._cache_key, self._cache_val = (key, final) if use_cache else (None, None)
+        self._cache_sum = float(w.detach().sum(dtype=torch.float64)) if self.cache_embeddings == "verify" else None
         self._scorer = None
         return final
 
     def forward(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """lightgcn.py:136-164: (user_embeddings [U,d], item_embeddings [I,d]), views of one buffer."""
+        if self._wants_grad():
+            return self.forward_with_grad()
         final = self._final_embeddings()
         return final[: self.num_users], final[self.num_users:]
+
+    def _wants_grad(self) -> bool:
+        """Train mode with autograd recording: the reference's differentiable behaviour.  Under ``no_grad`` or in
+        eval mode the (cached, detached) kernel results are returned."""
+        return (self.training and torch.is_grad_enabled() and self.embeddings.weight.requires_grad
+                and self.graph is not None)
 
     def forward_with_grad(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """The reference's forward() as it behaves under autograd (lightgcn.py:136-164): gradients flow to
@@ -185,11 +215,15 @@ class LightGCN(ModelBase):
     def predict(self, user_ids: torch.Tensor, item_ids: torch.Tensor) -> torch.Tensor:
         """lightgcn.py:166-186."""
         ue, ie = self.forward()
+        if self._wants_grad():
+            return (ue[user_ids.to(ue.device)] * ie[item_ids.to(ue.device)]).sum(dim=1)      # lightgcn.py:180-184
         return engine.pair_scores(ue, ie, user_ids, item_ids)
 
     def predict_all_items(self, user_ids: torch.Tensor) -> torch.Tensor:
         """lightgcn.py:188-204: [batch, num_items] fp32 scores."""
         ue, ie = self.forward()
+        if self._wants_grad():
+            return torch.matmul(ue[user_ids.to(ue.device)], ie.t())                           # lightgcn.py:199-202
         return engine.score_all_items(ue, ie, user_ids)
 
     # -------------------------------------------------------------- recommend

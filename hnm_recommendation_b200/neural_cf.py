@@ -5,7 +5,14 @@ path: same constructor, sub-module names / ``state_dict`` keys, ``forward(user_i
 item_ids)`` -> logits, ``predict_all_items``, ``recommend``.  Scoring always uses
 eval-mode semantics (Dropout = identity); the reference applies dropout when the
 caller forgot ``model.eval()``, which no serving caller wants.
-Inference only: no autograd through the kernels.
+
+Training (neural_cf.py:210-233, 274-298): in train mode, when autograd is recording and a
+parameter requires grad, ``forward`` takes the reference's own formulation over the same
+parameters (embedding lookups + ``mlp_layers`` + ``prediction_layer``, dropout live
+in train mode), so ``training_step`` / ``configure_optimizers`` / ``trainer.fit`` work
+on the mirror; the fused kernels serve ``no_grad`` / eval scoring.  The layer-1 tables
+are rebuilt whenever a parameter's version changes; a write through ``.data`` does not
+bump it -- call ``invalidate()`` after one (``load_state_dict`` and ``.to()`` do).
 """
 from __future__ import annotations
 
@@ -55,6 +62,16 @@ class NeuralCF(ModelBase):
         self.metrics = RecommendationMetrics(top_k=top_k)
         self._tables_key = None
         self._tables = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self) -> None:
+        """Drop the cached layer-1 tables (needed after writing parameters through ``.data``)."""
+        self._tables_key = None
+        self._tables = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate()
+        return super()._apply(fn, *args, **kwargs)
 
     def _build_mlp(self, dims: List[int], dropout: float) -> nn.Sequential:
         layers = []                                                           # :85-90
@@ -123,8 +140,19 @@ class NeuralCF(ModelBase):
         return self._tables
 
     # -------------------------------------------------------------- scoring
+    def _forward_autograd(self, user_ids: torch.Tensor, item_ids: torch.Tensor) -> torch.Tensor:
+        """neural_cf.py:125-139 as written (differentiable; dropout live in train mode)."""
+        dev = self.gmf_user_embedding.weight.device
+        user_ids, item_ids = user_ids.to(dev), item_ids.to(dev)
+        gmf_output = self.gmf_user_embedding(user_ids) * self.gmf_item_embedding(item_ids)
+        mlp_input = torch.cat([self.mlp_user_embedding(user_ids), self.mlp_item_embedding(item_ids)], dim=1)
+        mlp_output = self.mlp_layers(mlp_input)
+        return self.prediction_layer(torch.cat([gmf_output, mlp_output], dim=1)).squeeze()
+
     def forward(self, user_ids: torch.Tensor, item_ids: torch.Tensor) -> torch.Tensor:
         """neural_cf.py:112-141: logits [batch] (0-dim for a single pair, as ``.squeeze()`` yields)."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_autograd(user_ids, item_ids)
         t = self._prepared()
         dev = t["gu"].device
         u = engine._norm_ids(user_ids, self.num_users, dev)
@@ -178,12 +206,37 @@ class NeuralCF(ModelBase):
         if k > self.num_items or k <= 0:
             raise RuntimeError("selected index k out of range")
         with torch.no_grad():
-            scores = self.predict_all_items(user_ids)
-            if filter_items is not None:
-                for i, user_id in enumerate(user_ids.tolist()):
-                    if user_id in filter_items:
-                        scores[i, list(filter_items[user_id])] = float("-inf")
-            return torch.sort(scores, dim=1, descending=True, stable=True).indices[:, :k].contiguous()
+            scores = self.predict_all_items(user_ids)                     # [B, I] fp32 logits (the kernels above)
+            dev = scores.device
+            uids = user_ids.to(dev).view(-1)
+            if k > engine.EXACT_K_MAX:
+                if filter_items is not None:
+                    for i, user_id in enumerate(uids.tolist()):
+                        if user_id in filter_items:
+                            scores[i, list(filter_items[user_id])] = float("-inf")
+                return torch.sort(scores, dim=1, descending=True, stable=True).indices[:, :k].contiguous()
+            # filter + top-k in one select kernel (neural_cf.py:316-325), ties by item id ascending
+            excl = engine.exclusion_csr(uids, filter_items, dev)
+            ids = torch.empty(scores.size(0), k, dtype=torch.int64, device=dev)
+            with torch.cuda.device(dev):
+                call("hnm_topk_dense", ptr(scores), scores.size(0), scores.size(1), ptr(excl[0]), ptr(excl[1]), k,
+                     ptr(ids), None, stream())
+            return ids
+
+    def training_step(self, batch: Dict[str, Any], batch_idx: int) -> torch.Tensor:
+        """neural_cf.py:210-233: binary cross entropy with logits on (user, item, label) triples."""
+        predictions = self(batch["user_ids"], batch["item_ids"])
+        labels = batch["labels"].float().to(predictions.device)
+        loss = nn.functional.binary_cross_entropy_with_logits(predictions, labels)
+        self.log("train_loss", loss, prog_bar=True)
+        return loss
+
+    def configure_optimizers(self):
+        """neural_cf.py:274-298 (Adam with weight decay, ReduceLROnPlateau on val_map_at_k)."""
+        optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate, weight_decay=self.weight_decay)
+        scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode="max", factor=0.5, patience=5)
+        return {"optimizer": optimizer,
+                "lr_scheduler": {"scheduler": scheduler, "monitor": "val_map_at_k", "frequency": 1}}
 
     def validation_step(self, batch: Dict[str, Any], batch_idx: int):
         top_k_items = self.recommend(batch["user_ids"])

@@ -281,6 +281,17 @@ HNM_API int hnm_ncf_score_candidates(const float* gmf_user, const float* gmf_ite
                              const int32_t* cand_items, int32_t cand_per_user, int32_t mf_dim,
                              float* out /* [num_rows, cand_per_user] */, void* stream);
 
+/* ------------------------------------------------------------------------
+ * NeuralCF.recommend tail                          src/models/neural_cf.py:316-325
+ * Top-k of each row of a materialised fp32 score matrix [batch, num_items] (predict_all_items), after
+ * `scores[row, excluded] = -inf`, ordered by (score desc, item id asc); replaces the Python filter loop
+ * + torch.topk.  excl_ptr/excl_items: CSR over the rows, item ids sorted per row (NULL = no filter).
+ * out_scores may be NULL.  k <= 256.
+ * ---------------------------------------------------------------------- */
+HNM_API int hnm_topk_dense(const float* scores, int64_t batch, int64_t num_items, const int64_t* excl_ptr,
+                   const int64_t* excl_items, int32_t k, int64_t* out_ids /* [batch, k] */,
+                   float* out_scores /* [batch, k] or NULL */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
