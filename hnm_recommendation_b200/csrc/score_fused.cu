@@ -66,8 +66,8 @@ constexpr int kStagesB = 6;
 constexpr int kEpiWarps = 4 * kMU * kHalves;      // 16
 constexpr int kThreads = (4 + kEpiWarps) * 32;    // 640
 constexpr int kHalfBuckets = kNumBuckets / kHalves;
-constexpr int kCtlRegs = 32, kEpiRegs = 112;      // setmaxnreg: the CTA is launched with 96 registers x 640 threads = 61 440, and
-                                                  // 128 * 32 + 512 * 112 must not exceed THAT (not 64 K): a warpgroup whose
+constexpr int kCtlRegs = 64, kEpiRegs = 104;      // setmaxnreg: the CTA is launched with 96 registers x 640 threads = 61 440, and
+                                                  // 128 * 64 + 512 * 104 must not exceed THAT (not 64 K): a warpgroup whose
                                                   // setmaxnreg.inc cannot be served waits forever
 static_assert(128 * kCtlRegs + 512 * kEpiRegs <= 96 * kThreads, "register pool");
 
@@ -80,12 +80,14 @@ struct __align__(8) Barriers {
   uint64_t t_full[kSlots], t_empty[kSlots];
   uint32_t tmem_base;
 };
-// bucket exchange between the two threads of a row: [user tile][quarter][bucket][lane] + the agreed tau
-struct PairXchg {
-  float bm[kMU][4][kHalfBuckets][32];
+// The 32 bucket maxima of a user row live in shared memory, 16 per thread of the row: they are touched only
+// when a chunk beats tau (and by the threshold refresh), and in registers they cost the epilogue the room
+// it needs to keep its list pointers out of the constant bank.  [user tile][quarter][half][bucket][lane]
+struct PairBuckets {
+  float bm[kMU][4][kHalves][kHalfBuckets][32];
   float tau[kMU][4][32];
 };
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + 2 * kMU * kTileBytes + kStagesB * kTileBytes + sizeof(PairXchg) +
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + 2 * kMU * kTileBytes + kStagesB * kTileBytes + sizeof(PairBuckets) +
                               sizeof(Barriers);
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -212,8 +214,22 @@ __device__ __forceinline__ void tmem_ld_wait(float (&a)[32], float (&b)[32]) {
 struct RowState {
   float tau;                  // collect threshold (+inf while seeding), common to both threads of the row
   int cnt;                    // chunks this thread appended so far (may exceed its capacity: overflow)
-  float bm[kHalfBuckets];     // bucket maxima; bucket = position of the 4-column group inside the item tile
+  uint32_t bm;                // shared-memory address of this thread's 16 bucket maxima: bucket b at bm + 128 b
 };
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+// bucket <- max(bucket, q) for the 8 groups of chunk `chunk` (all loads first: one shared-memory round trip)
+__device__ __forceinline__ void bucket_update(uint32_t bm, int chunk, const float (&q)[8]) {
+  float b[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) b[h] = lds_f32(bm + (chunk * 8 + h) * 128);
+#pragma unroll
+  for (int h = 0; h < 8; ++h) sts_f32(bm + (chunk * 8 + h) * 128, fmaxf(b[h], q[h]));
+}
 
 __device__ __forceinline__ void cmpx(float& a, float& b) {   // a <- max, b <- min
   const float hi = fmaxf(a, b), lo = fminf(a, b);
@@ -245,29 +261,23 @@ __device__ __forceinline__ float kth_largest32(float (&t)[kNumBuckets], int kth)
 
 __device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-// tau = the kth largest of the row's 32 bucket maxima.  The buckets hold disjoint item sets, so tau is a
-// lower bound on the kth best score seen.  Thread h = 1 of the row hands its 16 maxima to thread h = 0
-// through shared memory, h = 0 sorts a copy of all 32 and hands tau back; the two warps meet at a 64-thread
-// named barrier (the schedule of refreshes is the same function of the pass for both).  The bucket
-// registers themselves are never permuted, so revisiting an item (the seed tiles are swept twice) is
+// tau = the kth largest of the row's 32 bucket maxima (bucket = position of a 4-column group inside an item
+// tile).  The buckets hold disjoint item sets, so tau is a lower bound on the kth best score seen.  The
+// two warps of a row meet at a 64-thread named barrier (the schedule of refreshes is the same function of
+// the pass for both); thread h = 0 sorts a register copy of all 32 and hands tau back through shared memory.
+// The buckets themselves are never permuted, so revisiting an item (the seed tiles are swept twice) is
 // idempotent.
-__device__ __forceinline__ float refresh_tau(const RowState& st, int h, float* xb /* [16][32] */, float* xt /* [32] */,
-                                             int bar_id, int kth, int lane) {
-  if (h == 1) {
+__device__ __forceinline__ float refresh_tau(uint32_t row_bm /* smem: [2][16][32] of this (tile, quarter), + lane */,
+                                             int h, uint32_t xt /* smem: tau slot of this lane */, int bar_id, int kth) {
+  pair_bar(bar_id);                                   // both threads' bucket updates are visible
+  if (h == 0) {
+    float t[kNumBuckets];
 #pragma unroll
-    for (int i = 0; i < kHalfBuckets; ++i) xb[i * 32 + lane] = st.bm[i];
-    pair_bar(bar_id);
-    pair_bar(bar_id);
-    return xt[lane];
+    for (int i = 0; i < kNumBuckets; ++i) t[i] = lds_f32(row_bm + i * 128);
+    sts_f32(xt, kth_largest32(t, kth));
   }
   pair_bar(bar_id);
-  float t[kNumBuckets];
-#pragma unroll
-  for (int i = 0; i < kHalfBuckets; ++i) { t[i] = st.bm[i]; t[kHalfBuckets + i] = xb[i * 32 + lane]; }
-  const float tau = kth_largest32(t, kth);
-  xt[lane] = tau;
-  pair_bar(bar_id);
-  return tau;
+  return lds_f32(xt);
 }
 
 // One nominated 32-column chunk of one user row: the chunk's eight group maxima (groups of 4 adjacent
@@ -320,16 +330,15 @@ enum { kSeed = 0, kCollect = 1 };
 // kSeed: first visit of the seed tiles -- buckets only (tau is +inf).  kCollect: everything else.
 template <int MODE>
 __device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col0, RowState& st,
-                                         const CandList cand, int cap) {
+                                         const CandList cand, int cap, int xp = 0) {
   if (MODE == kSeed) {
-#pragma unroll
-    for (int h = 0; h < 8; ++h) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
+    bucket_update(st.bm, chunk, q);
     return;
   }
   const float m32 = fmaxf(fmaxf(fmaxf(fmaxf(q[0], q[1]), q[2]), fmaxf(fmaxf(q[3], q[4]), q[5])), fmaxf(q[6], q[7]));
   if (m32 > st.tau) {
-#pragma unroll
-    for (int h = 0; h < 8; ++h) st.bm[chunk * 8 + h] = fmaxf(st.bm[chunk * 8 + h], q[h]);
+    if (!(xp & 16)) bucket_update(st.bm, chunk, q);
+    if (xp & 8) { ++st.cnt; return; }    // experiment: count, do not store
     if (st.cnt >= cap) {                 // no room: stop collecting, flag the row
       st.tau = INFINITY;
       st.cnt = cap + 1;
@@ -350,7 +359,7 @@ __device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col
 // accumulator goes back to its MMA issuer as soon as they have landed (the 8 warps of the user tile arrive).
 template <int MODE>
 __device__ __forceinline__ void drain_half(uint32_t taddr, int col0, RowState& st, const CandList cand, int cap,
-                                           uint64_t* t_empty, int lane) {
+                                           uint64_t* t_empty, int lane, int xp = 0) {
   float va[32], vb[32], q[8];
   tmem_ld32(taddr, va);
   tmem_ld32(taddr + 32, vb);
@@ -359,9 +368,9 @@ __device__ __forceinline__ void drain_half(uint32_t taddr, int col0, RowState& s
   __syncwarp();
   if (lane == 0) mbar_arrive(t_empty);
   group_max(va, q);
-  finish32<MODE>(q, 0, col0, st, cand, cap);
+  finish32<MODE>(q, 0, col0, st, cand, cap, xp);
   group_max(vb, q);
-  finish32<MODE>(q, 1, col0 + 32, st, cand, cap);
+  finish32<MODE>(q, 1, col0 + 32, st, cand, cap, xp);
 }
 
 // ----------------------------------------------------------------------------- work distribution
@@ -450,8 +459,8 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                   // [2][kMU][kTileBytes]
   uint8_t* smem_b = smem + 2 * kMU * kTileBytes;            // [kStagesB][kTileBytes]
-  PairXchg* xchg = reinterpret_cast<PairXchg*>(smem_b + kStagesB * kTileBytes);
-  Barriers* bars = reinterpret_cast<Barriers*>(xchg + 1);
+  PairBuckets* buckets = reinterpret_cast<PairBuckets*>(smem_b + kStagesB * kTileBytes);
+  Barriers* bars = reinterpret_cast<Barriers*>(buckets + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -551,8 +560,8 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
     const int h = (e >> 2) & 1;                    // column half
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + h * (kItemTile / kHalves);
-    float* xb = &xchg->bm[m][q][0][0];
-    float* xt = &xchg->tau[m][q][0];
+    const uint32_t row_bm = smem_u32(&buckets->bm[m][q][0][0][lane]);     // both threads' buckets: 32 x stride 128 B
+    const uint32_t xt = smem_u32(&buckets->tau[m][q][lane]);
     const int bar_id = 1 + m * 4 + q;              // barrier 0 is __syncthreads
     uint32_t uses = 0;
     for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
@@ -564,15 +573,19 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       const bool real = (p.t0 + m) * kUserTile + q * 32 + lane < num_users;
       const int out_cap = p.slice < 0 ? cap : sp.cap;
       const int half_cap = out_cap / kHalves;
-      const CandList my_cand = (p.slice < 0 ? cand : sp.cand).at((size_t)(real ? slot : 0) * out_cap + h * half_cap);
+      CandList my_cand = (p.slice < 0 ? cand : sp.cand).at((size_t)(real ? slot : 0) * out_cap + h * half_cap);
+      // opaque to the compiler, so that it keeps the two pointers in registers instead of re-deriving them from
+      // the kernel parameters (six constant-bank loads with their latency) inside the hit path
+      asm volatile("" : "+l"(my_cand.q), "+l"(my_cand.col));
       const int my_cap = real ? half_cap : 0;            // padded rows count but never store
       int32_t* out_count = (p.slice < 0 ? cand_count : sp.count) + (size_t)slot * kHalves + h;
       float* out_thresh = (p.slice < 0 ? cand_thresh : sp.thresh) + slot;
       RowState rs;
       rs.tau = INFINITY;
       rs.cnt = 0;
+      rs.bm = smem_u32(&buckets->bm[m][q][h][0][lane]);
 #pragma unroll
-      for (int i = 0; i < kHalfBuckets; ++i) rs.bm[i] = -INFINITY;
+      for (int i = 0; i < kHalfBuckets; ++i) sts_f32(rs.bm + i * 128, -INFINITY);
       // item tile of this iteration.  Only whole-catalog passes are rotated, so the sweep wraps at the end of
       // the catalog in both kinds of pass (a slice never gets there before its last iteration).
       const int restart = p.i0 + p.rot;
@@ -588,35 +601,35 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
         ++uses;                                                                                    \
         tc_fence_after();                                                                          \
         drain_half<MODE>(lane_base + slot_t * kItemTile, col0, rs, my_cand, my_cap,                \
-                         &bars->t_empty[slot_t], lane);                                            \
+                         &bars->t_empty[slot_t], lane, mode);                                      \
       }
-      if (mode != 0) {
+      if ((mode & 7) != 0) {
         // debug shapes of the pipeline: 3 = handshakes only, 4 = one load, 1 = both loads, 2 = + the hot path
         for (; it < num_iters; ++it) {
           const int slot_t = m * kBUF + (int)(uses & 1u);
-          if (mode == 2) { HNM_TILE_STEP(kSeed) continue; }
+          if ((mode & 7) == 2) { HNM_TILE_STEP(kSeed) continue; }
           mbar_wait(&bars->t_full[slot_t], (uses >> 1) & 1u);
           ++uses;
           tc_fence_after();
           float va[32];
           float acc = 0.f;
-          const int nld = mode == 1 ? 2 : (mode == 4 ? 1 : 0);
+          const int nld = (mode & 7) == 1 ? 2 : ((mode & 7) == 4 ? 1 : 0);
           for (int c = 0; c < nld; ++c) { tmem_ld32(lane_base + slot_t * kItemTile + c * 32, va); tmem_ld_wait(va); acc += va[c]; }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->t_empty[slot_t]);
-          rs.bm[0] += acc;
+          sts_f32(rs.bm, acc);
         }
       } else {
         for (; it < boot; ++it) HNM_TILE_STEP(kSeed)     // the seed tiles: buckets only
         cur = restart;                                    // ... and they are swept a second time, collecting
         while (it < num_iters) {
-          rs.tau = refresh_tau(rs, h, xb, xt, bar_id, kth_sel, lane);
+          if (!(mode & 32) || it == boot) rs.tau = refresh_tau(row_bm, h, xt, bar_id, kth_sel);
           const int seen = max(boot, it - boot);         // item tiles behind the current bucket maxima
           const int stop = min(num_iters, it + max(2, seen / refresh_div));
           for (; it < stop; ++it) HNM_TILE_STEP(kCollect)
         }
-        rs.tau = refresh_tau(rs, h, xb, xt, bar_id, kth_sel, lane);
+        rs.tau = refresh_tau(row_bm, h, xt, bar_id, kth_sel);
       }
 #undef HNM_TILE_STEP
       if (real) {

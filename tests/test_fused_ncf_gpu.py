@@ -198,9 +198,40 @@ def test_ncf_recommend_filter_and_errors(hnm_lib):
         m.predict_all_items(torch.tensor([300]))
     with pytest.raises(RuntimeError):
         m(torch.tensor([1, 2]), torch.tensor([1]))
-    cpu_model = NeuralCF(10, 10)
+    cpu_model = NeuralCF(10, 10).eval()                       # scoring (eval / no_grad) has no CPU path
     with pytest.raises(RuntimeError, match="CUDA"):
         cpu_model(torch.tensor([1]), torch.tensor([1]))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        NeuralCF(10, 10)(torch.tensor([1]), torch.tensor([1]))
+
+
+def test_ncf_training_step_matches_reference_formulation(hnm_lib):
+    """neural_cf.py:210-233: BCE-with-logits on the autograd forward (train mode); its eval-mode logits equal the
+    fused kernels' (same parameters), gradients reach every parameter, and one optimiser step changes what the
+    kernels score (the layer-1 tables follow the parameter versions)."""
+    from hnm_recommendation_b200 import NeuralCF
+    torch.manual_seed(5)
+    m = NeuralCF(500, 200).to("cuda")
+    u = torch.randint(0, 500, (256,), device="cuda")
+    i = torch.randint(0, 200, (256,), device="cuda")
+    labels = torch.randint(0, 2, (256,), device="cuda")
+    m.eval()
+    with torch.no_grad():
+        k_logits = m(u, i)                                   # kernels
+    ref_logits = m._forward_autograd(u, i)                   # reference formulation, dropout off in eval
+    assert_close(k_logits, ref_logits.detach(), what="kernel vs autograd logits")
+    m.train()
+    loss = m.training_step({"user_ids": u, "item_ids": i, "labels": labels}, 0)
+    assert loss.requires_grad and loss.dim() == 0
+    loss.backward()
+    assert all(p.grad is not None for p in m.parameters())
+    opt = m.configure_optimizers()["optimizer"]
+    opt.step()
+    m.eval()
+    with torch.no_grad():
+        after = m(u, i)
+    assert not torch.allclose(after, k_logits)
+    assert_close(after, m._forward_autograd(u, i).detach(), what="kernel logits after an optimiser step")
 
 
 def test_streamed_host_delivery_matches_device_result(hnm_lib):
