@@ -450,6 +450,32 @@ def run_ncf(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa(gpu_index: int):
+    """Run this rank on the CPUs of its GPU's NUMA node BEFORE the pinned host buffers are allocated (first touch
+    puts them on that node): with eight ranks' buffers all on node 0 the host-to-device copies of the e2e leg
+    shared one socket's memory controllers.  Best effort; returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch.distributed as dist
@@ -461,6 +487,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     barrier = (lambda: dist.barrier()) if world > 1 else None
@@ -601,6 +628,7 @@ def run_gpu(args):
     if mg_check is not None:
         line["multi_gpu_check"] = mg_check
         line["items_mode_ms"] = items_mode_ms
+        line["host_numa_node_rank0"] = numa
     if world == 1 and not args.no_cpu:
         line["gpu_comparators"] = gpu_comparators(model)
         cores = host_threads()

@@ -215,7 +215,20 @@ struct RowState {
   float tau;                  // collect threshold (+inf while seeding), common to both threads of the row
   int cnt;                    // chunks this thread appended so far (may exceed its capacity: overflow)
   uint32_t bm;                // shared-memory address of this thread's 16 bucket maxima: bucket b at bm + 128 b
+  const uint32_t* sig;        // the row's exclusion signature (kSigWords words) or nullptr
 };
+// Purchased-item filter (src/models/lightgcn.py:349-353, the serving default scripts/serve.py:350-352): the
+// excluded items are exactly a user's best-scoring ones, so a threshold that tracks the (k+3)-th best score of
+// ALL items leaves fewer than k contenders after the filter.  Each row therefore carries a 1 024-bit signature
+// of the 32-column chunks that hold an excluded item (bit = chunk index mod 1 024); such chunks are still
+// nominated, but they never feed the bucket maxima, so tau is a lower bound on the kth best score among items
+// of unflagged chunks -- all of them allowed.  A false positive (two chunks sharing a bit) only costs a little
+// tightness.  hnm_rescore_topk applies the filter exactly.
+constexpr int kSigWords = HNM_FUSED_SIG_WORDS;
+__device__ __forceinline__ bool chunk_flagged(const uint32_t* __restrict__ sig, int col0) {
+  const uint32_t chunk = (uint32_t)col0 >> 5;
+  return (__ldg(sig + ((chunk >> 5) & (kSigWords - 1))) >> (chunk & 31u)) & 1u;
+}
 __device__ __forceinline__ float lds_f32(uint32_t a) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -332,12 +345,12 @@ template <int MODE>
 __device__ __forceinline__ void finish32(const float (&q)[8], int chunk, int col0, RowState& st,
                                          const CandList cand, int cap, int xp = 0) {
   if (MODE == kSeed) {
-    bucket_update(st.bm, chunk, q);
+    if (st.sig == nullptr || !chunk_flagged(st.sig, col0)) bucket_update(st.bm, chunk, q);
     return;
   }
   const float m32 = fmaxf(fmaxf(fmaxf(fmaxf(q[0], q[1]), q[2]), fmaxf(fmaxf(q[3], q[4]), q[5])), fmaxf(q[6], q[7]));
   if (m32 > st.tau) {
-    if (!(xp & 16)) bucket_update(st.bm, chunk, q);
+    if (!(xp & 16) && (st.sig == nullptr || !chunk_flagged(st.sig, col0))) bucket_update(st.bm, chunk, q);
     if (xp & 8) { ++st.cnt; return; }    // experiment: count, do not store
     if (st.cnt >= cap) {                 // no room: stop collecting, flag the row
       st.tau = INFINITY;
@@ -453,8 +466,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                         int num_users, int num_user_tiles, int num_item_tiles, int kth_sel,
                         const CandList cand, int cap, int32_t* __restrict__ cand_count,
-                        float* __restrict__ cand_thresh, int mode, int boot_tiles, int refresh_div,
-                        uint32_t wait_hint_ns, const SplitPlan sp) {
+                        float* __restrict__ cand_thresh, const uint32_t* __restrict__ excl_sig, int mode,
+                        int boot_tiles, int refresh_div, uint32_t wait_hint_ns, const SplitPlan sp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                   // [2][kMU][kTileBytes]
@@ -584,6 +597,8 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       rs.tau = INFINITY;
       rs.cnt = 0;
       rs.bm = smem_u32(&buckets->bm[m][q][h][0][lane]);
+      rs.sig = (excl_sig != nullptr && real)
+                   ? excl_sig + (size_t)((p.t0 + m) * kUserTile + q * 32 + lane) * kSigWords : nullptr;
 #pragma unroll
       for (int i = 0; i < kHalfBuckets; ++i) sts_f32(rs.bm + i * 128, -INFINITY);
       // item tile of this iteration.  Only whole-catalog passes are rotated, so the sweep wraps at the end of
@@ -757,6 +772,38 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand
     cand_count[(size_t)row * kHalves + 1] = 0;
     cand_thresh[row] = total > cap ? INFINITY : thr;
   }
+}
+
+// ----------------------------------------------------------------------------- exclusion signatures
+// One warp per user: word w of the signature is built by lane w.
+__global__ void __launch_bounds__(128)
+excl_signature_kernel(const int64_t* __restrict__ excl_ptr, const int64_t* __restrict__ excl_items, int64_t batch,
+                      int64_t item_begin, int64_t num_items_local, uint32_t* __restrict__ sig) {
+  static_assert(kSigWords == 32, "one word per lane");
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= batch) return;
+  uint32_t mine = 0u;
+  const int64_t lo = excl_ptr[b], hi = excl_ptr[b + 1];
+  for (int64_t base = lo; base < hi; base += 32) {
+    int word = -1;
+    uint32_t bit = 0u;
+    if (base + lane < hi) {
+      const int64_t local = excl_items[base + lane] - item_begin;
+      if (local >= 0 && local < num_items_local) {
+        const uint32_t chunk = (uint32_t)(local >> 5);
+        word = (int)((chunk >> 5) & (kSigWords - 1));
+        bit = 1u << (chunk & 31u);
+      }
+    }
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const int wj = __shfl_sync(0xffffffffu, word, j);
+      const uint32_t bj = __shfl_sync(0xffffffffu, bit, j);
+      if (wj == lane) mine |= bj;
+    }
+  }
+  sig[(size_t)b * kSigWords + lane] = mine;
 }
 
 // ----------------------------------------------------------------------------- pack / absmax
@@ -1345,7 +1392,8 @@ extern "C" int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_pad
 extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, int64_t users_padded,
                                     const void* items_f16, int64_t num_items, int64_t items_padded, int32_t kth_sel,
                                     void* cand, int32_t cand_cap, int32_t* cand_count, float* cand_thresh,
-                                    void* workspace, int64_t workspace_bytes, void* stream_) {
+                                    const uint32_t* excl_sig, void* workspace, int64_t workspace_bytes,
+                                    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!users_f16 || !items_f16 || !cand || !cand_count || !cand_thresh) return HNM_E_NULL;
   if (num_users <= 0 || num_items <= 0 || users_padded < num_users || items_padded < num_items) return HNM_E_RANGE;
@@ -1379,7 +1427,7 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   HNM_CUDA_TRY(hnm_allow_smem(score_topk_fused_kernel, (int)kSmemBytes));
   score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(
       map_u, map_i, (int)num_users, num_user_tiles, num_tiles, kth_sel, cand_list(cand, (size_t)num_users, cand_cap),
-      cand_cap, cand_count, cand_thresh, debug_mode, boot_tiles, refresh_div, wait_hint, sp);
+      cand_cap, cand_count, cand_thresh, excl_sig, debug_mode, boot_tiles, refresh_div, wait_hint, sp);
   HNM_LAUNCH_CHECK();
   if (need > 0) {
     const int64_t split_users = std::min<int64_t>((int64_t)sp.triples * sp.mu * kUserTile,
@@ -1390,6 +1438,19 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
       HNM_LAUNCH_CHECK();
     }
   }
+  return HNM_OK;
+}
+
+extern "C" int hnm_exclusion_signature(const int64_t* excl_ptr, const int64_t* excl_items, int64_t batch,
+                                       int64_t item_begin, int64_t num_items_local, uint32_t* out_sig,
+                                       void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (batch == 0) return HNM_OK;
+  if (!excl_ptr || !excl_items || !out_sig) return HNM_E_NULL;
+  if (batch < 0 || num_items_local < 1) return HNM_E_RANGE;
+  excl_signature_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, stream>>>(excl_ptr, excl_items, batch, item_begin,
+                                                                        num_items_local, out_sig);
+  HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
 

@@ -17,12 +17,10 @@ from ._lib import call, ptr, stream
 HEAVY_THRESHOLD = 1024          # CSR rows longer than this are summed by a whole CTA
 HUGE_ROW = 8192                 # ... and rows longer than this by a cluster of 8 CTAs (HNM_HUGE_ROW)
 EXACT_K_MAX = 256               # hnm_topk_exact limit (XCAP - XT in score_exact.cu)
-FUSED_DIM = 64
-FUSED_USER_TILE = 128
-FUSED_ITEM_TILE = 256
-FUSED_CAND = 32
-FUSED_K_MAX = 16
-NUM_SMS = 148
+
+
+def num_sms(device=None) -> int:
+    return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
 
 
 @dataclass
@@ -140,6 +138,34 @@ def exclusion_csr(user_ids: torch.Tensor, filter_items: Optional[Dict[int, set]]
             torch.tensor(items, dtype=torch.int64, device=device))
 
 
+def slice_csr(ptr_all: torch.Tensor, items_all: torch.Tensor, user_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Rows `user_ids` of a CSR over all users -> a CSR over the listed users (device ops only)."""
+    lo, hi = ptr_all[user_ids], ptr_all[user_ids + 1]
+    lens = hi - lo
+    out_ptr = torch.zeros(user_ids.numel() + 1, dtype=torch.int64, device=ptr_all.device)
+    torch.cumsum(lens, 0, out=out_ptr[1:])
+    total = int(out_ptr[-1])
+    if total == 0:
+        return out_ptr, torch.zeros(1, dtype=torch.int64, device=ptr_all.device)
+    row = torch.repeat_interleave(torch.arange(user_ids.numel(), device=ptr_all.device), lens)
+    pos = torch.arange(total, device=ptr_all.device) - out_ptr[row] + lo[row]
+    return out_ptr, items_all[pos].contiguous()
+
+
+def history_csr(graph: Graph, num_users: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The purchased-item filter of the serving path (scripts/serve.py:174-177,350-352) straight from the graph:
+    user u's row of the adjacency holds its self loop and the item nodes it bought, so the exclusion lists are
+    the user block of the CSR minus the self loops, item NODE ids turned into item indices.  Sorted per user
+    (the CSR is), repeat purchases appear more than once (harmless).  Bipartite graphs only."""
+    if not is_bipartite(graph, num_users):
+        raise ValueError("history_csr needs a bipartite user-item graph")
+    split = int(graph.rowptr[num_users])
+    col = graph.col[:split]
+    items = (col[col >= num_users] - num_users).to(torch.int64).contiguous()
+    ptr_ = graph.rowptr[: num_users + 1].to(torch.int64) - torch.arange(num_users + 1, device=col.device)
+    return ptr_.contiguous(), items
+
+
 def _norm_ids(ids: Optional[torch.Tensor], limit: int, device) -> Optional[torch.Tensor]:
     if ids is None:
         return None
@@ -198,7 +224,7 @@ def topk_exact(user_emb, item_emb, user_ids: Optional[torch.Tensor], k: int,
     # few users (the fallback of the tensor-core path): split the item range so the launch fills the GPU
     n_items = int(item_emb.size(0))
     ctas = max(1, (b + 7) // 8)
-    splits = max(1, min(16, (2 * NUM_SMS + ctas - 1) // ctas, n_items // max(1024, k)))
+    splits = max(1, min(16, (2 * num_sms(dev) + ctas - 1) // ctas, n_items // max(1024, k)))
     ids = torch.empty(splits, b, k, dtype=torch.int64, device=dev)
     sc = torch.empty(splits, b, k, dtype=torch.float64, device=dev)
     if b == 0:

@@ -254,11 +254,13 @@ class LightGCN(ModelBase):
         return ids
 
     def recommend_all(self, k: Optional[int] = None, return_scores: bool = False,
-                      out_host: Optional[torch.Tensor] = None):
+                      out_host: Optional[torch.Tensor] = None, filter_purchased: bool = False):
         """Full-catalog top-k for every user (the BASELINE.json headline path): [num_users, k].
 
         out_host: optional pinned int64 [num_users, k] tensor that receives the ids as they are produced
-        (device-to-host copies overlap the scoring of the following users); complete when the call returns."""
+        (device-to-host copies overlap the scoring of the following users); complete when the call returns.
+        filter_purchased: drop every user's own purchases, the serving default of the reference
+        (scripts/serve.py:174-177,350-352); the exclusion lists come straight from the graph on the device."""
         self.eval()
         k = self.top_k if k is None else int(k)
         if k > self.num_items or k <= 0:
@@ -266,12 +268,13 @@ class LightGCN(ModelBase):
         with torch.no_grad():
             ue, ie = self.forward()
             from .scorer import FusedScorer
+            hist = engine.history_csr(self.graph, self.num_users) if filter_purchased else None
             if FusedScorer.supports(self.embedding_dim, k, self.num_items):
                 if self._scorer is None:
                     self._scorer = FusedScorer(ue, ie)
-                ids, sc = self._scorer.topk(None, k, None, out_host=out_host)
+                ids, sc = self._scorer.topk(None, k, hist, out_host=out_host)
             else:
-                ids, sc = engine.topk_exact(ue, ie, None, k)
+                ids, sc = engine.topk_exact(ue, ie, None, k, hist if hist is not None else (None, None))
                 if out_host is not None:
                     out_host.copy_(ids)
         return (ids, sc) if return_scores else ids

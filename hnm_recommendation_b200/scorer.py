@@ -19,10 +19,12 @@ USER_BLOCK = 128
 ITEM_TILE = 128
 CAND_CAP = 192                 # candidate entries (32-column chunks) per user; ~100 on average at the H&M shape
 CAND_WORDS = 5                 # HNM_FUSED_CAND_BYTES / 4 (16 bytes of group maxima + 4 bytes of column per entry)
+SIG_WORDS = 32                 # HNM_FUSED_SIG_WORDS
 K_MAX = 16
 SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maximum
 MAX_USERS_PER_LAUNCH = 1 << 21
-TIER2_MIN_USERS = 32
+TIER2_MIN_USERS = 192           # fewer uncertified users go straight to the exact kernel (measured: 2.4 ms per thousand
+                                # users at the H&M catalog; the second tensor pass costs ~0.5 ms at any count)
 
 
 class FusedScorer:
@@ -58,7 +60,7 @@ class FusedScorer:
         self.stage_ms: Dict[str, float] = {}
         self._events = []
 
-    def topk(self, user_ids: Optional[torch.Tensor], k: int, filter_items: Optional[Dict[int, set]] = None,
+    def topk(self, user_ids: Optional[torch.Tensor], k: int, filter_items=None,
              fallback: bool = True, out_host: Optional[torch.Tensor] = None,
              chunk_users: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """ids [B,k] int64 (global item indices), scores [B,k] fp64; canonical (score desc, id asc).
@@ -67,6 +69,11 @@ class FusedScorer:
         1. tensor-core nomination with tau tracking the (k + sel_margin)-th best score, exact rescoring;
         2. the same with a wider margin (k + 12): near-ties between the k-th score and tau disappear;
         3. exact fp64 brute force (hnm_topk_exact): exact ties, overflowing lists, anything else.
+
+        filter_items: the reference's ``{user_id: set(item ids)}`` dict (lightgcn.py:349-353), or a device CSR
+        ``(ptr int64 [U_all + 1], items int64 sorted per user)`` over ALL users of the table (engine.history_csr:
+        the purchased-item filter at full scale without a Python loop).  Filtered users stay on the tensor
+        path: their excluded chunks are kept out of the nomination threshold (hnm_exclusion_signature).
 
         out_host (pinned int64 [B, k]): the ids are also delivered to the host, chunk of users by chunk of
         users on a copy stream while the next chunk is being scored; the few rows the fallback tiers rewrite
@@ -79,10 +86,11 @@ class FusedScorer:
         sc = torch.empty(total, k, dtype=torch.float64, device=dev)
         cert = torch.empty(total, dtype=torch.int32, device=dev)
         excl = (None, None)
+        full_csr = isinstance(filter_items, tuple)
         if filter_items is not None:
             if uids is None:
                 uids = torch.arange(total, device=dev)
-            excl = engine.exclusion_csr(uids, filter_items, dev)
+            excl = self._exclusions(uids, filter_items)
         self._events = []
         sel = min(32, k + self.sel_margin)
         step = MAX_USERS_PER_LAUNCH
@@ -110,7 +118,7 @@ class FusedScorer:
             why = cert[bad] if (n_bad and self.profile) else None
             if n_bad:
                 bad_uids = bad if uids is None else uids[bad]
-                sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev) if excl[0] is not None else (None, None)
+                sub_excl = self._exclusions(bad_uids, filter_items) if excl[0] is not None else (None, None)
                 sel2 = min(32, k + 12)
                 # the second tensor-core pass slices the item range of its few user tiles over the CTAs
                 # (SplitPlan in csrc/score_fused.cu), so it is cheap for any count; only a handful of users
@@ -129,7 +137,7 @@ class FusedScorer:
                     bad = bad[rest]
                     bad_uids = bad_uids[rest]
                     if bad.numel() and excl[0] is not None:
-                        sub_excl = engine.exclusion_csr(bad_uids, filter_items, dev)
+                        sub_excl = self._exclusions(bad_uids, filter_items)
                 if bad.numel():
                     self.last_stats["tier3"] = int(bad.numel())
                     e_ids, e_sc = engine.topk_exact(self.user_emb, self.item_emb, bad_uids, k, sub_excl,
@@ -157,6 +165,13 @@ class FusedScorer:
                     ms[n0[:-6]] = ms.get(n0[:-6], 0.0) + e0.elapsed_time(e1)
             self.stage_ms = ms
         return ids, sc
+
+    def _exclusions(self, uids: torch.Tensor, filter_items):
+        """Exclusion CSR over the listed users: from the reference's dict, or sliced out of an all-users CSR."""
+        dev = self.item_emb.device
+        if isinstance(filter_items, tuple):
+            return engine.slice_csr(filter_items[0], filter_items[1], uids)
+        return engine.exclusion_csr(uids, filter_items, dev)
 
     def _copy_stream(self) -> torch.cuda.Stream:
         if getattr(self, "_cstream", None) is None:
@@ -197,11 +212,16 @@ class FusedScorer:
                 raise ValueError("bad padded sizes for the fused scorer")
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             note("pack_end")
+            ex_ptr = excl[0][b0:b1 + 1] if excl[0] is not None else None
+            sig = None
+            if ex_ptr is not None:
+                sig = torch.empty(n, SIG_WORDS, dtype=torch.int32, device=dev)
+                call("hnm_exclusion_signature", ptr(ex_ptr), ptr(excl[1]), n, self.item_begin, self.num_items,
+                     ptr(sig), s)
             note("fused_begin")
             call("hnm_score_topk_fused", ptr(users_f16), n, padded, ptr(self.items_f16), self.num_items,
-                 self.items_padded, sel, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(ws), ws_bytes, s)
+                 self.items_padded, sel, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(sig), ptr(ws), ws_bytes, s)
             note("fused_end")
-            ex_ptr = excl[0][b0:b1 + 1] if excl[0] is not None else None
             note("rescore_begin")
             call("hnm_rescore_topk", ptr(user_base), ptr(self.item_emb), ptr(rid), n, 64, self.item_begin,
                  self.num_items, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(inv_scale), ptr(self.item_params),

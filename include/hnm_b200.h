@@ -197,6 +197,7 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
 #define HNM_FUSED_ITEM_TILE 128     /* items per MMA tile (UMMA N); items_padded must be a multiple */
 #define HNM_FUSED_CAND_MAX 256      /* largest cand_cap (entries per user) */
 #define HNM_FUSED_CAND_BYTES 20     /* bytes per candidate entry (16 in the q array + 4 in the col array) */
+#define HNM_FUSED_SIG_WORDS 32      /* uint32 words of a user's exclusion signature (1 024 bits) */
 
 /* max |x - center[col]| over `count` floats of a [rows, dim] table -> *out_absmax (device float,
  * zeroed by the caller).  center NULL = no centring. */
@@ -220,8 +221,19 @@ HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */,
                          void* cand /* num_users * cand_cap * HNM_FUSED_CAND_BYTES bytes, 16-byte aligned (layout above) */,
                          int32_t cand_cap /* even */, int32_t* cand_count /* [num_users][2] */,
                          float* cand_thresh /* [num_users] final tau (scaled units) */,
+                         const uint32_t* excl_sig /* [num_users][HNM_FUSED_SIG_WORDS] from hnm_exclusion_signature,
+                                                     or NULL when nothing is filtered */,
                          void* workspace /* hnm_score_topk_fused_workspace_bytes(), may be NULL when that is 0 */,
                          int64_t workspace_bytes, void* stream);
+/* Purchased-item filter on the tensor path (src/models/lightgcn.py:349-353; the serving default,
+ * scripts/serve.py:350-352).  A user's excluded items are typically his best-scoring ones, so the nomination
+ * threshold must not be built from them: hnm_exclusion_signature marks, per user, the 32-item chunks of the
+ * shard that hold an excluded item (bit = chunk index mod 1 024); hnm_score_topk_fused still nominates such
+ * chunks but keeps them out of the threshold estimate, and hnm_rescore_topk applies the filter exactly.
+ * excl_ptr / excl_items: CSR over the `batch` users of excluded GLOBAL item ids, sorted per user. */
+HNM_API int hnm_exclusion_signature(const int64_t* excl_ptr, const int64_t* excl_items, int64_t batch,
+                            int64_t item_begin, int64_t num_items_local,
+                            uint32_t* out_sig /* [batch][HNM_FUSED_SIG_WORDS] */, void* stream);
 /* Scratch for the user tiles that do not fill a whole pass of the persistent grid: their item range is cut
  * into slices handled by different CTAs, with one candidate list per (user, slice) that a second kernel
  * merges into `cand` (at most ~240 MB at the H&M catalog).  < 0 on bad sizes. */

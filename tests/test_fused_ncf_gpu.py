@@ -250,3 +250,34 @@ def test_streamed_host_delivery_matches_device_result(hnm_lib):
     assert torch.equal(got, want) and torch.equal(host, want.cpu())
     with pytest.raises(ValueError):
         sc.topk(None, 12, out_host=torch.empty(3000, 12, dtype=torch.int64))   # not pinned
+
+
+def test_filter_own_history_stays_on_the_tensor_path(hnm_lib):
+    """The reference's serving default (scripts/serve.py:350-352): every user's own purchases are filtered.  A
+    user's purchases are also his best-scoring items, so without the exclusion signatures the nomination
+    threshold would sit above every allowed item and most users would fall to the brute-force tier.  Lists must
+    equal the exact kernel's with the same exclusion lists, bit for bit, and the fallback must stay rare."""
+    from hnm_recommendation_b200 import LightGCN, engine, synth
+    U, I, E = 30011, 8300, 700000
+    data = synth.interactions(U, I, E, seed=11)
+    m = LightGCN(U, I).to("cuda")
+    with torch.no_grad():
+        m.embeddings.weight.copy_(synth.trained_like_embeddings(U + I, 64, seed=11))
+    m.set_graph(data.edge_index().cuda())
+    ids, sc = m.recommend_all(return_scores=True, filter_purchased=True)
+    stats = m._scorer.last_stats
+    assert stats["tier3"] + stats["tier2"] <= U // 50, stats
+    ptr, items = engine.history_csr(m.graph, U)
+    assert int(ptr[-1]) == E and items.numel() == E                       # every interaction, repeats included
+    ue, ie = m.forward()
+    uids = torch.arange(0, U, 3, device="cuda")
+    e_ids, e_sc = engine.topk_exact(ue, ie, uids, 12, engine.slice_csr(ptr, items, uids))
+    assert torch.equal(ids[uids], e_ids) and torch.equal(sc[uids], e_sc)
+    # nothing a user bought is recommended to him
+    bought = torch.zeros(U, I, dtype=torch.bool, device="cuda")
+    bought[torch.from_numpy(data.users).cuda(), torch.from_numpy(data.items).cuda()] = True
+    assert not bool(torch.gather(bought, 1, ids).any())
+    # the dict form of the reference API takes the same path for a batch of users
+    some = uids[:300]
+    hist = {int(u): set(items[int(ptr[u]):int(ptr[u + 1])].tolist()) for u in some.tolist()}
+    assert torch.equal(m.recommend(some, filter_items=hist), ids[some])

@@ -94,15 +94,35 @@ def test_config1_forward_matches_oracle(hnm_lib):
     assert torch.equal(m.graph.rowptr.cpu().long(), orc.graph[0])
     assert torch.equal(m.graph.col.cpu().long(), orc.graph[1])
     assert_close(m.graph.dis, orc.graph[3], rtol=2e-7, atol_scale=0, what="dis")
+    gu, gi = m.forward()                                   # train mode + autograd on: differentiable, as the reference's
+    assert gu.requires_grad and gu.grad_fn is not None
+    assert_close(gu.detach(), ou, what="users")
+    assert_close(gi.detach(), oi, what="items")
+    assert m.forward()[0].data_ptr() != gu.data_ptr()      # ... and recomputed on every call, like the reference
+    m.eval()
     gu, gi = m.forward()
-    assert_close(gu, ou, what="users")
-    assert_close(gi, oi, what="items")
-    # cached forward returns the same buffer until the weights change
+    assert not gu.requires_grad
+    assert_close(gu, ou, what="users (eval)")
+    # eval mode: the cached forward returns the same buffer until the weights change
     assert m.forward()[0].data_ptr() == gu.data_ptr()
     with torch.no_grad():
         m.embeddings.weight.mul_(2.0)
     gu2, _ = m.forward()
     assert_close(gu2, 2 * ou, what="users after in-place weight update")
+    # a write through .data is invisible to the version counter: invalidate(), or the verify mode
+    m.embeddings.weight.data.mul_(0.5)
+    assert m.forward()[0].data_ptr() == gu2.data_ptr()     # stale by design of the key ...
+    m.invalidate()
+    assert_close(m.forward()[0], ou, what="users after invalidate()")
+    m.cache_embeddings = "verify"
+    m.invalidate()
+    a = m.forward()[0]
+    assert m.forward()[0].data_ptr() == a.data_ptr()
+    m.embeddings.weight.data.mul_(3.0)
+    assert_close(m.forward()[0], 3 * ou, what="users after a .data write in verify mode")
+    m.load_state_dict({"embeddings.weight": w})            # load_state_dict invalidates by itself
+    m.cache_embeddings = True
+    assert_close(m.forward()[0], ou, what="users after load_state_dict")
 
 
 def test_config1_topk_all_users_bit_exact(hnm_lib):
@@ -244,10 +264,13 @@ def test_propagate_dims_and_long_rows(hnm_lib, dim, weighted):
     if weighted:
         half = torch.rand(u.numel(), generator=gen) + 0.5
         ew = torch.cat([half, half])
-    m = LightGCN(U, I, embedding_dim=dim, num_layers=L).to("cuda")
+    torch.manual_seed(1000 + dim)                          # the table's Xavier init: same numbers on every run
+    m = LightGCN(U, I, embedding_dim=dim, num_layers=L).to("cuda").eval()
     m.set_graph(ei, ew)
     assert m.graph.num_huge >= 1 and m.graph.num_heavy > m.graph.num_huge
-    orc = O.LightGCNOracle(U, I, dim, L, weight=m.embeddings.weight.detach().cpu())
+    # the fp64 twin of the oracle is the yardstick here: a row of 12 000 entries summed sequentially in fp32 (the
+    # fp32 oracle) is itself ~5e-6 away from the exact sum, so fp32-vs-fp32 at rtol 1e-5 is a coin toss on such rows
+    orc = O.LightGCNOracle(U, I, dim, L, weight=m.embeddings.weight.detach().cpu(), dtype=torch.float64)
     orc.set_graph(ei, ew)
     gu, gi = m.forward()
     ou, oi = orc.forward()
@@ -354,7 +377,11 @@ def test_bpr_loss_gradients_match_autograd_oracle(hnm_lib, symmetric, weighted, 
     want.backward()
     assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
     assert_close(grad, w64.grad, rtol=1e-4, atol_scale=1e-5, what="dL/d embeddings.weight")
-    # forward() itself stays the cached inference path
+    # train mode: forward() is the reference's differentiable forward; eval / no_grad: the cached inference path
+    assert m.forward()[0].requires_grad
+    with torch.no_grad():
+        assert not m.forward()[0].requires_grad
+    m.eval()
     assert not m.forward()[0].requires_grad
     # an optimizer step through the reference's configuration changes the weights and invalidates the cache
     before = m.forward()[0].clone()
