@@ -152,7 +152,7 @@ ncf_score_default_kernel(const float* __restrict__ gu, const float* __restrict__
 // CANDS = true (candidate / all-items form): a warp owns a contiguous range of 32-candidate tiles, so the
 // user's slices of P[u] and gw[u] = gu[u] * wp[:64] stay in registers for the ~31 tiles of a user;
 // CANDS = false (pair form): every row brings its own user.
-constexpr int kTcWarps = 8;
+constexpr int kTcWarps = 4;           // 3 CTAs of 4 warps per SM at <= 168 registers (one CTA of 8 warps at 182: 12 % of the warp slots)
 
 __device__ __forceinline__ uint32_t tf32_hi(float x) {
   uint32_t r;
@@ -166,7 +166,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 template <bool CANDS>
-__global__ void __launch_bounds__(kTcWarps * 32)
+__global__ void __launch_bounds__(kTcWarps * 32, 3)
 ncf_score_tc_kernel(const float* __restrict__ gu, const float* __restrict__ gi, const float* __restrict__ pu,
                     const float* __restrict__ qi, const float* __restrict__ tail, const float* __restrict__ wp,
                     float bp, const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids,
@@ -186,20 +186,10 @@ ncf_score_tc_kernel(const float* __restrict__ gu, const float* __restrict__ gi, 
                                 b1 - __uint_as_float(h1));
   }
   __syncthreads();
-  // this lane's 8 output columns of layer 2 (N tile nt: columns 8 nt + 2 c, + 1): bias and prediction weights
-  float b2r[8], wpr[8];
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      b2r[2 * nt + e] = tail[H2 * H1 + 8 * nt + 2 * c + e];
-      wpr[2 * nt + e] = wp[MF + 8 * nt + 2 * c + e];
-    }
-  }
-  float4 wg[4];                                         // wp[:64] on this lane's 16 GMF columns
-#pragma unroll
-  for (int v = 0; v < 4; ++v) wg[v] = ldg_f4(wp + 16 * v + 4 * c);
-
+  // layer-2 bias and prediction weights of the 32 outputs, read in the tail as {b2, wp} pairs
+  __shared__ float2 s_tail2[32];
+  if (threadIdx.x < H2) s_tail2[threadIdx.x] = make_float2(tail[H2 * H1 + threadIdx.x], wp[MF + threadIdx.x]);
+  __syncthreads();
   const int64_t warp_global = (int64_t)blockIdx.x * kTcWarps + (threadIdx.x >> 5);
   const int64_t warp_count = (int64_t)gridDim.x * kTcWarps;
   const int tiles_per_row = CANDS ? (cand_per_user + 31) / 32 : 1;
@@ -221,7 +211,8 @@ ncf_score_tc_kernel(const float* __restrict__ gu, const float* __restrict__ gi, 
         for (int v = 0; v < 4; ++v) {
           pr[v] = ldg_f4(pu + (size_t)u * H1 + 16 * v + 4 * c);
           const float4 x = ldg_f4(gu + (size_t)u * MF + 16 * v + 4 * c);
-          gw[v] = make_float4(wg[v].x * x.x, wg[v].y * x.y, wg[v].z * x.z, wg[v].w * x.w);
+          const float4 wgv = ldg_f4(wp + 16 * v + 4 * c);            // wp[:64] on this lane's GMF columns
+          gw[v] = make_float4(wgv.x * x.x, wgv.y * x.y, wgv.z * x.z, wgv.w * x.w);
         }
       }
       if (cpos < cand_per_user) {
@@ -258,7 +249,8 @@ ncf_score_tc_kernel(const float* __restrict__ gu, const float* __restrict__ gi, 
           wv = gw[v];
         } else {
           const float4 x = ldg_f4(gu + (size_t)ut[r] * MF + 16 * v + 4 * c);
-          wv = make_float4(wg[v].x * x.x, wg[v].y * x.y, wg[v].z * x.z, wg[v].w * x.w);
+          const float4 wgv = ldg_f4(wp + 16 * v + 4 * c);
+          wv = make_float4(wgv.x * x.x, wgv.y * x.y, wgv.z * x.z, wgv.w * x.w);
         }
         h1[r][4 * v + 0] = fmaxf(pv.x + qv[v].x, 0.f);
         h1[r][4 * v + 1] = fmaxf(pv.y + qv[v].y, 0.f);
@@ -312,10 +304,11 @@ ncf_score_tc_kernel(const float* __restrict__ gu, const float* __restrict__ gi, 
       float s_lo = 0.f, s_hi = 0.f;                      // rows g + 16 mt and g + 16 mt + 8
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        s_lo = fmaf(wpr[2 * nt], fmaxf(acc[mt][nt][0] + b2r[2 * nt], 0.f), s_lo);
-        s_lo = fmaf(wpr[2 * nt + 1], fmaxf(acc[mt][nt][1] + b2r[2 * nt + 1], 0.f), s_lo);
-        s_hi = fmaf(wpr[2 * nt], fmaxf(acc[mt][nt][2] + b2r[2 * nt], 0.f), s_hi);
-        s_hi = fmaf(wpr[2 * nt + 1], fmaxf(acc[mt][nt][3] + b2r[2 * nt + 1], 0.f), s_hi);
+        const float2 t0 = s_tail2[8 * nt + 2 * c], t1 = s_tail2[8 * nt + 2 * c + 1];      // {b2, wp} of two columns
+        s_lo = fmaf(t0.y, fmaxf(acc[mt][nt][0] + t0.x, 0.f), s_lo);
+        s_lo = fmaf(t1.y, fmaxf(acc[mt][nt][1] + t1.x, 0.f), s_lo);
+        s_hi = fmaf(t0.y, fmaxf(acc[mt][nt][2] + t0.x, 0.f), s_hi);
+        s_hi = fmaf(t1.y, fmaxf(acc[mt][nt][3] + t1.x, 0.f), s_hi);
       }
       y[2 * mt] = s_lo + gsum[2 * mt];
       y[2 * mt + 1] = s_hi + gsum[2 * mt + 1];
@@ -415,7 +408,7 @@ int launch_score(const float* gu, const float* gi, const float* pu, const float*
     const int64_t rows = cand_per_user > 0 ? total / cand_per_user : 0;
     const int64_t tiles = cand_per_user > 0 ? rows * ((cand_per_user + 31) / 32) : (total + 31) / 32;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + kTcWarps - 1) / kTcWarps,
-                                                                           (int64_t)hnm_num_sms() * 2));
+                                                                           (int64_t)hnm_num_sms() * 3));
     if (cand_per_user > 0)
       ncf_score_tc_kernel<true><<<grid, T, 0, stream>>>(gu, gi, pu, qi, tail, wp, bp, user_ids, item_ids, cand_items,
                                                         cand_per_user, rows, total, out);
