@@ -675,6 +675,9 @@ __device__ __forceinline__ void cmpx_lane(float& v, int lane, int stride, bool d
   v = (lower == desc) ? fmaxf(v, o) : fminf(v, o);    // best-first block: the lower lane keeps the larger value
 }
 
+// Order-preserving key of a 16-bit float pattern (sign + exponent + 7 mantissa bits): larger key <=> larger value.
+__device__ __forceinline__ uint32_t order_key16(uint32_t t) { return t ^ ((t & 0x8000u) ? 0xFFFFu : 0x8000u); }
+
 __device__ __forceinline__ uint32_t cand_half(const uint4& q, int h) {     // 16-bit pattern of group h
   const uint32_t w = h < 2 ? q.x : (h < 4 ? q.y : (h < 6 ? q.z : q.w));
   return (h & 1) ? (w >> 16) : (w & 0xFFFFu);
@@ -1022,6 +1025,7 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   // 1. keep the groups that may have ended above the final threshold (upper end of the interval the stored
   //    16 bits stand for), compacted: slot j = kept group j with the interval of its maximum
   int groups = 0;
+  const uint32_t thr_key = order_key16(__float_as_uint(thr) >> 16);
   // one sweep over both lists: entry e < n0 comes from list 0, the others from list 1
   for (int e0 = 0; e0 < n0 + n1; e0 += 32) {
     const int e = e0 + lane;
@@ -1033,12 +1037,13 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
       q = __ldg(mine.q + idx);
       col0 = __ldg(mine.col + idx);
     }
-    float lo[8], hi[8];
+    // A group can exceed thr only if its 16-bit pattern is not below thr's own (truncation toward zero keeps
+    // the order of the buckets), so the test is an integer compare on order keys; the float interval of a
+    // group is decoded only for the ~20 of ~800 groups that pass.
     uint32_t kmask = 0u;
+    if (have) {
 #pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      cand_bounds(cand_half(q, h), lo[h], hi[h]);
-      if (have && hi[h] > thr) kmask |= 1u << h;
+      for (int h = 0; h < 8; ++h) kmask |= (order_key16(cand_half(q, h)) >= thr_key) ? (1u << h) : 0u;
     }
     // exclusive prefix sum of the per-lane counts
     const int mine_cnt = __popc(kmask);
@@ -1049,12 +1054,17 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
       if (lane >= off) incl += o;
     }
     int pos = groups + incl - mine_cnt;
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      if (kmask & (1u << h)) {
-        if (pos < kMaxGroups) { sm.col[pos] = col0 + 4u * h; sm.glo[pos] = lo[h]; sm.ghi[pos] = hi[h]; }
-        ++pos;
+    while (kmask) {
+      const int h = __ffs(kmask) - 1;
+      kmask &= kmask - 1;
+      if (pos < kMaxGroups) {
+        float lo, hi;
+        cand_bounds(cand_half(q, h), lo, hi);
+        sm.col[pos] = col0 + 4u * h;
+        sm.glo[pos] = lo;
+        sm.ghi[pos] = hi;
       }
+      ++pos;
     }
     groups += __shfl_sync(0xffffffffu, incl, 31);
   }
