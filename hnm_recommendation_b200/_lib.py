@@ -35,6 +35,8 @@ _SIGNATURES = {
     "hnm_lightgcn_layer": (C.c_int, [P, P, P, P, P, P, P, F32, I64, I32, I64, I64, P, I32, I32, I32, P]),
     "hnm_lightgcn_partial": (C.c_int, [P, P, P, P, P, P, I32, I64, I64, P, I32, I32, I32, I32, P]),
     "hnm_lightgcn_finish": (C.c_int, [P, P, P, F32, P, P, I64, I64, I32, P]),
+    "hnm_lightgcn_partial_peer": (C.c_int, [P, P, P, P, P, P, I32, I32, I32, I64, I64, P, I32, I32, I32, P]),
+    "hnm_lightgcn_finish_peer": (C.c_int, [P, I32, I32, I32, P, P, F32, P, P, P, I64, I64, I32, P]),
     "hnm_pair_scores": (C.c_int, [P, P, P, P, I64, I32, I64, I64, P, P]),
     "hnm_score_all_items": (C.c_int, [P, P, P, I64, I64, I32, P, P]),
     "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, I32, P, P, P]),
@@ -105,6 +107,8 @@ def call(fn: str, *args) -> None:
         n = 2                                     # + merge of the per-slice candidate lists
     if fn == "hnm_lightgcn_partial" and args[10]:
         n = 2 + (1 if args[11] else 0)
+    if fn == "hnm_lightgcn_partial_peer" and args[12]:
+        n = 2 + (1 if args[13] else 0)
     if fn == "hnm_lightgcn_layer" and args[13]:
         n = 2 + (1 if args[14] else 0)            # cluster pass + whole-CTA pass over the long rows + warp-per-row pass
     LAUNCHES += n

@@ -27,8 +27,21 @@ struct Seg {
   const int32_t* b;
   const int32_t* e;
   int64_t off;
+  // Peer scatter of the partial sums (hnm_lightgcn_partial_peer): local row lr belongs to rank lr / rpo, and
+  // this rank's partial for it goes straight into the owner's staging buffer [world][rpo][dim] over NVLink.
+  float* const* peer;      // device array of the ranks' staging buffers (mapped peer memory), or nullptr
+  int rpo;                 // rows per owner
+  int rank;
   __device__ __forceinline__ int beg(int64_t row) const { return __ldg(b + (row - off)); }
   __device__ __forceinline__ int end(int64_t row) const { return __ldg(e + (row - off)); }
+  // where row `row` of the output goes (partial mode: a row of the partial-sum table)
+  __device__ __forceinline__ float* out_row(float* xs_out, int64_t row, int dim, int partial) const {
+    if (!(partial & 1)) return xs_out ? xs_out + (size_t)row * dim : nullptr;
+    const int64_t lr = row - off;
+    if (peer == nullptr) return xs_out + (size_t)lr * dim;
+    const int64_t o = lr / rpo;
+    return peer[o] + ((size_t)rank * rpo + (size_t)(lr - o * rpo)) * dim;
+  }
 };
 
 template <int D>
@@ -152,11 +165,11 @@ spmm_rows_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const fl
     warp_gather<D, WEIGHTED>(col, w, xs_in, beg, end, lane, acc);
     if (lane < S::LPR) {
       const float di = (partial & 1) ? 1.f : __ldg(dis + row);
-      const size_t orow = (partial & 1) ? (size_t)(row - seg.off) : (size_t)row;
+      float* orow = seg.out_row(xs_out, row, D, partial);
 #pragma unroll
       for (int t = 0; t < S::VEC; ++t) {
-        const size_t off = orow * D + (size_t)(t * S::LPR + lane) * 4;
-        row_epilogue(acc[t], di, alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
+        const size_t c = (size_t)(t * S::LPR + lane) * 4;
+        row_epilogue(acc[t], di, alpha, orow ? orow + c : nullptr, accbuf + (size_t)row * D + c, partial);
       }
     }
   }
@@ -191,8 +204,10 @@ spmm_heavy_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const f
     float4 s = part[0][threadIdx.x];
 #pragma unroll
     for (int k = 1; k < NW; ++k) add4(s, part[k][threadIdx.x]);
-    const size_t off = ((partial & 1) ? (size_t)(row - seg.off) : (size_t)row) * D + (size_t)threadIdx.x * 4;
-    row_epilogue(s, (partial & 1) ? 1.f : __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
+    float* orow = seg.out_row(xs_out, row, D, partial);
+    const size_t c = (size_t)threadIdx.x * 4;
+    row_epilogue(s, (partial & 1) ? 1.f : __ldg(dis + row), alpha, orow ? orow + c : nullptr,
+                 accbuf + (size_t)row * D + c, partial);
   }
 }
 
@@ -242,8 +257,10 @@ spmm_huge_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const fl
       const float4* remote = cluster.map_shared_rank(cta_sum, r);
       add4(s, remote[threadIdx.x]);
     }
-    const size_t off = ((partial & 1) ? (size_t)(row - seg.off) : (size_t)row) * D + (size_t)threadIdx.x * 4;
-    row_epilogue(s, (partial & 1) ? 1.f : __ldg(dis + row), alpha, xs_out ? xs_out + off : nullptr, accbuf + off, partial);
+    float* orow = seg.out_row(xs_out, row, D, partial);
+    const size_t c = (size_t)threadIdx.x * 4;
+    row_epilogue(s, (partial & 1) ? 1.f : __ldg(dis + row), alpha, orow ? orow + c : nullptr,
+                 accbuf + (size_t)row * D + c, partial);
   }
   cluster.sync();                                          // keep every CTA's shared memory alive until read
 }
@@ -456,9 +473,9 @@ extern "C" int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_
   // bit 1 of the mode word: layer sum by red.global.add instead of load + add + store (A/B switch)
   static const int red_mode = (getenv("HNM_SPMM_RED") ? atoi(getenv("HNM_SPMM_RED")) : 1) ? 2 : 0;
   if (csr_w)
-    return dispatch_layer<true>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0}, red_mode, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+    return dispatch_layer<true>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0, nullptr, 1, 0}, red_mode, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
                                 heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
-  return dispatch_layer<false>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0}, red_mode, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
+  return dispatch_layer<false>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0, nullptr, 1, 0}, red_mode, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
 }
 
@@ -497,7 +514,7 @@ extern "C" int hnm_lightgcn_partial(const int32_t* seg_begin, const int32_t* seg
   if (dim <= 0 || row_begin < 0 || row_begin > row_end) return HNM_E_RANGE;
   if (dim % 4 == 0 && !(hnm_aligned16(xs_in) && hnm_aligned16(partial))) return HNM_E_ALIGN;
   if (row_begin == row_end) return HNM_OK;
-  const Seg seg{seg_begin, seg_end, row_begin};
+  const Seg seg{seg_begin, seg_end, row_begin, nullptr, 1, 0};
   if (csr_w)
     return dispatch_layer<true>(dim, seg, mode, csr_col, csr_w, nullptr, xs_in, partial, nullptr, 0.f, row_begin, row_end,
                                 heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
@@ -519,6 +536,97 @@ extern "C" int hnm_lightgcn_finish(const float* partial, const float* xs_in, con
   const unsigned grid = (unsigned)std::min<int64_t>((total4 + T - 1) / T, (int64_t)hnm_num_sms() * 16);
   finish_kernel<<<grid, T, 0, stream>>>((const float4*)partial, (const float4*)xs_in, dis, alpha, (float4*)xs_out,
                                         (float4*)acc, row_begin, total4, dim / 4);
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
+}
+
+
+// ----------------------------------------------------------------------------- peer-memory exchange (multi-GPU)
+namespace {
+// Owner side of the exchange: rank `rank` owns item rows [rank * rpo, min(I, (rank + 1) * rpo)).  Its staging
+// buffer holds one partial sum per rank for each of them ([world][rpo][dim], written by the peers' gather
+// kernels over NVLink).  The partials are added in rank order (deterministic), the self loop, the degree
+// normalisation and the layer sum are applied exactly as hnm_lightgcn_finish does, and the new row of the
+// pre-scaled table goes to EVERY rank's copy (peer stores) -- one kernel instead of an all-reduce of the item
+// block plus a finish pass replicated on every rank.
+__global__ void finish_peer_kernel(const float4* __restrict__ stage, int world, int rpo, int rank,
+                                   const float4* __restrict__ xs_in, const float* __restrict__ dis, float alpha,
+                                   float4* const* __restrict__ peer_xs_out, float4* __restrict__ acc,
+                                   float4* const* __restrict__ peer_acc, int64_t item_row_begin, int64_t own_rows,
+                                   int dim4) {
+  const int64_t total4 = own_rows * dim4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t lr = i / dim4;
+    const int64_t row = item_row_begin + (int64_t)rank * rpo + lr;            // node id
+    const int64_t g = row * dim4 + (i - lr * dim4);
+    float4 s = stage[i];
+    for (int r = 1; r < world; ++r) {
+      const float4 p = stage[(int64_t)r * rpo * dim4 + i];
+      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    const float di = __ldg(dis + row);
+    const float4 self = xs_in[g];                          // the self loop (weight 1, lightgcn.py:127-132)
+    s.x += self.x; s.y += self.y; s.z += self.z; s.w += self.w;
+    const float4 e = make_float4(__fmul_rn(di, s.x), __fmul_rn(di, s.y), __fmul_rn(di, s.z), __fmul_rn(di, s.w));
+    if (peer_xs_out) {
+      const float4 x = make_float4(__fmul_rn(di, e.x), __fmul_rn(di, e.y), __fmul_rn(di, e.z), __fmul_rn(di, e.w));
+      for (int r = 0; r < world; ++r) peer_xs_out[r][g] = x;
+    }
+    float4 a = acc[g];
+    a.x = __fadd_rn(a.x, __fmul_rn(alpha, e.x));
+    a.y = __fadd_rn(a.y, __fmul_rn(alpha, e.y));
+    a.z = __fadd_rn(a.z, __fmul_rn(alpha, e.z));
+    a.w = __fadd_rn(a.w, __fmul_rn(alpha, e.w));
+    acc[g] = a;
+    if (peer_acc) {                                        // last layer: the finished layer sum goes to every rank
+      for (int r = 0; r < world; ++r)
+        if (r != rank) peer_acc[r][g] = a;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int hnm_lightgcn_partial_peer(const int32_t* seg_begin, const int32_t* seg_end, const int32_t* csr_col,
+                                         const float* csr_w, const float* xs_in, void* const* peer_stage,
+                                         int32_t rows_per_owner, int32_t rank, int32_t dim, int64_t row_begin,
+                                         int64_t row_end, const int32_t* heavy_rows, int32_t num_heavy,
+                                         int32_t num_huge, int32_t heavy_threshold, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!seg_begin || !seg_end || !csr_col || !xs_in || !peer_stage) return HNM_E_NULL;
+  if (num_heavy > 0 && !heavy_rows) return HNM_E_NULL;
+  if (num_huge < 0 || num_huge > num_heavy) return HNM_E_RANGE;
+  if (dim <= 0 || dim % 4 != 0 || row_begin < 0 || row_begin > row_end || rows_per_owner < 1 || rank < 0)
+    return HNM_E_RANGE;
+  if (!hnm_aligned16(xs_in)) return HNM_E_ALIGN;
+  if (dim != 8 && dim != 16 && dim != 32 && dim != 64 && dim != 128 && dim != 256) return HNM_E_DIM;
+  if (row_begin == row_end) return HNM_OK;
+  const Seg seg{seg_begin, seg_end, row_begin, reinterpret_cast<float* const*>(peer_stage), rows_per_owner, rank};
+  float* dummy = reinterpret_cast<float*>(16);            // never dereferenced: out_row() goes through seg.peer
+  if (csr_w)
+    return dispatch_layer<true>(dim, seg, 1, csr_col, csr_w, nullptr, xs_in, dummy, nullptr, 0.f, row_begin, row_end,
+                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
+  return dispatch_layer<false>(dim, seg, 1, csr_col, csr_w, nullptr, xs_in, dummy, nullptr, 0.f, row_begin, row_end,
+                               heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
+}
+
+extern "C" int hnm_lightgcn_finish_peer(const float* stage, int32_t world, int32_t rows_per_owner, int32_t rank,
+                                        const float* xs_in, const float* dis, float alpha, void* const* peer_xs_out,
+                                        float* acc, void* const* peer_acc, int64_t item_row_begin, int64_t num_items,
+                                        int32_t dim, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!stage || !xs_in || !dis || !acc) return HNM_E_NULL;
+  if (world < 1 || rows_per_owner < 1 || rank < 0 || rank >= world || dim <= 0 || dim % 4 != 0 || num_items < 0 ||
+      item_row_begin < 0)
+    return HNM_E_RANGE;
+  if (!(hnm_aligned16(stage) && hnm_aligned16(xs_in) && hnm_aligned16(acc))) return HNM_E_ALIGN;
+  const int64_t own = std::max<int64_t>(0, std::min<int64_t>(rows_per_owner, num_items - (int64_t)rank * rows_per_owner));
+  if (own == 0) return HNM_OK;
+  const int64_t total4 = own * (dim / 4);
+  const int T = 256;
+  const unsigned grid = (unsigned)std::min<int64_t>((total4 + T - 1) / T, (int64_t)hnm_num_sms() * 8);
+  finish_peer_kernel<<<grid, T, 0, stream>>>((const float4*)stage, world, rows_per_owner, rank, (const float4*)xs_in,
+                                             dis, alpha, reinterpret_cast<float4* const*>(peer_xs_out), (float4*)acc,
+                                             reinterpret_cast<float4* const*>(peer_acc), item_row_begin, own, dim / 4);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }

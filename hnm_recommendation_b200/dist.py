@@ -224,12 +224,35 @@ class CudaBackend:
             # asynchronous on NCCL: the caller overlaps it with the rank's own user rows and waits on the handle
             return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=coll.group, async_op=coll.nccl)
 
-        acc = engine.propagate_user_sharded(m.graph, self._shard, m.embeddings.weight, m.alpha, m.num_layers,
-                                            m.num_users, allreduce)
+        pb = self._peer_buffers(m, coll)
+        if pb is not None:
+            acc = engine.propagate_user_sharded_peer(m.graph, self._shard, m.embeddings.weight, m.alpha, m.num_layers,
+                                                     m.num_users, pb)
+        else:
+            acc = engine.propagate_user_sharded(m.graph, self._shard, m.embeddings.weight, m.alpha, m.num_layers,
+                                                m.num_users, allreduce)
         if final_users:
             coll.allgather_rows(acc, plan.user_rows)
         sharded._scorer = None
         return acc[: m.num_users], acc[m.num_users:]
+
+    def _peer_buffers(self, m, coll):
+        """Peer-mapped exchange buffers (NCCL process groups on one node; HNM_PEER_EXCHANGE=0 keeps the NCCL
+        all-reduce form).  Allocated once per (graph, world); None when symmetric memory is unavailable."""
+        import os
+        if not coll.nccl or os.environ.get("HNM_PEER_EXCHANGE", "1") == "0":
+            return None
+        key = (id(m.graph), coll.world, coll.rank, m.embedding_dim)
+        if getattr(self, "_peer_key", None) != key:
+            from . import engine
+            try:
+                self._peer = engine.PeerBuffers(m.num_nodes, m.num_items, m.embedding_dim, coll.group)
+            except Exception as exc:  # noqa: BLE001
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using NCCL all-reduce")
+                self._peer = None
+            self._peer_key = key
+        return self._peer
 
     def propagate(self, model, my_ranges, exchange, exchange_final):
         from . import engine

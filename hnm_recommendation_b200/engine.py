@@ -417,3 +417,77 @@ def propagate_user_sharded(graph: Graph, shard: UserShard, e0: torch.Tensor, alp
             if not last:
                 cur, nxt = nxt, cur
     return acc
+
+
+class PeerBuffers:
+    """Symmetric (peer-mapped) buffers of the NVLink exchange: the two pre-scaled tables, the layer sum and the
+    staging buffer for the partial sums, allocated once per (graph, world) with torch's symmetric memory
+    (cuMem allocations whose handles the ranks exchange; every rank sees every rank's buffer).  Item row i is
+    owned by rank i // rows_per_owner."""
+
+    def __init__(self, num_nodes: int, num_items: int, dim: int, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rpo = -(-num_items // self.world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pg = group if group is not None else dist.group.WORLD
+
+        def make(*shape):
+            t = symm.empty(*shape, dtype=torch.float32, device=dev)
+            return t, symm.rendezvous(t, pg)
+
+        self.xs_a, self.h_a = make(num_nodes, dim)
+        self.xs_b, self.h_b = make(num_nodes, dim)
+        self.acc, self.h_acc = make(num_nodes, dim)
+        self.stage, self.h_stage = make(self.world * self.rpo, dim)
+
+    def handle(self, t: torch.Tensor):
+        return {id(self.xs_a): self.h_a, id(self.xs_b): self.h_b, id(self.acc): self.h_acc}[id(t)]
+
+
+def propagate_user_sharded_peer(graph: Graph, shard: UserShard, e0: torch.Tensor, alphas: Sequence[float],
+                                num_layers: int, num_users: int, pb: PeerBuffers) -> torch.Tensor:
+    """propagate_user_sharded with the exchange inside the kernels: the partial-sum kernel stores every item
+    row's partial straight into its owner's staging buffer over NVLink, the owner reduces in rank order, finishes
+    the row and writes it into every rank's table (hnm_lightgcn_partial_peer / hnm_lightgcn_finish_peer), with
+    one cross-rank barrier after each of the two.  No NCCL call and no replicated finish pass on the data path.
+    Returns the symmetric layer-sum buffer (reused by the next call): valid for all item rows and for user rows
+    [u0, u1)."""
+    _lib.require_device()
+    e0 = e0.detach().to(torch.float32).contiguous()
+    n, d = e0.shape
+    U = num_users
+    I = n - U
+    u0, u1 = shard.u0, shard.u1
+    acc, xs_a, xs_b = pb.acc, pb.xs_a, pb.xs_b
+    with torch.cuda.device(e0.device):
+        s = stream()
+        # No barrier is needed here: a peer writes into this rank's buffers only after a barrier of the NEW step that
+        # this rank has reached, i.e. after everything it enqueued for the previous step (scoring included) is done.
+        if u1 > u0:
+            call("hnm_lightgcn_prescale", ptr(e0[u0:u1]), ptr(graph.dis[u0:u1]), float(alphas[0]), ptr(xs_a[u0:u1]),
+                 ptr(acc[u0:u1]), u1 - u0, d, s)
+        call("hnm_lightgcn_prescale", ptr(e0[U:]), ptr(graph.dis[U:]), float(alphas[0]), ptr(xs_a[U:]), ptr(acc[U:]),
+             I, d, s)
+        cur, nxt = xs_a, xs_b
+        heavy = ptr(graph.heavy_rows) if graph.num_heavy else None
+        sh_heavy = ptr(shard.heavy_rows) if shard.heavy_rows.numel() else None
+        for layer in range(1, num_layers + 1):
+            last = layer == num_layers
+            call("hnm_lightgcn_partial_peer", ptr(shard.seg_begin), ptr(shard.seg_end), ptr(graph.col), ptr(graph.w),
+                 ptr(cur), pb.h_stage.buffer_ptrs_dev, pb.rpo, pb.rank, d, U, n, sh_heavy,
+                 int(shard.heavy_rows.numel()), shard.num_huge, graph.heavy_threshold, s)
+            if u1 > u0:       # this rank's user rows need neither the partial sums nor the other ranks
+                call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
+                     None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, u0, u1, heavy, graph.num_heavy,
+                     graph.num_huge, graph.heavy_threshold, s)
+            pb.h_stage.barrier(channel=0)                 # every rank's partial sums have landed
+            call("hnm_lightgcn_finish_peer", ptr(pb.stage), pb.world, pb.rpo, pb.rank, ptr(cur), ptr(graph.dis),
+                 float(alphas[layer]), None if last else pb.handle(nxt).buffer_ptrs_dev, ptr(acc),
+                 pb.h_acc.buffer_ptrs_dev if last else None, U, I, d, s)
+            pb.h_stage.barrier(channel=1)                 # ... and every owner's finished rows
+            if not last:
+                cur, nxt = nxt, cur
+    return acc

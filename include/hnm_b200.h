@@ -118,6 +118,27 @@ HNM_API int hnm_lightgcn_finish(const float* partial /* [num_rows, dim] */, cons
                         const float* dis, float alpha, float* xs_out /* [N, dim] or NULL */, float* acc /* [N, dim] */,
                         int64_t row_begin, int64_t num_rows, int32_t dim, void* stream);
 
+/* The same exchange without NCCL and without the replicated finish pass (one process per GPU, the ranks'
+ * buffers mapped into each other's address space, e.g. torch.distributed._symmetric_memory): item row i is
+ * OWNED by rank i / rows_per_owner.  hnm_lightgcn_partial_peer is hnm_lightgcn_partial whose epilogue stores
+ * each partial sum straight into the owner's staging buffer [world][rows_per_owner][dim] over NVLink
+ * (peer_stage: device array of the `world` staging-buffer addresses as seen from this rank).  After a
+ * cross-rank barrier hnm_lightgcn_finish_peer adds the `world` partials of the rows this rank owns in rank
+ * order (deterministic), applies self loop / normalisation / layer sum like hnm_lightgcn_finish, and writes the
+ * new pre-scaled rows into every rank's xs_out (peer_xs_out, NULL on the last layer) and, when peer_acc is
+ * given (last layer), the finished layer-sum rows into every other rank's acc.  A second barrier makes the rows
+ * visible before the next layer gathers from them. */
+HNM_API int hnm_lightgcn_partial_peer(const int32_t* seg_begin, const int32_t* seg_end, const int32_t* csr_col,
+                              const float* csr_w, const float* xs_in, void* const* peer_stage /* device [world] */,
+                              int32_t rows_per_owner, int32_t rank, int32_t dim, int64_t row_begin, int64_t row_end,
+                              const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge,
+                              int32_t heavy_threshold, void* stream);
+HNM_API int hnm_lightgcn_finish_peer(const float* stage /* this rank's [world][rows_per_owner][dim] */, int32_t world,
+                             int32_t rows_per_owner, int32_t rank, const float* xs_in /* [N, dim] */,
+                             const float* dis, float alpha, void* const* peer_xs_out /* device [world] or NULL */,
+                             float* acc /* [N, dim] */, void* const* peer_acc /* device [world] or NULL */,
+                             int64_t item_row_begin, int64_t num_items, int32_t dim, void* stream);
+
 /* ------------------------------------------------------------------------
  * LightGCN.predict                              src/models/lightgcn.py:180-184
  * out[b] = dot(user_emb[user_ids[b]], item_emb[item_ids[b]]) in fp32.
