@@ -118,9 +118,14 @@ class Collectives:
             rows = max(sizes)
             padded = torch.empty((self.world, rows) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
             padded[self.rank, :sizes[self.rank]] = mine
-            dist.all_gather_into_tensor(padded.view((self.world * rows,) + tuple(mine.shape[1:])), padded[self.rank],
-                                        group=self.group)
-            return torch.cat([padded[r, :sizes[r]] for r in range(self.world)])
+            flat = padded.view((self.world * rows,) + tuple(mine.shape[1:]))
+            dist.all_gather_into_tensor(flat, padded[self.rank], group=self.group)
+            # drop the padding rows with ONE gather kernel (index cached per partition) instead of a cat of slices
+            key = (tuple(sizes), str(mine.device))
+            cache = self.__dict__.setdefault("_keep_index", {})
+            if key not in cache:
+                cache[key] = torch.cat([torch.arange(r * rows, r * rows + sizes[r]) for r in range(self.world)]).to(mine.device)
+            return flat.index_select(0, cache[key])
         out = torch.empty((total,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
         a, b = slices[self.rank]
         out[a:b] = mine
@@ -174,12 +179,25 @@ class ShardedLightGCN:
             if self.mode == "users":
                 ue, ie = self.forward(all_rows=False)
                 u0, u1 = p.user_slices[p.rank]
-                ids, sc = self.backend.local_topk(self, ue[u0:u1], ie, 0, k)           # my users vs all items
-                if m.num_items < 2 ** 31:
-                    # item ids fit 32 bits: half the bytes on the wire (66 instead of 132 MB at the H&M shape)
-                    out_ids = self.coll.allgather_slices(ids.to(torch.int32), p.user_slices, m.num_users).long()
-                else:
-                    out_ids = self.coll.allgather_slices(ids, p.user_slices, m.num_users)
+                # my users vs all items; the scorer's single host read is deferred until the all-gather is enqueued
+                ids, sc = self.backend.local_topk(self, ue[u0:u1], ie, 0, k, defer=True)
+
+                def gather():
+                    if m.num_items < 2 ** 31:
+                        # item ids fit 32 bits: half the bytes on the wire (66 instead of 132 MB at the H&M shape)
+                        return self.coll.allgather_slices(ids.to(torch.int32), p.user_slices, m.num_users).long()
+                    return self.coll.allgather_slices(ids, p.user_slices, m.num_users)
+
+                out_ids = gather()
+                # every rank's "something is left for tier 3" flag travels behind the ids, so that all ranks take
+                # the same decision from ONE host read (the step's only synchronisation) without another collective
+                mine = self.backend.pending_flag(self, ids.device)
+                flags = torch.empty(self.coll.world, dtype=torch.int64, device=ids.device)
+                dist.all_gather_into_tensor(flags, mine, group=self.coll.group)
+                anyone = bool(flags.sum().item())
+                self.backend.finalize_topk(self)
+                if anyone:                       # rare: some rank patched rows after the fact, gather again
+                    out_ids = gather()
                 if return_scores:
                     return out_ids, self.coll.allgather_slices(sc, p.user_slices, m.num_users)
                 return out_ids
@@ -259,15 +277,27 @@ class CudaBackend:
         return engine.propagate(model.graph, model.embeddings.weight, model.alpha, model.num_layers,
                                 row_ranges=my_ranges, exchange=exchange, exchange_final=exchange_final)
 
-    def local_topk(self, sharded, ue, ie_shard, item_begin, k):
+    def local_topk(self, sharded, ue, ie_shard, item_begin, k, defer=False):
         from . import engine
         from .scorer import FusedScorer
         ie_shard = ie_shard.contiguous()
         ue = ue.contiguous()
         if FusedScorer.supports(ue.size(1), k, ie_shard.size(0)):
             sharded._scorer = FusedScorer(ue, ie_shard, item_begin=item_begin)
-            return sharded._scorer.topk(None, k)
+            return sharded._scorer.topk(None, k, defer=defer)
+        sharded._scorer = None
         return engine.topk_exact(ue, ie_shard, None, k, item_begin=item_begin)
+
+    def pending_flag(self, sharded, device) -> torch.Tensor:
+        """int64 [1] on the device: 1 when this rank's enqueued fallback leaves work for tier 3."""
+        sc = sharded._scorer
+        if sc is None or sc._pending is None:
+            return torch.zeros(1, dtype=torch.int64, device=device)
+        f = sc._pending["flags"]
+        return ((f[0] > sc._pending["slots"]) | (f[1] > 0)).to(torch.int64).view(1)
+
+    def finalize_topk(self, sharded) -> bool:
+        return sharded._scorer.finalize() if sharded._scorer is not None else False
 
     def merge(self, ids, scores):
         from . import engine

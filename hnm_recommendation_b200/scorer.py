@@ -23,8 +23,8 @@ SIG_WORDS = 32                 # HNM_FUSED_SIG_WORDS
 K_MAX = 16
 SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maximum
 MAX_USERS_PER_LAUNCH = 1 << 21
-TIER2_MIN_USERS = 192           # fewer uncertified users go straight to the exact kernel (measured: 2.4 ms per thousand
-                                # users at the H&M catalog; the second tensor pass costs ~0.5 ms at any count)
+TIER2_MIN_USERS = 32            # fewer uncertified users go straight to the exact kernel
+TIER2_SLOTS = 2048              # size of the second pass when it is enqueued without knowing the count (no host sync)
 
 
 class FusedScorer:
@@ -62,7 +62,7 @@ class FusedScorer:
 
     def topk(self, user_ids: Optional[torch.Tensor], k: int, filter_items=None,
              fallback: bool = True, out_host: Optional[torch.Tensor] = None,
-             chunk_users: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+             chunk_users: Optional[int] = None, defer: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """ids [B,k] int64 (global item indices), scores [B,k] fp64; canonical (score desc, id asc).
 
         Three tiers, each only for the users the previous one could not certify:
@@ -78,12 +78,20 @@ class FusedScorer:
         out_host (pinned int64 [B, k]): the ids are also delivered to the host, chunk of users by chunk of
         users on a copy stream while the next chunk is being scored; the few rows the fallback tiers rewrite
         are patched afterwards.  The call returns with out_host complete.
+
+        Without a filter and without out_host the whole call is enqueued WITHOUT a host synchronisation: the
+        second tier runs on a fixed number of slots filled by a device-side compaction of the uncertified users,
+        and the two counters that say whether anything is left (more uncertified users than slots, or users the
+        second tier could not certify either) are read once, at the end -- by this call, or, with defer=True, by
+        ``finalize()``, which the caller invokes after it has enqueued whatever follows (the sharded form
+        launches its result all-gather first).  ``finalize()`` returns True when it had to patch rows.
         """
         dev = self.item_emb.device
         uids = engine._norm_ids(user_ids, self.user_emb.size(0), dev)
         total = uids.numel() if uids is not None else int(self.user_emb.size(0))
-        ids = torch.empty(total, k, dtype=torch.int64, device=dev)
-        sc = torch.empty(total, k, dtype=torch.float64, device=dev)
+        ids_full = torch.empty(total + 1, k, dtype=torch.int64, device=dev)      # + one spare row, see _enqueue_fallback
+        sc_full = torch.empty(total + 1, k, dtype=torch.float64, device=dev)
+        ids, sc = ids_full[:total], sc_full[:total]
         cert = torch.empty(total, dtype=torch.int32, device=dev)
         excl = (None, None)
         full_csr = isinstance(filter_items, tuple)
@@ -110,7 +118,14 @@ class FusedScorer:
                     out_host[b0:b1].copy_(ids[b0:b1], non_blocking=True)
         self.last_stats = {"users": total, "uncertified": 0, "tier2": 0, "tier3": 0}
         why = None
+        self._pending = None
         self._mark("fallback_begin")
+        if fallback and total and filter_items is None and out_host is None and not self.profile:
+            self._enqueue_fallback(uids, total, k, ids_full, sc_full, cert)
+            self._mark("fallback_end")
+            if not defer:
+                self.finalize()
+            return ids, sc
         if fallback and total:
             bad = (cert != 1).nonzero().view(-1)
             n_bad = int(bad.numel())
@@ -165,6 +180,52 @@ class FusedScorer:
                     ms[n0[:-6]] = ms.get(n0[:-6], 0.0) + e0.elapsed_time(e1)
             self.stage_ms = ms
         return ids, sc
+
+    def _enqueue_fallback(self, uids, total, k, ids_full, sc_full, cert) -> None:
+        """Tier 2 on a fixed number of slots, no host round trip (see topk).  ids_full / sc_full carry one spare
+        row at index `total` that absorbs the write-back of the unused slots."""
+        dev = self.item_emb.device
+        slots = min(total, TIER2_SLOTS)
+        sel2 = min(32, k + 12)
+        bad = torch.nonzero_static(cert != 1, size=slots, fill_value=-1).view(-1)       # device-side compaction
+        valid = bad >= 0
+        safe = bad.clamp(min=0)
+        bad_uids = safe if uids is None else uids[safe]
+        ids2 = torch.empty(slots, k, dtype=torch.int64, device=dev)
+        sc2 = torch.empty(slots, k, dtype=torch.float64, device=dev)
+        cert2 = torch.empty(slots, dtype=torch.int32, device=dev)
+        self._launch(bad_uids, 0, slots, k, sel2, (None, None), ids2, sc2, cert2, mark=False)
+        tgt = torch.where(valid, bad, torch.full_like(bad, total))
+        ids_full.index_copy_(0, tgt, ids2)
+        sc_full.index_copy_(0, tgt, sc2)
+        flags = torch.stack([(cert != 1).sum(), ((cert2 != 1) & valid).sum()])
+        self._pending = dict(uids=uids, total=total, k=k, ids=ids_full[:total], sc=sc_full[:total], cert=cert, bad=bad,
+                             valid=valid, cert2=cert2, flags=flags, slots=slots)
+
+    def finalize(self) -> bool:
+        """Read the two counters of the enqueued fallback (the call's only host synchronisation) and handle what
+        the fixed-size second tier left: users beyond its slots, users it could not certify (tier 3)."""
+        p, self._pending = self._pending, None
+        if p is None:
+            return False
+        n_bad, n_left = (int(x) for x in p["flags"].tolist())
+        self.last_stats.update({"uncertified": n_bad, "tier2": min(n_bad, p["slots"]), "tier3": 0})
+        if n_bad <= p["slots"] and n_left == 0:
+            return False
+        dev = self.item_emb.device
+        ids, sc, cert, uids, k = p["ids"], p["sc"], p["cert"], p["uids"], p["k"]
+        fixed = torch.zeros(p["total"], dtype=torch.bool, device=dev)
+        ok2 = p["valid"] & (p["cert2"] == 1)
+        fixed[p["bad"][ok2]] = True
+        rest = ((cert != 1) & ~fixed).nonzero().view(-1)
+        if rest.numel():
+            rest_uids = rest if uids is None else uids[rest]
+            e_ids, e_sc = engine.topk_exact(self.user_emb, self.item_emb, rest_uids, k, (None, None),
+                                            item_begin=self.item_begin)
+            ids[rest] = e_ids
+            sc[rest] = e_sc
+            self.last_stats["tier3"] = int(rest.numel())
+        return True
 
     def _exclusions(self, uids: torch.Tensor, filter_items):
         """Exclusion CSR over the listed users: from the reference's dict, or sliced out of an all-users CSR."""

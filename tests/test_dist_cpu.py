@@ -41,9 +41,15 @@ class OracleBackend:
         exchange_final(acc)
         return acc
 
-    def local_topk(self, sharded, ue, ie_shard, item_begin, k):
+    def local_topk(self, sharded, ue, ie_shard, item_begin, k, defer=False):
         ids, sc = O.recommend_exact(ue, ie_shard.contiguous(), torch.arange(ue.size(0)), k)
         return ids + item_begin, sc
+
+    def pending_flag(self, sharded, device):
+        return torch.zeros(1, dtype=torch.int64, device=device)
+
+    def finalize_topk(self, sharded):
+        return False
 
     def merge(self, ids, scores):
         g, n, k = ids.shape
