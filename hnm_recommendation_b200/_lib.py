@@ -32,12 +32,12 @@ _SIGNATURES = {
     "hnm_graph_build_workspace_bytes": (SZ, [I64, I64, C.c_int]),
     "hnm_graph_build": (C.c_int, [P, P, P, I64, I64, P, P, P, P, I32, P, P, P, SZ, P]),
     "hnm_lightgcn_prescale": (C.c_int, [P, P, F32, P, P, I64, I32, P]),
-    "hnm_lightgcn_layer": (C.c_int, [P, P, P, P, P, P, P, F32, I64, I32, I64, I64, P, I32, I32, I32, P]),
+    "hnm_lightgcn_layer": (C.c_int, [P, P, P, P, P, P, P, F32, I64, I32, I64, I64, P, I32, I32, I32, I32, P]),
     "hnm_lightgcn_partial": (C.c_int, [P, P, P, P, P, P, I32, I64, I64, P, I32, I32, I32, I32, P]),
     "hnm_lightgcn_finish": (C.c_int, [P, P, P, F32, P, P, I64, I64, I32, P]),
     "hnm_lightgcn_partial_peer": (C.c_int, [P, P, P, P, P, P, I32, I32, I32, I64, I64, P, I32, I32, I32, P]),
     "hnm_lightgcn_finish_peer": (C.c_int, [P, I32, I32, I32, P, P, F32, P, P, P, I64, I64, I32, P]),
-    "hnm_pair_scores": (C.c_int, [P, P, P, P, I64, I32, I64, I64, P, P]),
+    "hnm_pair_scores": (C.c_int, [P, P, P, P, I64, I32, I64, I64, P, P, P]),
     "hnm_score_all_items": (C.c_int, [P, P, P, I64, I64, I32, P, P]),
     "hnm_topk_exact": (C.c_int, [P, P, P, I64, I64, I64, I32, I32, P, P, I32, P, P, P]),
     "hnm_score_pack_items": (C.c_int, [P, I64, I64, I32, P, P, P, P]),

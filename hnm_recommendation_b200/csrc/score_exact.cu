@@ -21,7 +21,7 @@ __global__ void pair_scores_kernel(const float* __restrict__ ue, const float* __
   int64_t u = uids[b], i = iids[b];
   if (u < 0) u += nu;   // torch indexing accepts negative indices
   if (i < 0) i += ni;
-  if (u < 0 || u >= nu || i < 0 || i >= ni) { if (lane == 0) { atomicExch(bad, 1); out[b] = nanf(""); } return; }
+  if (u < 0 || u >= nu || i < 0 || i >= ni) { if (lane == 0) { if (bad) atomicExch(bad, 1); out[b] = nanf(""); } return; }
   const float* pu = ue + (size_t)u * dim;
   const float* pi = ie + (size_t)i * dim;
   float s = 0.f;
@@ -309,24 +309,19 @@ __global__ void merge_topk_kernel(const int64_t* __restrict__ in_ids, const doub
 
 extern "C" int hnm_pair_scores(const float* user_emb, const float* item_emb, const int64_t* user_ids,
                                const int64_t* item_ids, int64_t batch, int32_t dim, int64_t num_users,
-                               int64_t num_items, float* out, void* stream_) {
+                               int64_t num_items, float* out, int32_t* out_of_range, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (batch == 0) return HNM_OK;
   if (!user_emb || !item_emb || !user_ids || !item_ids || !out) return HNM_E_NULL;
   if (batch < 0 || dim <= 0) return HNM_E_RANGE;
-  int* bad = nullptr;
-  HNM_CUDA_TRY(cudaMallocAsync(&bad, sizeof(int), stream));
-  HNM_CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+  // Asynchronous and capturable: the indices are validated by the caller (engine.pair_scores, like every other
+  // entry point); an out-of-range pair yields NaN in its slot (and `out_of_range`, a caller-provided device flag
+  // that may be NULL, is raised) instead of a device-side malloc + read-back + stream synchronisation per call.
   const int wpc = 8;
   pair_scores_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
-      user_emb, item_emb, user_ids, item_ids, batch, dim, num_users, num_items, out, bad);
-  cudaError_t le = cudaGetLastError();
-  int host_bad = 0;
-  cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
-  cudaStreamSynchronize(stream);
-  cudaFreeAsync(bad, stream);
-  if (le != cudaSuccess) return (int)le;
-  return host_bad ? HNM_E_RANGE : HNM_OK;
+      user_emb, item_emb, user_ids, item_ids, batch, dim, num_users, num_items, out, out_of_range);
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
 }
 
 extern "C" int hnm_score_all_items(const float* user_emb, const float* item_emb, const int64_t* user_ids,

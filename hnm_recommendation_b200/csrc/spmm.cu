@@ -175,6 +175,162 @@ spmm_rows_kernel(Seg seg, int partial, const int32_t* __restrict__ col, const fl
   }
 }
 
+// ---- short rows (the user rows: 24 entries on average at the H&M shape) --------------------------------------
+// With one row at a time a warp pays two dependent round trips (row pointer -> column indices) before it can
+// issue the ~1.5 batches of gathers of an average user row: the user side ran at 10 TB/s where the same gathers
+// stream at 19-21 TB/s when the indices are simply there (tools/bench_l2_gather.cu, uniform and Zipf).  Here a
+// warp takes 8 consecutive rows: one coalesced load brings their 9 row pointers (and 8 dis values), one sweep
+// brings ALL their column indices (contiguous in the CSR) into shared memory, and the rows are then gathered
+// back to back with the indices read as shared-memory broadcasts.  Groups with more than kStageCap entries
+// (or a long row inside) fall back to the per-row path.
+constexpr int kStageRows = 8;
+constexpr int kStageCap = 512;
+
+template <int D, bool WEIGHTED>
+__device__ __forceinline__ void staged_gather(const int* __restrict__ s_col, const float* __restrict__ s_w,
+                                              const float* __restrict__ xs, int cnt, int lane,
+                                              float4 (&acc)[Shape<D>::VEC]) {
+  using S = Shape<D>;
+  const int g = lane / S::LPR;
+  const int sub = lane % S::LPR;
+#pragma unroll
+  for (int t = 0; t < S::VEC; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = 0; j0 < cnt; j0 += S::G * S::UNROLL) {
+    float4 v[S::UNROLL][S::VEC];
+    float wj[S::UNROLL];
+#pragma unroll
+    for (int u = 0; u < S::UNROLL; ++u) {
+      const int j = j0 + u * S::G + g;
+      const bool ok = j < cnt;
+      const int cj = s_col[ok ? j : 0];
+      if (WEIGHTED) wj[u] = ok ? s_w[j] : 0.f;
+      const float* p = xs + (size_t)cj * D + sub * 4;
+#pragma unroll
+      for (int t = 0; t < S::VEC; ++t)
+        v[u][t] = ok ? ldg_f4(p + t * S::LPR * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < S::UNROLL; ++u) {
+#pragma unroll
+      for (int t = 0; t < S::VEC; ++t) {
+        if (WEIGHTED) fma4(acc[t], wj[u], v[u][t]);
+        else add4(acc[t], v[u][t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = S::LPR; off < 32; off <<= 1) {
+#pragma unroll
+    for (int t = 0; t < S::VEC; ++t) {
+      acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, off);
+      acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, off);
+      acc[t].z += __shfl_xor_sync(0xffffffffu, acc[t].z, off);
+      acc[t].w += __shfl_xor_sync(0xffffffffu, acc[t].w, off);
+    }
+  }
+}
+
+template <int D, bool WEIGHTED, int WPC>
+__global__ void __launch_bounds__(WPC * 32)
+spmm_rows_staged_kernel(const int32_t* __restrict__ rowptr, int partial, const int32_t* __restrict__ col,
+                        const float* __restrict__ w, const float* __restrict__ dis, const float* __restrict__ xs_in,
+                        float* __restrict__ xs_out, float* __restrict__ accbuf, float alpha, int64_t row_begin,
+                        int64_t row_end, int32_t heavy_threshold) {
+  using S = Shape<D>;
+  __shared__ int s_col[WPC][kStageCap];
+  __shared__ float s_w[WEIGHTED ? WPC : 1][WEIGHTED ? kStageCap : 1];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t first = row_begin + ((int64_t)blockIdx.x * WPC + warp) * kStageRows;
+  if (first >= row_end) return;
+  const int nrows = (int)min((int64_t)kStageRows, row_end - first);
+  const int rp = lane <= nrows ? __ldg(rowptr + first + lane) : 0;
+  const float dv = lane < nrows ? __ldg(dis + first + lane) : 0.f;
+  const int beg = __shfl_sync(0xffffffffu, rp, 0);
+  const int total = __shfl_sync(0xffffffffu, rp, nrows) - beg;
+  const bool staged = total <= kStageCap;
+  if (staged) {
+    for (int i = lane; i < total; i += 32) {
+      s_col[warp][i] = __ldg(col + beg + i);
+      if (WEIGHTED) s_w[warp][i] = __ldg(w + beg + i);
+    }
+    __syncwarp();
+  }
+  const Seg seg{rowptr, rowptr + 1, 0, nullptr, 1, 0};
+  if (staged) {
+    // G = 32 / LPR rows side by side, one per lane group (d = 64: one row per half warp): every group walks its
+    // own row with UNROLL gathers in flight per lane, so a 24-entry row is three full batches of 8 instead of
+    // one and a half batches of 16, and no partial sums cross the groups.
+    const int g = lane / S::LPR;
+    const int sub = lane % S::LPR;
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrows; r0 += S::G) {
+      const int r = min(r0 + g, nrows - 1);                    // (a group past the last row repeats it, unused)
+      const int b = __shfl_sync(0xffffffffu, rp, r), e = __shfl_sync(0xffffffffu, rp, r + 1);
+      const bool mine = r0 + g < nrows && e - b <= heavy_threshold;     // long rows: summed by the long-row kernels
+      const int cnt = mine ? e - b : 0;
+      int maxcnt = cnt;
+#pragma unroll
+      for (int off = S::LPR; off < 32; off <<= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, off));
+      const int* sc = s_col[warp] + (b - beg);
+      float4 acc[S::VEC];
+#pragma unroll
+      for (int t = 0; t < S::VEC; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j0 = 0; j0 < maxcnt; j0 += S::UNROLL) {
+        float4 v[S::UNROLL][S::VEC];
+        float wj[S::UNROLL];
+#pragma unroll
+        for (int u = 0; u < S::UNROLL; ++u) {
+          const int j = j0 + u;
+          const bool ok = j < cnt;
+          const int cj = sc[ok ? j : 0];
+          if (WEIGHTED) wj[u] = ok ? s_w[warp][(b - beg) + j] : 0.f;
+          const float* p = xs_in + (size_t)cj * D + sub * 4;
+#pragma unroll
+          for (int t = 0; t < S::VEC; ++t)
+            v[u][t] = ok ? ldg_f4(p + t * S::LPR * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < S::UNROLL; ++u) {
+#pragma unroll
+          for (int t = 0; t < S::VEC; ++t) {
+            if (WEIGHTED) fma4(acc[t], wj[u], v[u][t]);
+            else add4(acc[t], v[u][t]);
+          }
+        }
+      }
+      const float di = __shfl_sync(0xffffffffu, dv, r);
+      if (mine) {
+        const int64_t row = first + r;
+        float* orow = seg.out_row(xs_out, row, D, partial);
+#pragma unroll
+        for (int t = 0; t < S::VEC; ++t) {
+          const size_t c = (size_t)(t * S::LPR + sub) * 4;
+          row_epilogue(acc[t], di, alpha, orow ? orow + c : nullptr, accbuf + (size_t)row * D + c, partial);
+        }
+      }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int r = 0; r < nrows; ++r) {
+    const int b = __shfl_sync(0xffffffffu, rp, r), e = __shfl_sync(0xffffffffu, rp, r + 1);
+    if (e - b > heavy_threshold) continue;                    // summed by the long-row kernels
+    const int64_t row = first + r;
+    float4 acc[S::VEC];
+    warp_gather<D, WEIGHTED>(col, w, xs_in, b, e, lane, acc);
+    const float di = __shfl_sync(0xffffffffu, dv, r);
+    if (lane < S::LPR) {
+      float* orow = seg.out_row(xs_out, row, D, partial);
+#pragma unroll
+      for (int t = 0; t < S::VEC; ++t) {
+        const size_t c = (size_t)(t * S::LPR + lane) * 4;
+        row_epilogue(acc[t], di, alpha, orow ? orow + c : nullptr, accbuf + (size_t)row * D + c, partial);
+      }
+    }
+  }
+}
+
 // Long rows (more than heavy_threshold entries): one 512-thread CTA per row, warps take contiguous
 // 32-aligned chunks (coalesced col[] reads) and the partial sums are added in warp order.
 template <int D, bool WEIGHTED>
@@ -354,7 +510,7 @@ template <int D, bool WEIGHTED>
 int launch_layer(Seg seg, int partial, const int32_t* col, const float* w, const float* dis, const float* xs_in,
                  float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
                  const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge, int32_t heavy_threshold,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int short_rows = 0) {
   // The long rows run on a side stream next to the warp-per-row kernel (they touch disjoint output
   // rows); fork/join with events so the caller still sees one stream-ordered operation.
   cudaStream_t main_stream = stream;
@@ -390,6 +546,17 @@ int launch_layer(Seg seg, int partial, const int32_t* col, const float* w, const
       spmm_rows_kernel<D, WEIGHTED, WPC, RPW><<<grid, (WPC)*32, 0, stream>>>(seg, partial, col, w, dis, xs_in, xs_out, acc, \
                                                                              alpha, row_begin, row_end, thr); \
   }
+  if (short_rows && !(partial & 1) && seg.e == seg.b + 1 && seg.off == 0 && variant == 0) {
+    constexpr int WPC = 4;
+    const int64_t per_cta = (int64_t)WPC * kStageRows;
+    const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);
+    if (grid > 0)
+      spmm_rows_staged_kernel<D, WEIGHTED, WPC><<<grid, WPC * 32, 0, stream>>>(seg.b, partial, col, w, dis, xs_in, xs_out,
+                                                                               acc, alpha, row_begin, row_end, thr);
+    HNM_LAUNCH_CHECK();
+    if (side) HNM_CUDA_TRY(cudaStreamWaitEvent(main_stream, side->join, 0));
+    return HNM_OK;
+  }
   switch (variant) {
     // small CTAs retire (and free their warp slots) at a finer grain: 2 warps x 4 rows measured best
     // at the H&M shape (6.28 ms / 3 layers vs 7.32 ms for 8 x 4; profiles/r1_spmm_notes.md)
@@ -408,11 +575,11 @@ template <bool WEIGHTED>
 int dispatch_layer(int dim, Seg seg, int partial, const int32_t* col, const float* w, const float* dis,
                    const float* xs_in, float* xs_out, float* acc, float alpha, int64_t row_begin, int64_t row_end,
                    const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge, int32_t heavy_threshold,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int short_rows = 0) {
 #define HNM_CASE(DD)                                                                                          \
   case DD:                                                                                                    \
     return launch_layer<DD, WEIGHTED>(seg, partial, col, w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,   \
-                                      heavy_rows, num_heavy, num_huge, heavy_threshold, stream)
+                                      heavy_rows, num_heavy, num_huge, heavy_threshold, stream, short_rows)
   switch (dim) {
     HNM_CASE(8);
     HNM_CASE(16);
@@ -460,7 +627,7 @@ extern "C" int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_
                                   const float* dis, const float* xs_in, float* xs_out, float* acc, float alpha,
                                   int64_t num_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
                                   const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge,
-                                  int32_t heavy_threshold, void* stream_) {
+                                  int32_t heavy_threshold, int32_t short_rows, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!csr_rowptr || !csr_col || !dis || !xs_in || !acc) return HNM_E_NULL;
   if (num_heavy > 0 && !heavy_rows) return HNM_E_NULL;
@@ -474,9 +641,9 @@ extern "C" int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_
   static const int red_mode = (getenv("HNM_SPMM_RED") ? atoi(getenv("HNM_SPMM_RED")) : 1) ? 2 : 0;
   if (csr_w)
     return dispatch_layer<true>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0, nullptr, 1, 0}, red_mode, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
-                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
+                                heavy_rows, num_heavy, num_huge, heavy_threshold, stream, short_rows);
   return dispatch_layer<false>(dim, Seg{csr_rowptr, csr_rowptr + 1, 0, nullptr, 1, 0}, red_mode, csr_col, csr_w, dis, xs_in, xs_out, acc, alpha, row_begin, row_end,
-                               heavy_rows, num_heavy, num_huge, heavy_threshold, stream);
+                               heavy_rows, num_heavy, num_huge, heavy_threshold, stream, short_rows);
 }
 
 

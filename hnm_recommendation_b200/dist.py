@@ -1,12 +1,18 @@
 """Multi-GPU form of the hot path: one process per GPU, torch.distributed for the plumbing.
 
-No counterpart in the reference (single device, scripts/train.py:233-234); the partitioning is the
-one BASELINE.json's north_star prescribes:
+No counterpart in the reference (single device, scripts/train.py:233-234).  BASELINE.json's north_star
+prescribes item-catalog shards + allgather + merge for the scoring and row shards + allgather for the
+propagation; both are implemented (mode "items", the row-sliced propagation), but the DEFAULT is the
+user partitioning below, which moves 13x fewer bytes per layer and lets every stage shrink as 1/G
+(the north_star form is timed beside it in every multi-GPU bench line as items_mode_ms):
 
   * propagation: the USERS are partitioned.  A rank computes its own user rows (they gather from the
     item block, which every rank holds) and, for every item row, the partial neighbour sum over its own
-    users; one all-reduce per layer adds the partial sums (27 MB at the H&M shape -- an all-gather of
-    the user block would move 351 MB), then every rank normalises the item block locally;
+    users; the partial sums (27 MB at the H&M shape -- an all-gather of the user block would move 351 MB)
+    are exchanged inside the kernels over NVLink peer memory -- stored straight into the owning rank's
+    staging buffer, reduced there in rank order and written back into every rank's table
+    (engine.propagate_user_sharded_peer) -- or, with HNM_PEER_EXCHANGE=0 / on gloo, by one all-reduce per
+    layer followed by a local finish pass;
   * scoring, mode "items" (north_star): the item catalog is sharded; each rank runs the fused
     score/select + exact rescoring against its item shard for ALL users, the per-shard exact top-k
     lists are exchanged (all-to-all by user slice), merged by (score desc, item id asc), and the
@@ -338,8 +344,7 @@ def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) ->
         def layer():
             # one layer's kernels on this rank (no communication)
             if chunks is not None:
-                call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
-                     0.25, n, d, 0, U, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
+                engine.layer_call(g, xs, xo, acc, 0.25, 0, U, stream())
                 for c, sh in enumerate(chunks.chunks):
                     call("hnm_lightgcn_partial", ptr(sh.seg_begin), ptr(sh.seg_end), ptr(g.col), ptr(g.w), ptr(xs),
                          ptr(part), d, U, n, ptr(sh.heavy_rows) if sh.heavy_rows.numel() else None,
@@ -347,12 +352,10 @@ def profile_stages(model, sharded: Optional[ShardedLightGCN], steps: int = 3) ->
                 call("hnm_lightgcn_finish", ptr(part), ptr(xs), ptr(g.dis), 0.25, ptr(xo), ptr(acc), U, n - U, d, stream())
                 return
             if shard is None:
-                call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
-                     0.25, n, d, 0, n, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
+                engine.layer_call(g, xs, xo, acc, 0.25, 0, n, stream())
                 return
             if shard.u1 > shard.u0:
-                call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc),
-                     0.25, n, d, shard.u0, shard.u1, heavy, g.num_heavy, g.num_huge, g.heavy_threshold, stream())
+                engine.layer_call(g, xs, xo, acc, 0.25, shard.u0, shard.u1, stream())
             call("hnm_lightgcn_partial", ptr(shard.seg_begin), ptr(shard.seg_end), ptr(g.col), ptr(g.w), ptr(xs),
                  ptr(part), d, U, n, ptr(shard.heavy_rows) if shard.heavy_rows.numel() else None,
                  int(shard.heavy_rows.numel()), shard.num_huge, g.heavy_threshold, 0, stream())

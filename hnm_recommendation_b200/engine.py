@@ -35,6 +35,8 @@ class Graph:
     heavy_rows: torch.Tensor      # int32 [H], the num_huge very long rows first
     heavy_threshold: int = HEAVY_THRESHOLD
     num_huge: int = 0             # rows with more than HUGE_ROW entries (summed by a CTA cluster)
+    short_prefix: int = 0         # rows [0, short_prefix) are short on average (the user rows of a bipartite graph):
+                                  # they take the staged 8-rows-per-warp kernel (hnm_lightgcn_layer short_rows = 1)
 
     @property
     def num_heavy(self) -> int:
@@ -76,6 +78,23 @@ def build_graph(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n
     return Graph(num_nodes, nnz, rowptr, col, w, dis, heavy_rows.contiguous(), heavy_threshold, num_huge)
 
 
+def layer_call(graph: Graph, cur: torch.Tensor, nxt: Optional[torch.Tensor], acc: torch.Tensor, alpha: float, r0: int,
+          r1: int, s) -> None:
+    """One hnm_lightgcn_layer call over rows [r0, r1), split at graph.short_prefix so that the short (user) rows
+    take the staged kernel and the long (item) rows the row-at-a-time one."""
+    n, d = cur.shape
+    parts = [(r0, r1, 0)]
+    sp = graph.short_prefix
+    if r0 < sp:
+        parts = [(r0, min(r1, sp), 1)] + ([(sp, r1, 0)] if r1 > sp else [])
+    for a, b, short in parts:
+        if b > a:
+            call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
+                 None if nxt is None else ptr(nxt), ptr(acc), float(alpha), n, d, a, b,
+                 ptr(graph.heavy_rows) if graph.num_heavy else None, graph.num_heavy, graph.num_huge,
+                 graph.heavy_threshold, short, s)
+
+
 def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layers: int,
               row_ranges: Optional[Sequence[Tuple[int, int]]] = None, exchange=None,
               exchange_final=None, item_chunks: Optional["ItemChunks"] = None) -> torch.Tensor:
@@ -107,10 +126,7 @@ def propagate(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], num_layer
         for layer in range(1, num_layers + 1):
             last = layer == num_layers
             for r0, r1 in ranges:
-                call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
-                     None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, r0, r1,
-                     ptr(graph.heavy_rows) if graph.num_heavy else None, graph.num_heavy, graph.num_huge,
-                     graph.heavy_threshold, s)
+                layer_call(graph, cur, None if last else nxt, acc, alphas[layer], r0, r1, s)
             if not last:
                 if exchange is not None:
                     exchange(nxt)
@@ -180,22 +196,18 @@ def _norm_ids(ids: Optional[torch.Tensor], limit: int, device) -> Optional[torch
 
 
 def pair_scores(user_emb, item_emb, user_ids, item_ids) -> torch.Tensor:
-    """LightGCN.predict tail (lightgcn.py:180-184)."""
+    """LightGCN.predict tail (lightgcn.py:180-184).  Indices are validated here (as for every other entry point),
+    so the kernel call itself stays asynchronous."""
     _lib.require_device()
     dev = user_emb.device
-    u = user_ids.to(device=dev, dtype=torch.int64).contiguous().view(-1)
-    i = item_ids.to(device=dev, dtype=torch.int64).contiguous().view(-1)
+    u = _norm_ids(user_ids, user_emb.size(0), dev)
+    i = _norm_ids(item_ids, item_emb.size(0), dev)
     if u.numel() != i.numel():
         raise RuntimeError("user_ids and item_ids must have the same length")
     out = torch.empty(u.numel(), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        try:
-            call("hnm_pair_scores", ptr(user_emb), ptr(item_emb), ptr(u), ptr(i), u.numel(), user_emb.size(1),
-                 user_emb.size(0), item_emb.size(0), ptr(out), stream())
-        except _lib.HnmError as e:
-            if e.code == -2:
-                raise IndexError("index out of range in self") from None
-            raise
+        call("hnm_pair_scores", ptr(user_emb), ptr(item_emb), ptr(u), ptr(i), u.numel(), user_emb.size(1),
+             user_emb.size(0), item_emb.size(0), ptr(out), None, stream())
     return out
 
 
@@ -351,9 +363,7 @@ def _propagate_chunked(graph: Graph, e0: torch.Tensor, alphas: Sequence[float], 
         heavy = ptr(graph.heavy_rows) if graph.num_heavy else None
         for layer in range(1, num_layers + 1):
             last = layer == num_layers
-            call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
-                 None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, 0, U, heavy, graph.num_heavy,
-                 graph.num_huge, graph.heavy_threshold, s)
+            layer_call(graph, cur, None if last else nxt, acc, alphas[layer], 0, U, s)
             for c, sh in enumerate(ic.chunks):
                 call("hnm_lightgcn_partial", ptr(sh.seg_begin), ptr(sh.seg_end), ptr(graph.col), ptr(graph.w), ptr(cur),
                      ptr(part), d, U, n, ptr(sh.heavy_rows) if sh.heavy_rows.numel() else None,
@@ -407,9 +417,7 @@ def propagate_user_sharded(graph: Graph, shard: UserShard, e0: torch.Tensor, alp
             # need neither `part` nor the other ranks, are gathered while the partial sums travel
             pending = allreduce_items(part)
             if u1 > u0:
-                call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
-                     None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, u0, u1, heavy, graph.num_heavy,
-                     graph.num_huge, graph.heavy_threshold, s)
+                layer_call(graph, cur, None if last else nxt, acc, alphas[layer], u0, u1, s)
             if pending is not None:
                 pending.wait()
             call("hnm_lightgcn_finish", ptr(part), ptr(cur), ptr(graph.dis), float(alphas[layer]),
@@ -480,9 +488,7 @@ def propagate_user_sharded_peer(graph: Graph, shard: UserShard, e0: torch.Tensor
                  ptr(cur), pb.h_stage.buffer_ptrs_dev, pb.rpo, pb.rank, d, U, n, sh_heavy,
                  int(shard.heavy_rows.numel()), shard.num_huge, graph.heavy_threshold, s)
             if u1 > u0:       # this rank's user rows need neither the partial sums nor the other ranks
-                call("hnm_lightgcn_layer", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(graph.dis), ptr(cur),
-                     None if last else ptr(nxt), ptr(acc), float(alphas[layer]), n, d, u0, u1, heavy, graph.num_heavy,
-                     graph.num_huge, graph.heavy_threshold, s)
+                layer_call(graph, cur, None if last else nxt, acc, alphas[layer], u0, u1, s)
             pb.h_stage.barrier(channel=0)                 # every rank's partial sums have landed
             call("hnm_lightgcn_finish_peer", ptr(pb.stage), pb.world, pb.rpo, pb.rank, ptr(cur), ptr(graph.dis),
                  float(alphas[layer]), None if last else pb.handle(nxt).buffer_ptrs_dev, ptr(acc),

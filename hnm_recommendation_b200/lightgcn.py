@@ -111,6 +111,8 @@ class LightGCN(ModelBase):
         self.edge_index = edge_index
         self.edge_weight = edge_weight
         self.graph = engine.build_graph(edge_index, edge_weight, self.num_nodes, self.embeddings.weight.device)
+        if engine.is_bipartite(self.graph, self.num_users):
+            self.graph.short_prefix = self.num_users        # user rows: the staged short-row kernel
         # item rows gather from the user block; when that does not fit the L2 they are walked chunk by chunk
         self._item_chunks = engine.make_item_chunks(self.graph, self.num_users, self.num_items, self.embedding_dim)
         self._cache_key = None

@@ -93,7 +93,11 @@ HNM_API int hnm_lightgcn_layer(const int32_t* csr_rowptr, const int32_t* csr_col
                        const float* dis, const float* xs_in, float* xs_out, float* acc, float alpha,
                        int64_t num_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
                        const int32_t* heavy_rows, int32_t num_heavy, int32_t num_huge,
-                       int32_t heavy_threshold, void* stream);
+                       int32_t heavy_threshold,
+                       int32_t short_rows /* 1: the rows of the range are short on average (user rows): a warp takes 8
+                                             consecutive rows and stages all their column indices in shared memory
+                                             with one sweep; 0: one row at a time */,
+                       void* stream);
 #define HNM_HUGE_ROW 8192
 
 /* User-sharded propagation (no reference counterpart; one process per GPU).  A rank that owns the
@@ -141,11 +145,13 @@ HNM_API int hnm_lightgcn_finish_peer(const float* stage /* this rank's [world][r
 
 /* ------------------------------------------------------------------------
  * LightGCN.predict                              src/models/lightgcn.py:180-184
- * out[b] = dot(user_emb[user_ids[b]], item_emb[item_ids[b]]) in fp32.
+ * out[b] = dot(user_emb[user_ids[b]], item_emb[item_ids[b]]) in fp32.  Asynchronous on `stream` (no read-back):
+ * negative indices count from the end like torch indexing; a pair whose index is out of range gets NaN and
+ * raises *out_of_range (device int32 zeroed by the caller, may be NULL).
  * ---------------------------------------------------------------------- */
 HNM_API int hnm_pair_scores(const float* user_emb, const float* item_emb, const int64_t* user_ids,
                     const int64_t* item_ids, int64_t batch, int32_t dim, int64_t num_users,
-                    int64_t num_items, float* out, void* stream);
+                    int64_t num_items, float* out, int32_t* out_of_range, void* stream);
 
 /* ------------------------------------------------------------------------
  * LightGCN.predict_all_items                    src/models/lightgcn.py:199-202

@@ -27,6 +27,22 @@ __global__ void fill_table(float* t, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     t[i] = (float)(i & 1023) * 1e-3f;
 }
+// Zipf-like popularity as in hnm_recommendation_b200/synth.py: P(rank r) ~ 1 / (r + 100); the ranks are scattered
+// over the table by a multiplicative hash so that popular rows are not neighbours.  Inverse CDF of the continuous
+// approximation: r = (R + 100)^u * 100^(1-u) - 100.
+__global__ void fill_idx_zipf(int* idx, size_t n, uint32_t rows, uint32_t seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint64_t z = (i + 1) * 0x9E3779B97F4A7C15ull + seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    double r = pow((double)rows + 100.0, u) * pow(100.0, 1.0 - u) - 100.0;
+    uint64_t rank = (uint64_t)fmin(fmax(r, 0.0), (double)rows - 1.0);
+    idx[i] = (int)((rank * 2654435761ull) % rows);
+  }
+}
+
 __global__ void fill_idx(int* idx, size_t n, uint32_t rows, uint32_t seed) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     uint64_t z = (i + 1) * 0x9E3779B97F4A7C15ull + seed;
@@ -212,6 +228,15 @@ int main() {
         cudaError_t e = cudaGetLastError();
         printf("  gather4  3 stages x 32 KB, 4 consumer warps, 2 CTAs per SM  : %.3f ms  %.2f TB/s  (%s)\n", ms, gb / ms,
                cudaGetErrorString(e));
+      }
+    }
+    if (rows == 105542u) {
+      // the same table read with the item popularity of the synthetic H&M graph (what the user rows of a layer do)
+      fill_idx_zipf<<<sms * 8, 256>>>(idx, n, rows, 777u);
+      CK(cudaDeviceSynchronize());
+      for (int ctas_per_sm : {4, 8}) {
+        float ms = time_ms([&] { gather_ldg<8><<<sms * ctas_per_sm, 256>>>(table, idx, n, out); }, 5);
+        printf("  ldg  ZIPF 8 rows in flight per lane, %d CTAs x 256 thr per SM : %.3f ms  %.2f TB/s\n", ctas_per_sm, ms, gb / ms);
       }
     }
     CK(cudaFree(table));

@@ -24,13 +24,15 @@ xs, xo, acc = torch.empty_like(w), torch.empty_like(w), torch.empty_like(w)
 call("hnm_lightgcn_prescale", ptr(w), ptr(g.dis), 0.25, ptr(xs), ptr(acc), n, d, stream())
 heavy = ptr(g.heavy_rows) if g.num_heavy else None
 
-def layer(r0, r1, with_heavy=True):
+def layer(r0, r1, with_heavy=True, short=0):
     call("hnm_lightgcn_layer", ptr(g.rowptr), ptr(g.col), ptr(g.w), ptr(g.dis), ptr(xs), ptr(xo), ptr(acc), 0.25, n, d,
          r0, r1, heavy if with_heavy else None, g.num_heavy if with_heavy else 0, g.num_huge if with_heavy else 0,
-         g.heavy_threshold, stream())
+         g.heavy_threshold, short, stream())
 
 print("all rows      %.3f ms" % ev_time(lambda: layer(0, n)))
 print("user rows     %.3f ms" % ev_time(lambda: layer(0, U)))
+print("user rows, staged 8-row kernel  %.3f ms" % ev_time(lambda: layer(0, U, short=1)))
+print("user rows, staged, no heavy launches  %.3f ms" % ev_time(lambda: layer(0, U, with_heavy=False, short=1)))
 print("item rows     %.3f ms" % ev_time(lambda: layer(U, n)))
 print("item rows, no heavy kernels (heavy rows skipped) %.3f ms" % ev_time(lambda: layer(U, n, True) if False else layer(U, n)))
 deg = (g.rowptr[1:] - g.rowptr[:-1]).long()
