@@ -43,7 +43,7 @@ _SIGNATURES = {
     "hnm_score_pack_items": (C.c_int, [P, I64, I64, I32, P, P, P, P]),
     "hnm_score_pack_users": (C.c_int, [P, P, I64, I64, I32, P, P, P]),
     "hnm_absmax": (C.c_int, [P, I64, P, I32, P, P]),
-    "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, P, I32, P, P, P, P, I64, P]),
+    "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, I32, P, I32, P, P, P, P, I64, P]),
     "hnm_exclusion_signature": (C.c_int, [P, P, I64, I64, I64, P, P]),
     "hnm_score_topk_fused_workspace_bytes": (C.c_int64, [I64, I64]),
     "hnm_score_topk_fused_plan": (C.c_int, [I64, I64, P]),
@@ -103,7 +103,7 @@ def call(fn: str, *args) -> None:
     global LAUNCHES
     check(fn, getattr(load(), fn)(*args))
     n = _LAUNCHES_PER_CALL.get(fn, 1)
-    if fn == "hnm_score_topk_fused" and args[13] > 256:
+    if fn == "hnm_score_topk_fused" and args[14] > 256:
         n = 2                                     # + merge of the per-slice candidate lists
     if fn == "hnm_lightgcn_partial" and args[10]:
         n = 2 + (1 if args[11] else 0)

@@ -43,7 +43,7 @@
 
 namespace {
 
-constexpr int kDim = HNM_FUSED_DIM;         // 64 fp16 = one 128-byte swizzle row
+constexpr int kDim = HNM_FUSED_DIM;         // K chunk: 64 fp16 = one 128-byte swizzle row; embedding dim = KC chunks
 constexpr int kUserTile = 128;              // UMMA M
 constexpr int kItemTile = 128;              // UMMA N
 constexpr int kBootTiles = 16;              // item tiles used to seed the bucket maxima (run twice)
@@ -62,7 +62,7 @@ constexpr int kMU = 2;                      // user tiles per CTA pass
 constexpr int kBUF = 2;                     // accumulators per user tile
 constexpr int kHalves = 2;                  // threads per user row (column halves of an accumulator)
 constexpr int kSlots = kMU * kBUF;
-constexpr int kStagesB = 6;
+constexpr int kStagesB = 6;                 // B ring (d = 64); the wider shapes take what the A tiles leave
 constexpr int kEpiWarps = 4 * kMU * kHalves;      // 16
 constexpr int kThreads = (4 + kEpiWarps) * 32;    // 640
 constexpr int kHalfBuckets = kNumBuckets / kHalves;
@@ -80,6 +80,17 @@ struct __align__(8) Barriers {
   uint64_t t_full[kSlots], t_empty[kSlots];
   uint32_t tmem_base;
 };
+// Embedding dimension d = 64 KC (KC K-chunks of one 128-byte swizzle row each; BASELINE.json configs[4] is d = 256).
+// The user tiles of a pass stay in shared memory for the whole catalog sweep: KC x 16 KB per tile.  d = 64 and
+// 128 double-buffer them across passes; at d = 256 (128 KB for the two tiles) there is one buffer, and the few
+// microseconds the producer waits at a pass boundary are nothing against the ~2 ms of a pass.  The B ring holds
+// (item tile, chunk) stages.
+template <int KC> struct KShape {
+  static_assert(KC == 1 || KC == 2 || KC == 4, "d = 64, 128 or 256");
+  static constexpr int kAbufs = KC == 4 ? 1 : 2;
+  static constexpr int kStages = KC == 1 ? 6 : 4;    // 128 KB of user tiles + 33 KB of buckets leave room for four
+  static_assert(kStages <= kStagesB, "barrier arrays");
+};
 // The 32 bucket maxima of a user row live in shared memory, 16 per thread of the row: they are touched only
 // when a chunk beats tau (and by the threshold refresh), and in registers they cost the epilogue the room
 // it needs to keep its list pointers out of the constant bank.  [user tile][quarter][half][bucket][lane]
@@ -87,8 +98,11 @@ struct PairBuckets {
   float bm[kMU][4][kHalves][kHalfBuckets][32];
   float tau[kMU][4][32];
 };
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + 2 * kMU * kTileBytes + kStagesB * kTileBytes + sizeof(PairBuckets) +
-                              sizeof(Barriers);
+template <int KC> constexpr size_t smem_bytes() {
+  return 1024 /*align slack*/ + (size_t)KShape<KC>::kAbufs * kMU * KC * kTileBytes + KShape<KC>::kStages * kTileBytes +
+         sizeof(PairBuckets) + sizeof(Barriers);
+}
+static_assert(smem_bytes<4>() <= 227 * 1024, "shared memory");
 
 // ----------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -462,6 +476,7 @@ __device__ __forceinline__ int pass_tile(const PassDesc& p, int it) {
 // ----------------------------------------------------------------------------- the kernel
 // Candidate storage of a row: `cap` entries, the first cap/2 for thread h = 0 (columns 0..63 of every item
 // tile), the rest for h = 1; cand_count[2 row + h] entries are valid in each half.
+template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                         int num_users, int num_user_tiles, int num_item_tiles, int kth_sel,
@@ -470,8 +485,9 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
                         int boot_tiles, int refresh_div, uint32_t wait_hint_ns, const SplitPlan sp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                   // [2][kMU][kTileBytes]
-  uint8_t* smem_b = smem + 2 * kMU * kTileBytes;            // [kStagesB][kTileBytes]
+  constexpr int kAbufs = KShape<KC>::kAbufs, kStagesB = KShape<KC>::kStages;
+  uint8_t* smem_a = smem;                                   // [kAbufs][kMU][KC][kTileBytes]
+  uint8_t* smem_b = smem + kAbufs * kMU * KC * kTileBytes;  // [kStagesB][kTileBytes]
   PairBuckets* buckets = reinterpret_cast<PairBuckets*>(smem_b + kStagesB * kTileBytes);
   Barriers* bars = reinterpret_cast<Barriers*>(buckets + 1);
 
@@ -507,19 +523,22 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       uint32_t g = 0;
       for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
         const int mc = p.mc;
-        const int abuf = n & 1;
-        mbar_wait_hint(&bars->a_empty[abuf], ((n >> 1) & 1) ^ 1, wait_hint_ns);
-        mbar_expect_tx(&bars->a_full[abuf], mc * kTileBytes);
+        const int abuf = n % kAbufs;
+        mbar_wait_hint(&bars->a_empty[abuf], ((n / kAbufs) & 1) ^ 1, wait_hint_ns);
+        mbar_expect_tx(&bars->a_full[abuf], mc * KC * kTileBytes);
         for (int m = 0; m < mc; ++m)
-          tma_load_2d(smem_a + (abuf * kMU + m) * kTileBytes, &map_users, &bars->a_full[abuf], 0,
-                      (p.t0 + m) * kUserTile);
+          for (int kc = 0; kc < KC; ++kc)
+            tma_load_2d(smem_a + ((abuf * kMU + m) * KC + kc) * kTileBytes, &map_users, &bars->a_full[abuf], kc * kDim,
+                        (p.t0 + m) * kUserTile);
         const int num_iters = p.ni + p.boot;
-        for (int it = 0; it < num_iters; ++it, ++g) {
+        for (int it = 0; it < num_iters; ++it) {
           const int tile = pass_tile(p, it);
-          const int stage = g % kStagesB;
-          mbar_wait_hint(&bars->b_empty[stage], ((g / kStagesB) & 1) ^ 1, wait_hint_ns);
-          mbar_expect_tx(&bars->b_full[stage], kTileBytes);
-          tma_load_2d(smem_b + stage * kTileBytes, &map_items, &bars->b_full[stage], 0, tile * kItemTile);
+          for (int kc = 0; kc < KC; ++kc, ++g) {
+            const int stage = g % kStagesB;
+            mbar_wait_hint(&bars->b_empty[stage], ((g / kStagesB) & 1) ^ 1, wait_hint_ns);
+            mbar_expect_tx(&bars->b_full[stage], kTileBytes);
+            tma_load_2d(smem_b + stage * kTileBytes, &map_items, &bars->b_full[stage], kc * kDim, tile * kItemTile);
+          }
         }
       }
     }
@@ -535,29 +554,38 @@ score_topk_fused_kernel(const __grid_constant__ CUtensorMap map_users, const __g
       for (int n = 0; pass_desc(n, num_user_tiles, num_item_tiles, boot_tiles, sp, p); ++n) {
         const int num_iters = p.ni + p.boot;
         const bool active = m < p.mc;
-        const int abuf = n & 1;
-        mbar_wait_hint(&bars->a_full[abuf], (n >> 1) & 1, wait_hint_ns);
+        const int abuf = n % kAbufs;
+        mbar_wait_hint(&bars->a_full[abuf], (n / kAbufs) & 1, wait_hint_ns);
         tc_fence_after();
-        const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(smem_a + (abuf * kMU + m) * kTileBytes) >> 4) & 0x3FFF);
-        for (int it = 0; it < num_iters; ++it, ++g) {
-          const int stage = g % kStagesB;
-          mbar_wait_hint(&bars->b_full[stage], (g / kStagesB) & 1, wait_hint_ns);
+        const uint32_t a_addr = smem_u32(smem_a + (abuf * kMU + m) * KC * kTileBytes);
+        for (int it = 0; it < num_iters; ++it) {
+          // the accumulators of user tile m belong to it alone (use counter `uses`), so no issuer ever
+          // has to order itself against another one
+          const int slot = m * kBUF + (int)(uses % kBUF);
+          const uint32_t d_tmem = tmem_base + slot * kItemTile;
           if (active) {
-            // the accumulators of user tile m belong to it alone (use counter `uses`), so no issuer ever
-            // has to order itself against another one
-            const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(smem_b + stage * kTileBytes) >> 4) & 0x3FFF);
-            const int slot = m * kBUF + (int)(uses % kBUF);
             mbar_wait_hint(&bars->t_empty[slot], ((uses / kBUF) & 1) ^ 1, wait_hint_ns);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + slot * kItemTile;
+          }
 #pragma unroll
-            for (int k = 0; k < kDim / 16; ++k)      // +32 bytes along K = +2 in the 16-byte address field
-              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, k > 0 ? 1u : 0u);
+          for (int kc = 0; kc < KC; ++kc, ++g) {
+            const int stage = g % kStagesB;
+            mbar_wait_hint(&bars->b_full[stage], (g / kStagesB) & 1, wait_hint_ns);
+            if (active) {
+              tc_fence_after();
+              const uint64_t a_desc = desc_hi | (uint64_t)(((a_addr + kc * kTileBytes) >> 4) & 0x3FFF);
+              const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(smem_b + stage * kTileBytes) >> 4) & 0x3FFF);
+#pragma unroll
+              for (int k = 0; k < kDim / 16; ++k)      // +32 bytes along K = +2 in the 16-byte address field
+                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, (kc | k) > 0 ? 1u : 0u);
+              umma_commit(&bars->b_empty[stage]);
+            } else {
+              mbar_arrive(&bars->b_empty[stage]);       // keep the stage's arrival count at kMU
+            }
+          }
+          if (active) {
             umma_commit(&bars->t_full[slot]);
-            umma_commit(&bars->b_empty[stage]);
             ++uses;
-          } else {
-            mbar_arrive(&bars->b_empty[stage]);       // keep the stage's arrival count at kMU
           }
         }
         if (active) umma_commit(&bars->a_empty[abuf]);
@@ -829,24 +857,26 @@ __device__ __forceinline__ float pow2_scale(float absmax) {
   return __uint_as_float((uint32_t)se << 23);
 }
 
-// One 8-lane group per row of 64: a lane handles 8 consecutive floats -> one 16-byte store.
+// D / 8 lanes per row (8 for d = 64, a whole warp for d = 256): a lane handles 8 consecutive floats -> one
+// 16-byte store.
 // PER_ROW = false (item shard): one scale for the table, derived from the device-resident absmax
 //   (params[0]); the kernel also publishes params[1] = scale and params[2] = max_j ||x_j - c||^2.
 // PER_ROW = true (users): every row gets its own power of two -- the ranking of the items for a fixed
 //   user does not depend on that user's scale, so a table with a heavy-tailed norm distribution keeps
 //   11 significant bits in every row; 1/scale goes to row_inv_scale[r] for hnm_rescore_topk.
-template <bool PER_ROW>
+template <bool PER_ROW, int D>
 __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __restrict__ row_ids, int64_t num_rows,
                             int64_t rows_padded, const float* __restrict__ center, float* __restrict__ params,
                             __half* __restrict__ out, float* __restrict__ row_inv_scale) {
+  constexpr int TPR = D / 8;                                             // lanes per row: 8, 16 or 32
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t r = t >> 3;
-  const int sub = (int)(t & 7);
-  if (r >= rows_padded) return;                                          // whole 8-lane groups leave together
+  const int64_t r = t / TPR;
+  const int sub = (int)(t % TPR);
+  if (r >= rows_padded) return;                                          // whole lane groups leave together
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
   if (r < num_rows) {
     const int64_t src = row_ids ? row_ids[r] : r;
-    const float* p = emb + (size_t)src * kDim + sub * 8;
+    const float* p = emb + (size_t)src * D + sub * 8;
     a = ldg_f4(p);
     b = ldg_f4(p + 4);
     if (center) {     // w = fl(x - c): ranking of u.x and u.(x - c) is the same for a fixed user
@@ -855,15 +885,14 @@ __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __rest
       b = make_float4(__fsub_rn(b.x, cb.x), __fsub_rn(b.y, cb.y), __fsub_rn(b.z, cb.z), __fsub_rn(b.w, cb.w));
     }
   }
-  // the 8 lanes of a row are 8 consecutive lanes of one warp: xor-shuffles 1, 2, 4 stay inside the row
-  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  // the lanes of a row are TPR consecutive lanes of one warp: xor-shuffles below TPR stay inside the row
+  const unsigned gmask = TPR == 32 ? 0xffffffffu : (((1u << TPR) - 1u) << ((threadIdx.x & 31) & ~(TPR - 1)));
   float scale;
   if (PER_ROW) {
     float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
                     fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
-    m = fmaxf(m, __shfl_xor_sync(gmask, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(gmask, m, 2));
-    m = fmaxf(m, __shfl_xor_sync(gmask, m, 4));
+#pragma unroll
+    for (int off = 1; off < TPR; off <<= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, off));
     scale = pow2_scale(m);
     if (sub == 0 && r < num_rows) row_inv_scale[r] = 1.f / scale;       // exact: a power of two
   } else {
@@ -875,12 +904,11 @@ __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __rest
   h[1] = __floats2half2_rn(a.z * scale, a.w * scale);
   h[2] = __floats2half2_rn(b.x * scale, b.y * scale);
   h[3] = __floats2half2_rn(b.z * scale, b.w * scale);
-  *reinterpret_cast<uint4*>(out + (size_t)r * kDim + sub * 8) = *reinterpret_cast<uint4*>(h);
+  *reinterpret_cast<uint4*>(out + (size_t)r * D + sub * 8) = *reinterpret_cast<uint4*>(h);
   if (!PER_ROW) {
     float sq = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
-    sq += __shfl_xor_sync(gmask, sq, 1);
-    sq += __shfl_xor_sync(gmask, sq, 2);
-    sq += __shfl_xor_sync(gmask, sq, 4);
+#pragma unroll
+    for (int off = 1; off < TPR; off <<= 1) sq += __shfl_xor_sync(gmask, sq, off);
     if (sub == 0 && r < num_rows) atomicMax(reinterpret_cast<int*>(params + 2), __float_as_int(sq));   // sq >= 0
   }
 }
@@ -933,10 +961,11 @@ constexpr int kMaxSel = 128;               // pass-1 survivors a user may have (
 constexpr int kRescorePrefetch = 4096;     // users ahead whose inputs are pulled into the L2 (> users resident on the GPU)
 static_assert(32 * kStride1 * 4 <= (kRows2 * kStride2 + 32) * 8, "tile union");
 
+template <int D>
 struct __align__(16) RescoreSmem {
-  double tile[kRows2 * kStride2 + 32];     // pass 1: float [32][kStride1]; pass 2: double [16][kStride2]
+  double tile[kRows2 * kStride2 + 32];     // pass 1: float [32][kStride1]; pass 2: double [16][kStride2] (one 64-wide slab)
   double sc[kMaxContenders];               // contender scores
-  float uf[kDim];
+  float uf[D];
   int id[kMaxContenders];
   uint32_t col[kMaxGroups];
   float glo[kMaxGroups];                   // interval of the group's tensor-core maximum
@@ -951,8 +980,9 @@ __device__ __forceinline__ void cmpx_desc(float& v, int lane, int stride, bool d
   v = (lower == desc) ? fmaxf(v, o) : fminf(v, o);
 }
 
+template <int D>
 __global__ void __launch_bounds__(kRescoreWarps * 32, 5)
-rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
+rescore_dim_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
                  const int64_t* __restrict__ user_ids, int64_t batch, int64_t item_begin, int num_items_local,
                  const CandList cand, int cap, const int32_t* __restrict__ cand_count,
                  const float* __restrict__ cand_thresh, const float* __restrict__ user_inv_scale,
@@ -960,15 +990,16 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
                  const float* __restrict__ center, const int64_t* __restrict__ excl_ptr,
                  const int64_t* __restrict__ excl_items, int k, int64_t* __restrict__ out_ids,
                  double* __restrict__ out_scores, int32_t* __restrict__ certified) {
-  __shared__ RescoreSmem smem[kRescoreWarps];
+  constexpr int SL = D / kDim;              // 64-wide slabs of the embedding dimension
+  __shared__ RescoreSmem<D> smem[kRescoreWarps];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * kRescoreWarps + wib;
   if (b >= batch) return;
-  RescoreSmem& sm = smem[wib];
+  RescoreSmem<D>& sm = smem[wib];
   float* tile1 = reinterpret_cast<float*>(sm.tile);
   const int64_t uid = user_ids ? user_ids[b] : b;
-  const float* urow = user_emb + (size_t)uid * kDim;
+  const float* urow = user_emb + (size_t)uid * D;
   // the row's storage: cap entries; list 0 starts at entry 0, list 1 at cap / 2 (the two threads of the row in
   // the fused kernel); a lone list 0 (merge_split_kernel) may use all of it
   const int raw0 = cand_count[2 * b], raw1 = cand_count[2 * b + 1];
@@ -999,26 +1030,28 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
       const char* pm = nullptr;
       if (lane == 0) pm = reinterpret_cast<const char*>(cand_count + 2 * pb);
       else if (lane == 1) pm = reinterpret_cast<const char*>(cand_thresh + pb);
-      else if (lane < 10 && !user_ids) pm = reinterpret_cast<const char*>(user_emb + (size_t)pb * kDim) + (lane - 2) * 32;
+      else if (lane < 10 && !user_ids) pm = reinterpret_cast<const char*>(user_emb + (size_t)pb * D) + (lane - 2) * 32;
       if (pm) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm));
     }
   }
 
-  // the user's row: fp32 copy in shared memory for pass 1, this lane's four values as doubles for pass 2
-  const float4 uf = ldg_f4(urow + sub * 4);
-  if (half == 0) *reinterpret_cast<float4*>(sm.uf + sub * 4) = uf;
-  const double ud0 = (double)uf.x, ud1 = (double)uf.y, ud2 = (double)uf.z, ud3 = (double)uf.w;
+  // the user's row: fp32 copy in shared memory (pass 1 reads it as broadcasts, pass 2 turns it into doubles)
   // u.c in fp64 (it enters the cut); the three quantities that only feed error bounds as fp32 upper bounds
   double uc = 0.0;
   float un2 = 0.f, uc_absf = 0.f, cn2 = 0.f;
-  if (half == 0) {
-    un2 = fmaf(uf.x, uf.x, fmaf(uf.y, uf.y, fmaf(uf.z, uf.z, uf.w * uf.w)));
-    if (center) {
-      const float4 cf = ldg_f4(center + sub * 4);
-      uc = fma(ud0, (double)cf.x, uc); uc = fma(ud1, (double)cf.y, uc);
-      uc = fma(ud2, (double)cf.z, uc); uc = fma(ud3, (double)cf.w, uc);
-      uc_absf = fabsf(uf.x * cf.x) + fabsf(uf.y * cf.y) + fabsf(uf.z * cf.z) + fabsf(uf.w * cf.w);
-      cn2 = fmaf(cf.x, cf.x, fmaf(cf.y, cf.y, fmaf(cf.z, cf.z, cf.w * cf.w)));
+#pragma unroll
+  for (int sl = 0; sl < SL; ++sl) {
+    const float4 uf = ldg_f4(urow + sl * kDim + sub * 4);
+    if (half == 0) {
+      *reinterpret_cast<float4*>(sm.uf + sl * kDim + sub * 4) = uf;
+      un2 += fmaf(uf.x, uf.x, fmaf(uf.y, uf.y, fmaf(uf.z, uf.z, uf.w * uf.w)));
+      if (center) {
+        const float4 cf = ldg_f4(center + sl * kDim + sub * 4);
+        uc = fma((double)uf.x, (double)cf.x, uc); uc = fma((double)uf.y, (double)cf.y, uc);
+        uc = fma((double)uf.z, (double)cf.z, uc); uc = fma((double)uf.w, (double)cf.w, uc);
+        uc_absf += fabsf(uf.x * cf.x) + fabsf(uf.y * cf.y) + fabsf(uf.z * cf.z) + fabsf(uf.w * cf.w);
+        cn2 += fmaf(cf.x, cf.x, fmaf(cf.y, cf.y, fmaf(cf.z, cf.z, cf.w * cf.w)));
+      }
     }
   }
 
@@ -1078,17 +1111,17 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     uc_absf += __shfl_xor_sync(0xffffffffu, uc_absf, off);
     cn2 += __shfl_xor_sync(0xffffffffu, cn2, off);
   }
-  // fp32 sums of 64 non-negative terms are within 64 * 2^-24 of the truth: 1.00002 makes them upper bounds
+  // fp32 sums of D non-negative terms are within D * 2^-24 of the truth: 1.00002 makes them upper bounds
   const double un = (double)(sqrtf(un2) * 1.00002f);
   const double cn_norm = (double)(sqrtf(cn2) * 1.00002f);
   const double uc_abs = (double)(uc_absf * 1.00002f);
   // for any item j outside the kept groups:  u.x_j = u.(x_j - c) + u.c <= thr/(su*si) + eps + u.c =: cut
-  const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)kDim * 0.00390625 * inv_scale + 1e-12 * uc_abs;
+  const double eps = 1.1 * 0.0009765625 * un * max_item_norm + (double)D * 0.00390625 * inv_scale + 1e-12 * uc_abs;
   const double cut = (double)thr * inv_scale + eps + uc;
   const float cutf = __double2float_rd(cut);                // a_j + rad <= cutf  =>  u.x_j <= cut
-  // fp32 dot product radius: 2 gamma_64 ||u|| ||x_j||, ||x_j|| <= max ||x - c|| + ||c||; the absolute term
-  // covers products that underflow in fp32
-  const float rad = __double2float_ru(7.62939453125e-6 * un * (max_item_norm + cn_norm) * 1.0001 + 1e-36);
+  // fp32 dot product radius: 2 gamma_D ||u|| ||x_j|| (2 D 2^-24), ||x_j|| <= max ||x - c|| + ||c||; the absolute
+  // term covers products that underflow in fp32
+  const float rad = __double2float_ru(7.62939453125e-6 * SL * un * (max_item_norm + cn_norm) * 1.0001 + 1e-36);
   __syncwarp();
 
   // 2. g_(k) over (at most the first 32 of) the kept groups whose four items all exist and are not excluded
@@ -1140,31 +1173,33 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
     bool live = item >= 0 && item < num_items_local;        // columns past the catalog are zero padding
     if (live && ex_lo < ex_hi && in_sorted(excl_items, ex_lo, ex_hi, item_begin + (int64_t)item)) live = false;
     const int litem = live ? item : 0;                      // dead slots fetch row 0; their result is not used
-#pragma unroll
-    for (int h0 = 0; h0 < 16; h0 += 8) {
-      float4 v[8];
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const int il = __shfl_sync(0xffffffffu, litem, 2 * (h0 + s) + half);
-        v[s] = ldg_f4(item_emb + (size_t)il * kDim + sub * 4);
-      }
-#pragma unroll
-      for (int s = 0; s < 8; ++s)
-        *reinterpret_cast<float4*>(tile1 + (2 * (h0 + s) + half) * kStride1 + sub * 4) = v[s];
-    }
-    __syncwarp();
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // four partial sums: any order satisfies the bound
-    {
+#pragma unroll 1
+    for (int sl = 0; sl < SL; ++sl) {                       // one 64-wide slab of the rows at a time
+#pragma unroll
+      for (int h0 = 0; h0 < 16; h0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const int il = __shfl_sync(0xffffffffu, litem, 2 * (h0 + s) + half);
+          v[s] = ldg_f4(item_emb + (size_t)il * D + sl * kDim + sub * 4);
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          *reinterpret_cast<float4*>(tile1 + (2 * (h0 + s) + half) * kStride1 + sub * 4) = v[s];
+      }
+      __syncwarp();
       const float* t = tile1 + lane * kStride1;
 #pragma unroll
       for (int kk = 0; kk < kDim; kk += 4) {
-        const float4 u4 = *reinterpret_cast<const float4*>(sm.uf + kk);
+        const float4 u4 = *reinterpret_cast<const float4*>(sm.uf + sl * kDim + kk);
         const float4 x4 = *reinterpret_cast<const float4*>(t + kk);
         a0 = fmaf(u4.x, x4.x, a0);
         a1 = fmaf(u4.y, x4.y, a1);
         a2 = fmaf(u4.z, x4.z, a2);
         a3 = fmaf(u4.w, x4.w, a3);
       }
+      if (SL > 1) __syncwarp();                             // the tile is rewritten by the next slab
     }
     const float up = ((a0 + a1) + (a2 + a3)) + rad;
     const bool s = live && up >= t0f && up > cutf;
@@ -1181,37 +1216,45 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   // 4. pass 2: exact scores of the survivors; contenders = strictly above the cut
   int total = 0;
   for (int base = 0; base < nsel; base += kRows2) {
-    {
-      // all eight row loads of this half warp are issued before the first one is used
-      // (slots past the last survivor repeat it: no predicates, and nobody reads those rows)
-      float4 v[kRows2 / 2];
-#pragma unroll
-      for (int s = 0; s < kRows2 / 2; ++s) {
-        const int it = sm.sel[min(base + 2 * s + half, nsel - 1)];
-        const int item = (int)sm.col[it / kGroup] + (it % kGroup);
-        v[s] = ldg_f4(item_emb + (size_t)item * kDim + sub * 4);
-      }
-#pragma unroll
-      for (int s = 0; s < kRows2 / 2; ++s) {
-        double2* t = reinterpret_cast<double2*>(sm.tile + (2 * s + half) * kStride2 + sub * 4);
-        t[0] = make_double2(ud0 * (double)v[s].x, ud1 * (double)v[s].y);
-        t[1] = make_double2(ud2 * (double)v[s].z, ud3 * (double)v[s].w);
-      }
-    }
-    __syncwarp();
     double acc = 0.0;
     int item = -1;
     const bool mine2 = lane < kRows2 && base + lane < nsel;
     if (mine2) {
       const int it = sm.sel[base + lane];
       item = (int)sm.col[it / kGroup] + (it % kGroup);
-      const double2* t = reinterpret_cast<const double2*>(sm.tile + lane * kStride2);
-#pragma unroll 8
-      for (int kk = 0; kk < kDim / 2; ++kk) {          // == fma(u_k, x_k, acc) for k = 0..63: the products are exact
-        const double2 pr = t[kk];
-        acc = __dadd_rn(pr.x, acc);
-        acc = __dadd_rn(pr.y, acc);
+    }
+#pragma unroll 1
+    for (int sl = 0; sl < SL; ++sl) {                          // slabs in order: the chain runs k = 0 .. D-1
+      {
+        // all eight row loads of this half warp are issued before the first one is used
+        // (slots past the last survivor repeat it: no predicates, and nobody reads those rows)
+        float4 v[kRows2 / 2];
+#pragma unroll
+        for (int s = 0; s < kRows2 / 2; ++s) {
+          const int it = sm.sel[min(base + 2 * s + half, nsel - 1)];
+          const int itm = (int)sm.col[it / kGroup] + (it % kGroup);
+          v[s] = ldg_f4(item_emb + (size_t)itm * D + sl * kDim + sub * 4);
+        }
+        const float4 uf = *reinterpret_cast<const float4*>(sm.uf + sl * kDim + sub * 4);
+        const double ud0 = (double)uf.x, ud1 = (double)uf.y, ud2 = (double)uf.z, ud3 = (double)uf.w;
+#pragma unroll
+        for (int s = 0; s < kRows2 / 2; ++s) {
+          double2* t = reinterpret_cast<double2*>(sm.tile + (2 * s + half) * kStride2 + sub * 4);
+          t[0] = make_double2(ud0 * (double)v[s].x, ud1 * (double)v[s].y);
+          t[1] = make_double2(ud2 * (double)v[s].z, ud3 * (double)v[s].w);
+        }
       }
+      __syncwarp();
+      if (mine2) {
+        const double2* t = reinterpret_cast<const double2*>(sm.tile + lane * kStride2);
+#pragma unroll 8
+        for (int kk = 0; kk < kDim / 2; ++kk) {        // == fma(u_k, x_k, acc) in the order of k: the products are exact
+          const double2 pr = t[kk];
+          acc = __dadd_rn(pr.x, acc);
+          acc = __dadd_rn(pr.y, acc);
+        }
+      }
+      if (SL > 1) __syncwarp();                                // the tile is rewritten by the next slab
     }
     const bool c = mine2 && acc > cut;
     const unsigned mask = __ballot_sync(0xffffffffu, c);
@@ -1273,7 +1316,7 @@ rescore64_kernel(const float* __restrict__ user_emb, const float* __restrict__ i
   }
 }
 
-int make_map(CUtensorMap* map, const void* base, int64_t rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -1282,8 +1325,8 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows) {
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return HNM_E_DRIVER;
     encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   }
-  cuuint64_t gdim[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)(kDim * 2)};
+  cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};             // box = one 64-wide K chunk of 128 rows
+  cuuint64_t gstride[1] = {(cuuint64_t)(dim * 2)};
   cuuint32_t box[2] = {(cuuint32_t)kDim, (cuuint32_t)kItemTile};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -1310,13 +1353,15 @@ extern "C" int hnm_score_pack_items(const float* emb, int64_t num_rows, int64_t 
                                     const float* center, float* params, void* out_f16, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!emb || !out_f16 || !params) return HNM_E_NULL;
-  if (dim != kDim) return HNM_E_DIM;
+  if (dim != 64 && dim != 128 && dim != 256) return HNM_E_DIM;
   if (num_rows < 0 || rows_padded < num_rows || rows_padded <= 0) return HNM_E_RANGE;
   if (!hnm_aligned16(emb) || !hnm_aligned16(out_f16) || (center && !hnm_aligned16(center))) return HNM_E_ALIGN;
   const int T = 256;
-  const int64_t threads = rows_padded * 8;
-  pack_kernel<false><<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(emb, nullptr, num_rows, rows_padded, center,
-                                                                         params, (__half*)out_f16, nullptr);
+  const int64_t threads = rows_padded * (dim / 8);
+  const unsigned grid = (unsigned)((threads + T - 1) / T);
+  if (dim == 64) pack_kernel<false, 64><<<grid, T, 0, stream>>>(emb, nullptr, num_rows, rows_padded, center, params, (__half*)out_f16, nullptr);
+  else if (dim == 128) pack_kernel<false, 128><<<grid, T, 0, stream>>>(emb, nullptr, num_rows, rows_padded, center, params, (__half*)out_f16, nullptr);
+  else pack_kernel<false, 256><<<grid, T, 0, stream>>>(emb, nullptr, num_rows, rows_padded, center, params, (__half*)out_f16, nullptr);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
@@ -1325,13 +1370,15 @@ extern "C" int hnm_score_pack_users(const float* emb, const int64_t* row_ids, in
                                     int32_t dim, void* out_f16, float* out_inv_scale, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!emb || !out_f16 || !out_inv_scale) return HNM_E_NULL;
-  if (dim != kDim) return HNM_E_DIM;
+  if (dim != 64 && dim != 128 && dim != 256) return HNM_E_DIM;
   if (num_rows < 0 || rows_padded < num_rows || rows_padded <= 0) return HNM_E_RANGE;
   if (!hnm_aligned16(emb) || !hnm_aligned16(out_f16)) return HNM_E_ALIGN;
   const int T = 256;
-  const int64_t threads = rows_padded * 8;
-  pack_kernel<true><<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(emb, row_ids, num_rows, rows_padded, nullptr,
-                                                                        nullptr, (__half*)out_f16, out_inv_scale);
+  const int64_t threads = rows_padded * (dim / 8);
+  const unsigned grid = (unsigned)((threads + T - 1) / T);
+  if (dim == 64) pack_kernel<true, 64><<<grid, T, 0, stream>>>(emb, row_ids, num_rows, rows_padded, nullptr, nullptr, (__half*)out_f16, out_inv_scale);
+  else if (dim == 128) pack_kernel<true, 128><<<grid, T, 0, stream>>>(emb, row_ids, num_rows, rows_padded, nullptr, nullptr, (__half*)out_f16, out_inv_scale);
+  else pack_kernel<true, 256><<<grid, T, 0, stream>>>(emb, row_ids, num_rows, rows_padded, nullptr, nullptr, (__half*)out_f16, out_inv_scale);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
@@ -1400,7 +1447,8 @@ extern "C" int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_pad
 }
 
 extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, int64_t users_padded,
-                                    const void* items_f16, int64_t num_items, int64_t items_padded, int32_t kth_sel,
+                                    const void* items_f16, int64_t num_items, int64_t items_padded, int32_t dim,
+                                    int32_t kth_sel,
                                     void* cand, int32_t cand_cap, int32_t* cand_count, float* cand_thresh,
                                     const uint32_t* excl_sig, void* workspace, int64_t workspace_bytes,
                                     void* stream_) {
@@ -1414,8 +1462,9 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   int rc = hnm_check_device();
   if (rc != HNM_OK) return rc;
   CUtensorMap map_u, map_i;
-  if ((rc = make_map(&map_u, users_f16, users_padded)) != HNM_OK) return rc;
-  if ((rc = make_map(&map_i, items_f16, items_padded)) != HNM_OK) return rc;
+  if (dim != 64 && dim != 128 && dim != 256) return HNM_E_DIM;
+  if ((rc = make_map(&map_u, users_f16, users_padded, dim)) != HNM_OK) return rc;
+  if ((rc = make_map(&map_i, items_f16, items_padded, dim)) != HNM_OK) return rc;
   static const int debug_mode = getenv("HNM_FUSED_DEBUG") ? atoi(getenv("HNM_FUSED_DEBUG")) : 0;
   static const int boot_tiles = getenv("HNM_FUSED_BOOT") ? std::max(1, atoi(getenv("HNM_FUSED_BOOT"))) : kBootTiles;
   static const int refresh_div = getenv("HNM_FUSED_REFRESH") ? std::max(1, atoi(getenv("HNM_FUSED_REFRESH"))) : 4;
@@ -1434,10 +1483,17 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
     sp.count = reinterpret_cast<int32_t*>(ws + off_count);
     sp.thresh = reinterpret_cast<float*>(ws + off_thresh);
   }
-  HNM_CUDA_TRY(hnm_allow_smem(score_topk_fused_kernel, (int)kSmemBytes));
-  score_topk_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(
-      map_u, map_i, (int)num_users, num_user_tiles, num_tiles, kth_sel, cand_list(cand, (size_t)num_users, cand_cap),
-      cand_cap, cand_count, cand_thresh, excl_sig, debug_mode, boot_tiles, refresh_div, wait_hint, sp);
+#define HNM_FUSED_LAUNCH(KC)                                                                                       \
+  {                                                                                                                \
+    HNM_CUDA_TRY(hnm_allow_smem(score_topk_fused_kernel<KC>, (int)smem_bytes<KC>()));                              \
+    score_topk_fused_kernel<KC><<<grid, kThreads, smem_bytes<KC>(), stream>>>(                                     \
+        map_u, map_i, (int)num_users, num_user_tiles, num_tiles, kth_sel, cand_list(cand, (size_t)num_users, cand_cap), \
+        cand_cap, cand_count, cand_thresh, excl_sig, debug_mode, boot_tiles, refresh_div, wait_hint, sp);          \
+  }
+  if (dim == 64) HNM_FUSED_LAUNCH(1)
+  else if (dim == 128) HNM_FUSED_LAUNCH(2)
+  else HNM_FUSED_LAUNCH(4)
+#undef HNM_FUSED_LAUNCH
   HNM_LAUNCH_CHECK();
   if (need > 0) {
     const int64_t split_users = std::min<int64_t>((int64_t)sp.triples * sp.mu * kUserTile,
@@ -1476,17 +1532,24 @@ extern "C" int hnm_rescore_topk(const float* user_emb, const float* item_emb, co
       !out_scores || !out_certified)
     return HNM_E_NULL;
   if ((excl_ptr != nullptr) != (excl_items != nullptr)) return HNM_E_NULL;
-  if (dim != kDim) return HNM_E_DIM;
+  if (dim != 64 && dim != 128 && dim != 256) return HNM_E_DIM;
   if (batch < 0 || k < 1 || k > 32 || cand_cap < 2 || cand_cap % 2 || cand_cap > 32 * kMaxPerLane || num_items_local < 1 ||
       num_items_local > INT32_MAX)
     return HNM_E_RANGE;
   if (!hnm_aligned16(user_emb) || !hnm_aligned16(item_emb) || !hnm_aligned16(cand) || (center && !hnm_aligned16(center)))
     return HNM_E_ALIGN;
   const int wpc = kRescoreWarps;
-  rescore64_kernel<<<(unsigned)((batch + wpc - 1) / wpc), wpc * 32, 0, stream>>>(
-      user_emb, item_emb, user_ids, batch, item_begin, (int)num_items_local, cand_list(const_cast<void*>(cand), (size_t)batch, cand_cap), cand_cap,
-      cand_count, cand_thresh, user_inv_scale, item_params, center, excl_ptr, excl_items, k, out_ids, out_scores,
-      out_certified);
+  const unsigned grid = (unsigned)((batch + wpc - 1) / wpc);
+  const CandList cl = cand_list(const_cast<void*>(cand), (size_t)batch, cand_cap);
+#define HNM_RESCORE(DD)                                                                                          \
+  rescore_dim_kernel<DD><<<grid, wpc * 32, 0, stream>>>(user_emb, item_emb, user_ids, batch, item_begin,         \
+                                                        (int)num_items_local, cl, cand_cap, cand_count, cand_thresh, \
+                                                        user_inv_scale, item_params, center, excl_ptr, excl_items, k, \
+                                                        out_ids, out_scores, out_certified)
+  if (dim == 64) HNM_RESCORE(64);
+  else if (dim == 128) HNM_RESCORE(128);
+  else HNM_RESCORE(256);
+#undef HNM_RESCORE
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }

@@ -21,6 +21,7 @@ CAND_CAP = 192                 # candidate entries (32-column chunks) per user; 
 CAND_WORDS = 5                 # HNM_FUSED_CAND_BYTES / 4 (16 bytes of group maxima + 4 bytes of column per entry)
 SIG_WORDS = 32                 # HNM_FUSED_SIG_WORDS
 K_MAX = 16
+FUSED_DIMS = (64, 128, 256)    # embedding dimensions of the tensor-core path (K chunks of 64)
 SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maximum
 MAX_USERS_PER_LAUNCH = 1 << 21
 TIER2_MIN_USERS = 32            # fewer uncertified users go straight to the exact kernel
@@ -32,7 +33,7 @@ class FusedScorer:
 
     @staticmethod
     def supports(dim: int, k: int, num_items: int) -> bool:
-        return dim == 64 and 1 <= k <= K_MAX and num_items >= 2 * ITEM_TILE
+        return dim in FUSED_DIMS and 1 <= k <= K_MAX and num_items >= 2 * ITEM_TILE
 
     def __init__(self, user_emb: torch.Tensor, item_emb: torch.Tensor, item_begin: int = 0,
                  center: bool = True, sel_margin: int = SEL_MARGIN):
@@ -43,6 +44,9 @@ class FusedScorer:
         self.sel_margin = sel_margin
         dev = self.item_emb.device
         self.num_items = int(self.item_emb.size(0))
+        self.dim = int(self.item_emb.size(1))
+        if self.dim not in FUSED_DIMS or int(self.user_emb.size(1)) != self.dim:
+            raise ValueError(f"the fused scorer takes embedding dimensions {FUSED_DIMS}")
         self.items_padded = (self.num_items + ITEM_TILE - 1) // ITEM_TILE * ITEM_TILE
         with torch.cuda.device(dev):
             # any fp32 vector is a valid centre; the mean row is the one that shrinks the items most
@@ -50,10 +54,10 @@ class FusedScorer:
             # {absmax, scale, max ||x - c||^2, -} of the shard: produced and consumed on the device, so the
             # set-up needs no host synchronisation (two .tolist()/.max() round trips in round 1)
             self.item_params = torch.zeros(4, dtype=torch.float32, device=dev)
-            call("hnm_absmax", ptr(self.item_emb), self.item_emb.numel(), ptr(self.center), 64,
+            call("hnm_absmax", ptr(self.item_emb), self.item_emb.numel(), ptr(self.center), self.dim,
                  self.item_params.data_ptr(), stream())
-            self.items_f16 = torch.empty(self.items_padded, 64, dtype=torch.float16, device=dev)
-            call("hnm_score_pack_items", ptr(self.item_emb), self.num_items, self.items_padded, 64,
+            self.items_f16 = torch.empty(self.items_padded, self.dim, dtype=torch.float16, device=dev)
+            call("hnm_score_pack_items", ptr(self.item_emb), self.num_items, self.items_padded, self.dim,
                  ptr(self.center), ptr(self.item_params), ptr(self.items_f16), stream())
         self.last_stats: Dict[str, int] = {}
         self.profile = False                       # record CUDA events around each stage of topk()
@@ -252,17 +256,17 @@ class FusedScorer:
         note = self._mark if mark else (lambda name: None)
         with torch.cuda.device(dev):
             s = stream()
-            users_f16 = torch.empty(padded, 64, dtype=torch.float16, device=dev)
+            users_f16 = torch.empty(padded, self.dim, dtype=torch.float16, device=dev)
             inv_scale = torch.empty(n, dtype=torch.float32, device=dev)      # 1 / (the row's own power of two)
             note("pack_begin")
             if uids is None:
                 src = self.user_emb[b0:b1]
-                call("hnm_score_pack_users", ptr(src), None, n, padded, 64, ptr(users_f16), ptr(inv_scale), s)
+                call("hnm_score_pack_users", ptr(src), None, n, padded, self.dim, ptr(users_f16), ptr(inv_scale), s)
                 rid = None
                 user_base = src
             else:
                 rid = uids[b0:b1]
-                call("hnm_score_pack_users", ptr(self.user_emb), ptr(rid), n, padded, 64, ptr(users_f16),
+                call("hnm_score_pack_users", ptr(self.user_emb), ptr(rid), n, padded, self.dim, ptr(users_f16),
                      ptr(inv_scale), s)
                 user_base = self.user_emb
             cand = torch.empty(n * CAND_CAP * CAND_WORDS, dtype=torch.int32, device=dev)
@@ -281,10 +285,11 @@ class FusedScorer:
                      ptr(sig), s)
             note("fused_begin")
             call("hnm_score_topk_fused", ptr(users_f16), n, padded, ptr(self.items_f16), self.num_items,
-                 self.items_padded, sel, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(sig), ptr(ws), ws_bytes, s)
+                 self.items_padded, self.dim, sel, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(sig), ptr(ws),
+                 ws_bytes, s)
             note("fused_end")
             note("rescore_begin")
-            call("hnm_rescore_topk", ptr(user_base), ptr(self.item_emb), ptr(rid), n, 64, self.item_begin,
+            call("hnm_rescore_topk", ptr(user_base), ptr(self.item_emb), ptr(rid), n, self.dim, self.item_begin,
                  self.num_items, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(inv_scale), ptr(self.item_params),
                  ptr(self.center), ptr(ex_ptr), ptr(excl[1]), k, ptr(ids[b0:b1]), ptr(sc[b0:b1]), ptr(cert[b0:b1]), s)
             note("rescore_end")

@@ -219,7 +219,7 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
  * Users whose certificate fails are re-run by the caller: the same three calls with a wider kth_sel,
  * then hnm_topk_exact for what is left.
  * ---------------------------------------------------------------------- */
-#define HNM_FUSED_DIM 64            /* embedding dimension of the tensor-core path */
+#define HNM_FUSED_DIM 64            /* K chunk of the tensor-core path; supported embedding dimensions: 64, 128, 256 */
 #define HNM_FUSED_USER_TILE 128     /* users per accumulator (UMMA M); users_padded must be a multiple */
 #define HNM_FUSED_ITEM_TILE 128     /* items per MMA tile (UMMA N); items_padded must be a multiple */
 #define HNM_FUSED_CAND_MAX 256      /* largest cand_cap (entries per user) */
@@ -242,9 +242,9 @@ HNM_API int hnm_score_pack_items(const float* emb, int64_t num_rows, int64_t row
 HNM_API int hnm_score_pack_users(const float* emb, const int64_t* row_ids /* NULL = identity */, int64_t num_rows,
                          int64_t rows_padded, int32_t dim, void* out_f16 /* [rows_padded, dim] __half */,
                          float* out_inv_scale /* [num_rows] */, void* stream);
-HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, 64] */, int64_t num_users, int64_t users_padded,
-                         const void* items_f16 /* [items_padded, 64] */, int64_t num_items, int64_t items_padded,
-                         int32_t kth_sel /* 1..32 */,
+HNM_API int hnm_score_topk_fused(const void* users_f16 /* [users_padded, dim] */, int64_t num_users, int64_t users_padded,
+                         const void* items_f16 /* [items_padded, dim] */, int64_t num_items, int64_t items_padded,
+                         int32_t dim /* 64, 128 or 256 */, int32_t kth_sel /* 1..32 */,
                          void* cand /* num_users * cand_cap * HNM_FUSED_CAND_BYTES bytes, 16-byte aligned (layout above) */,
                          int32_t cand_cap /* even */, int32_t* cand_count /* [num_users][2] */,
                          float* cand_thresh /* [num_users] final tau (scaled units) */,

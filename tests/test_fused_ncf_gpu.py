@@ -306,3 +306,38 @@ def test_heavy_tailed_user_norms_stay_on_the_tensor_path(hnm_lib):
     uids = torch.cat([torch.arange(0, U, 5), torch.tensor([7])]).cuda()
     w_ids, w_s = engine.topk_exact(ue, ie, uids, 12)
     assert torch.equal(ids[uids], w_ids) and torch.equal(s[uids], w_s)
+
+
+@pytest.mark.parametrize("dim", [128, 256])
+def test_fused_topk_wide_embeddings_bit_exact(hnm_lib, dim):
+    """BASELINE.json configs[4] asks for d = 256: the tensor path takes the embedding dimension as 2 or 4 K chunks
+    of 64 (user tiles resident in shared memory for the catalog sweep, B ring of (item tile, chunk) stages; the
+    rescoring walks the slabs in order, so the fp64 chain still runs k = 0 .. d-1).  ids AND fp64 scores
+    bit-identical to the oracle, with filters, on whole passes and on sliced left-over tiles."""
+    from hnm_recommendation_b200 import engine
+    from hnm_recommendation_b200.scorer import FusedScorer
+    assert FusedScorer.supports(dim, 12, 5000)
+    g = torch.Generator().manual_seed(dim)
+    U, I = 3000, 5100
+    ue = torch.randn(U, dim, generator=g) * 0.1
+    ie = torch.randn(I, dim, generator=g) * 0.1 + 0.02
+    sc = FusedScorer(ue.cuda(), ie.cuda())
+    ids, s = sc.topk(None, 12)
+    uids = torch.arange(0, U, 7)
+    want_ids, want_s = O.recommend_exact(ue, ie, uids, 12)
+    assert torch.equal(ids[uids.cuda()].cpu(), want_ids) and torch.equal(s[uids.cuda()].cpu(), want_s)
+    w_ids, w_s = engine.topk_exact(ue.cuda(), ie.cuda(), None, 12)
+    assert torch.equal(ids, w_ids) and torch.equal(s, w_s)
+    assert sc.last_stats["tier3"] <= 3, sc.last_stats
+    filt = {int(u): set(want_ids[r, :5].tolist()) for r, u in enumerate(uids[:40].tolist())}
+    f_ids, f_s = sc.topk(uids[:40].cuda(), 12, filt)
+    e_ids, e_s = O.recommend_exact(ue, ie, uids[:40], 12, filt)
+    assert torch.equal(f_ids.cpu(), e_ids) and torch.equal(f_s.cpu(), e_s)
+    # an item shard, k < 12, and more users than one pass of the persistent grid (whole passes + sliced tiles)
+    U2 = (148 * 2 + 5) * 128 - 17
+    ue2 = torch.randn(U2, dim, generator=g) * 0.1
+    sh = FusedScorer(ue2.cuda(), ie[900:].cuda().contiguous(), item_begin=900)
+    ids2, s2 = sh.topk(None, 7)
+    chk = torch.cat([torch.arange(0, U2, 97), torch.arange(U2 - 700, U2)]).cuda()
+    x_ids, x_s = engine.topk_exact(ue2.cuda(), ie[900:].cuda().contiguous(), chk, 7, item_begin=900)
+    assert torch.equal(ids2[chk], x_ids) and torch.equal(s2[chk], x_s)
