@@ -85,6 +85,11 @@ def workload(config: str):
     if config == "config1":
         u, i, e = synth.CONFIG1
         name = "LightGCN L3 d64, synthetic 10k users x 5k items x 200k interactions (configs[0])"
+    elif config == "sweep":
+        f = float(os.environ.get("HNM_SWEEP_SCALE", "1.0"))
+        u, i, e = int(5_000_000 * f), int(1_000_000 * f), int(200_000_000 * f)
+        name = (f"LightGCN L4 d256, synthetic {u} users x {i} items x {e} interactions (configs[4]"
+                + ("" if f == 1.0 else f", scaled by {f}") + ")")
     elif config == "ncf":
         u, i, e = synth.HM_USERS, synth.HM_ITEMS, 0
         name = ("NeuralCF GMF 64 + MLP [128,64,32], 1371980 users x 1000 candidate items each out of 105542 "
@@ -493,16 +498,33 @@ def run_gpu(args):
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
     u, i, e, name = workload(args.config)
-    data = synth.interactions(u, i, e, seed=42)
-    w_host = synth.xavier_embeddings(u + i, DIM, seed=42).pin_memory()
+    sweep = args.config == "sweep"
+    DIM, LAYERS = (256, 4) if sweep else (globals()["DIM"], globals()["LAYERS"])
     model = LightGCN(u, i, embedding_dim=DIM, num_layers=LAYERS, top_k=K_TOP).to(dev)
-    with torch.no_grad():
-        model.embeddings.weight.copy_(w_host)
-    model.set_graph(data.edge_index().to(dev))
-    del data
+    if sweep:
+        # configs[4]: the graph is drawn once (rank 0) and broadcast; the 6 M x 256 table is initialised on the
+        # device (N(0, 0.1), same seed on every rank); no host copy of the table -> no e2e leg for this config
+        m2 = 2 * e
+        ei = torch.empty(2, m2, dtype=torch.int64, device=dev)
+        if rank == 0:
+            ei.copy_(synth.interactions(u, i, e, seed=42).edge_index())
+        if world > 1:
+            dist.broadcast(ei, src=0)
+        with torch.no_grad():
+            model.embeddings.weight.normal_(0.0, 0.1, generator=torch.Generator(device=dev).manual_seed(42))
+        model.set_graph(ei)
+        del ei
+        w_host = out_host = None
+    else:
+        data = synth.interactions(u, i, e, seed=42)
+        w_host = synth.xavier_embeddings(u + i, DIM, seed=42).pin_memory()
+        with torch.no_grad():
+            model.embeddings.weight.copy_(w_host)
+        model.set_graph(data.edge_index().to(dev))
+        del data
+        out_host = torch.empty(u, K_TOP, dtype=torch.int64).pin_memory()
     model.cache_embeddings = False                  # every step recomputes the propagation
     sharded = hdist.ShardedLightGCN(model) if world > 1 else None
-    out_host = torch.empty(u, K_TOP, dtype=torch.int64).pin_memory()
 
     def step_resident():
         return sharded.recommend_all() if sharded else model.recommend_all()
@@ -536,7 +558,7 @@ def run_gpu(args):
     _lib.LAUNCHES = 0
     ms = cuda_ms(step_resident, args.steps, args.warmup, barrier)
     launches = _lib.LAUNCHES // max(1, args.steps + args.warmup)
-    ms_e2e = cuda_ms(step_e2e, max(2, args.steps // 2), 1, barrier)
+    ms_e2e = cuda_ms(step_e2e, max(2, args.steps // 2), 1, barrier) if not sweep else float("nan")
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -563,6 +585,8 @@ def run_gpu(args):
                     "against": "hnm_topk_exact on the all-gathered embeddings of the sharded propagation, every rank"}
         # north_star's own partitioning (item-catalog shards + all-to-all + hnm_merge_topk), same job
         try:
+            if sweep:
+                raise RuntimeError("not run for configs[4] (every rank would hold candidate lists for all 5 M users)")
             sh_items = hdist.ShardedLightGCN(model, mode="items")
             items_mode_ms = cuda_ms(lambda: sh_items.recommend_all(), 2, 1, barrier)
             t = torch.tensor([items_mode_ms], device=dev, dtype=torch.float64)
@@ -593,13 +617,15 @@ def run_gpu(args):
     traffic, traffic_src = ncu_dram_bytes()
     hm1 = world == 1 and args.config == "hm"
     line = {
-        "metric": METRIC, "value": u / ms * 1e3, "unit": "users/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if not sweep else METRIC.replace("3-layer dim-64", "4-layer dim-256"),
+        "value": u / ms * 1e3, "unit": "users/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 propagate / f16xf16->f32 tensor-core nomination / f64 exact rescoring",
         "data": "synthetic",
         "config": config_dict(name, world, sharded.mode if sharded else "users"),
-        "e2e": {"value": u / ms_e2e * 1e3, "unit": "users/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+        "e2e": ({"value": u / ms_e2e * 1e3, "unit": "users/s", "ms_per_step": ms_e2e,
+                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)} if not sweep else
+                {"value": None, "unit": "users/s", "note": "not measured for configs[4]: the table is initialised on the device"}),
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "score_topk_fused_kernel", "achieved": ach_tf,
@@ -629,7 +655,10 @@ def run_gpu(args):
         line["multi_gpu_check"] = mg_check
         line["items_mode_ms"] = items_mode_ms
         line["host_numa_node_rank0"] = numa
-    if world == 1 and not args.no_cpu:
+    if sweep:
+        line["config"]["embedding_init"] = "normal(0, 0.1) on the device, seed 42"
+        line["config"]["l2"] = "inputs far larger than L2 (6.1 GB table)"
+    if world == 1 and not args.no_cpu and not sweep:
         line["gpu_comparators"] = gpu_comparators(model)
         cores = host_threads()
         cpu = CpuArm(u, i, e).step(16384 if args.config == "hm" else u)
@@ -639,7 +668,7 @@ def run_gpu(args):
                        f"{cpu['sample_users']} users in 1024-user batches ({cpu['t_score_sample_s']:.2f} s), "
                        f"extrapolated linearly to {u} users"),
             "t_forward_s": cpu["t_forward_s"], "t_score_sample_s": cpu["t_score_sample_s"]}
-    if world == 1 and args.config == "hm" and not args.no_ncf:
+    if world == 1 and args.config == "hm" and not args.no_ncf and not sweep:
         del model, out_host
         torch.cuda.empty_cache()
         try:
@@ -657,7 +686,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="hm", choices=["hm", "config1", "ncf"])
+    ap.add_argument("--config", default="hm", choices=["hm", "config1", "ncf", "sweep"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ncf", action="store_true", help="skip the NeuralCF (configs[3]) object of the headline line")
     args = ap.parse_args()

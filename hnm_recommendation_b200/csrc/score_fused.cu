@@ -1466,11 +1466,15 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   if ((rc = make_map(&map_u, users_f16, users_padded, dim)) != HNM_OK) return rc;
   if ((rc = make_map(&map_i, items_f16, items_padded, dim)) != HNM_OK) return rc;
   static const int debug_mode = getenv("HNM_FUSED_DEBUG") ? atoi(getenv("HNM_FUSED_DEBUG")) : 0;
-  static const int boot_tiles = getenv("HNM_FUSED_BOOT") ? std::max(1, atoi(getenv("HNM_FUSED_BOOT"))) : kBootTiles;
+  static const int boot_env = getenv("HNM_FUSED_BOOT") ? std::max(1, atoi(getenv("HNM_FUSED_BOOT"))) : 0;
   static const int refresh_div = getenv("HNM_FUSED_REFRESH") ? std::max(1, atoi(getenv("HNM_FUSED_REFRESH"))) : 4;
   static const uint32_t wait_hint = getenv("HNM_FUSED_WAIT_NS") ? (uint32_t)atoi(getenv("HNM_FUSED_WAIT_NS")) : kWaitHintNs;
   const int num_user_tiles = (int)(users_padded / kUserTile);
   const int num_tiles = (int)(items_padded / kItemTile);
+  // Seed tiles: the number of chunks a row nominates grows like (k + 3) ln(#item tiles / #seed tiles), so the seed
+  // scales with the catalog (2 % of it, at least 16 tiles): at 1 M items 16 seed tiles left 3 % of the users with
+  // an overflowing list (profiles/r2_sweep_n8_first.json), for 2 % more MMA work nobody overflows.
+  const int boot_tiles = boot_env ? boot_env : std::max(kBootTiles, num_tiles / 48);
   const int grid = fused_grid(num_user_tiles);
   SplitPlan sp = make_plan(num_user_tiles, num_tiles, grid);
   size_t off_count = 0, off_thresh = 0;

@@ -18,6 +18,7 @@ from ._lib import call, ptr, stream
 USER_BLOCK = 128
 ITEM_TILE = 128
 CAND_CAP = 192                 # candidate entries (32-column chunks) per user; ~100 on average at the H&M shape
+CAND_CAP_MAX = 256             # ... the count grows like (k + 3) ln(#item tiles): catalogs beyond ~250 k items take the maximum
 CAND_WORDS = 5                 # HNM_FUSED_CAND_BYTES / 4 (16 bytes of group maxima + 4 bytes of column per entry)
 SIG_WORDS = 32                 # HNM_FUSED_SIG_WORDS
 K_MAX = 16
@@ -48,6 +49,7 @@ class FusedScorer:
         if self.dim not in FUSED_DIMS or int(self.user_emb.size(1)) != self.dim:
             raise ValueError(f"the fused scorer takes embedding dimensions {FUSED_DIMS}")
         self.items_padded = (self.num_items + ITEM_TILE - 1) // ITEM_TILE * ITEM_TILE
+        self.cand_cap = CAND_CAP if self.num_items <= 250_000 else CAND_CAP_MAX
         with torch.cuda.device(dev):
             # any fp32 vector is a valid centre; the mean row is the one that shrinks the items most
             self.center = self.item_emb.mean(dim=0, dtype=torch.float64).float().contiguous() if center else None
@@ -269,7 +271,7 @@ class FusedScorer:
                 call("hnm_score_pack_users", ptr(self.user_emb), ptr(rid), n, padded, self.dim, ptr(users_f16),
                      ptr(inv_scale), s)
                 user_base = self.user_emb
-            cand = torch.empty(n * CAND_CAP * CAND_WORDS, dtype=torch.int32, device=dev)
+            cand = torch.empty(n * self.cand_cap * CAND_WORDS, dtype=torch.int32, device=dev)
             count = torch.empty(n, 2, dtype=torch.int32, device=dev)     # one list per thread of the row
             thresh = torch.empty(n, dtype=torch.float32, device=dev)
             ws_bytes = int(_lib.load().hnm_score_topk_fused_workspace_bytes(padded, self.items_padded))
@@ -285,12 +287,12 @@ class FusedScorer:
                      ptr(sig), s)
             note("fused_begin")
             call("hnm_score_topk_fused", ptr(users_f16), n, padded, ptr(self.items_f16), self.num_items,
-                 self.items_padded, self.dim, sel, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(sig), ptr(ws),
+                 self.items_padded, self.dim, sel, ptr(cand), self.cand_cap, ptr(count), ptr(thresh), ptr(sig), ptr(ws),
                  ws_bytes, s)
             note("fused_end")
             note("rescore_begin")
             call("hnm_rescore_topk", ptr(user_base), ptr(self.item_emb), ptr(rid), n, self.dim, self.item_begin,
-                 self.num_items, ptr(cand), CAND_CAP, ptr(count), ptr(thresh), ptr(inv_scale), ptr(self.item_params),
+                 self.num_items, ptr(cand), self.cand_cap, ptr(count), ptr(thresh), ptr(inv_scale), ptr(self.item_params),
                  ptr(self.center), ptr(ex_ptr), ptr(excl[1]), k, ptr(ids[b0:b1]), ptr(sc[b0:b1]), ptr(cert[b0:b1]), s)
             note("rescore_end")
         if mark:

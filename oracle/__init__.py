@@ -21,3 +21,4 @@ from .lightgcn_oracle import (  # noqa: F401
     recommend, recommend_exact, LightGCNOracle, bpr_loss,
 )
 from .ncf_oracle import ncf_forward, ncf_predict_all_items, NeuralCFOracle  # noqa: F401
+from .mf_oracle import mf_forward, mf_predict_all_items, mf_rank_scores_fp64, mf_recommend_exact  # noqa: F401

@@ -127,3 +127,19 @@ def test_bpr_loss_oracle_matches_reference(path):
     assert len(TRAIN) >= 2
     assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
     assert_close(w.grad, g["grad"], rtol=1e-4, atol_scale=1e-5, what="gradient")
+
+
+@pytest.mark.parametrize("path", golden_files("mf"), ids=lambda p: p.split("mf_")[-1][:-4])
+def test_mf_oracle_matches_reference_golden(path):
+    """oracle/mf_oracle.py against the outputs of the reference's own matrix_factorization.py."""
+    g = load_golden(path)
+    state = {k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state.")}
+    uids, iids = torch.from_numpy(g["user_ids"]), torch.from_numpy(g["item_ids"])
+    assert torch.allclose(O.mf_forward(state, uids, iids), torch.from_numpy(g["pred"]), rtol=1e-6, atol=1e-9)
+    au = torch.from_numpy(g["all_user_ids"])
+    scores = O.mf_predict_all_items(state, au)
+    assert torch.allclose(scores, torch.from_numpy(g["scores"]), rtol=1e-6, atol=1e-9)
+    k = int(g["top_k"])
+    canon = O.mf_recommend_exact(state, au, k)
+    # the exact ranking differs from the fp32 one only at near-ties
+    assert int((canon != torch.from_numpy(g["topk_canonical"])).any(dim=1).sum()) <= 2
