@@ -914,7 +914,7 @@ __global__ void pack_kernel(const float* __restrict__ emb, const int64_t* __rest
 }
 
 // ----------------------------------------------------------------------------- rescoring
-constexpr int kMaxPerLane = 8;   // candidate capacity handled = 32 * kMaxPerLane
+constexpr int kMaxPerLane = 32;  // candidate capacity handled = 32 * kMaxPerLane (HNM_FUSED_CAND_MAX)
 constexpr int kGroup = 4;        // items per nominated group (select32)
 constexpr int kMaxGroups = 64;   // surviving groups hnm_rescore_topk can take per user
 constexpr int kMaxContenders = 128;  // rescored items above the cut it can rank per user
@@ -1384,7 +1384,7 @@ extern "C" int hnm_score_pack_users(const float* emb, const int64_t* row_ids, in
 }
 
 namespace {
-constexpr int kSplitCap = 128;      // candidate entries (32-column chunks) per (sliced user, item slice)
+constexpr int kSplitCap = 256;      // candidate entries (32-column chunks) per (sliced user, item slice)
 constexpr int kMinSliceTiles = 32;  // an item slice is at least this many item tiles
 
 int fused_mu() { return kMU; }

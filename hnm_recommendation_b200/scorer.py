@@ -18,15 +18,18 @@ from ._lib import call, ptr, stream
 USER_BLOCK = 128
 ITEM_TILE = 128
 CAND_CAP = 192                 # candidate entries (32-column chunks) per user; ~100 on average at the H&M shape
-CAND_CAP_MAX = 256             # ... the count grows like (k + 3) ln(#item tiles): catalogs beyond ~250 k items take the maximum
+CAND_CAP_BIG = 384             # ... the count grows like (k + margin) ln(#item tiles): catalogs beyond ~250 k items
+CAND_CAP_MAX = 1024            # HNM_FUSED_CAND_MAX
 CAND_WORDS = 5                 # HNM_FUSED_CAND_BYTES / 4 (16 bytes of group maxima + 4 bytes of column per entry)
 SIG_WORDS = 32                 # HNM_FUSED_SIG_WORDS
 K_MAX = 16
 FUSED_DIMS = (64, 128, 256)    # embedding dimensions of the tensor-core path (K chunks of 64)
 SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maximum
+SEL_MARGIN_BIG = 5             # ... catalogs beyond ~250 k items: the top scores lie closer together (profiles/r2_margin_sweep_configs4.jsonl)
 MAX_USERS_PER_LAUNCH = 1 << 21
 TIER2_MIN_USERS = 32            # fewer uncertified users go straight to the exact kernel
 TIER2_SLOTS = 2048              # size of the second pass when it is enqueued without knowing the count (no host sync)
+TIER2_MARGIN = 12               # tau of the second pass tracks the (k + 12)-th best bucket maximum
 
 
 class FusedScorer:
@@ -37,19 +40,28 @@ class FusedScorer:
         return dim in FUSED_DIMS and 1 <= k <= K_MAX and num_items >= 2 * ITEM_TILE
 
     def __init__(self, user_emb: torch.Tensor, item_emb: torch.Tensor, item_begin: int = 0,
-                 center: bool = True, sel_margin: int = SEL_MARGIN):
+                 center: bool = True, sel_margin: Optional[int] = None, tier2_margin: int = TIER2_MARGIN,
+                 cand_cap: Optional[int] = None):
         _lib.require_device()
         self.user_emb = user_emb.contiguous()
         self.item_emb = item_emb.contiguous()
         self.item_begin = item_begin
-        self.sel_margin = sel_margin
+        self.tier2_margin = tier2_margin
         dev = self.item_emb.device
         self.num_items = int(self.item_emb.size(0))
         self.dim = int(self.item_emb.size(1))
         if self.dim not in FUSED_DIMS or int(self.user_emb.size(1)) != self.dim:
             raise ValueError(f"the fused scorer takes embedding dimensions {FUSED_DIMS}")
         self.items_padded = (self.num_items + ITEM_TILE - 1) // ITEM_TILE * ITEM_TILE
-        self.cand_cap = CAND_CAP if self.num_items <= 250_000 else CAND_CAP_MAX
+        big = self.num_items > 250_000
+        self.sel_margin = int(sel_margin) if sel_margin is not None else (SEL_MARGIN_BIG if big else SEL_MARGIN)
+        self.cand_cap = int(cand_cap) if cand_cap else (CAND_CAP_BIG if big else CAND_CAP)
+        if self.cand_cap % 2 or not 2 <= self.cand_cap <= CAND_CAP_MAX:
+            raise ValueError(f"cand_cap must be even and at most {CAND_CAP_MAX}")
+        # share of the users the sync-free second pass has slots for: near-ties between the k-th score and tau
+        # become more frequent with the catalog size and the embedding dimension (0.07 % of the users at the
+        # H&M shape, 0.7 % at 1 M items x 256)
+        self.tier2_share = 1.0 / 64 if big else 1.0 / 512
         with torch.cuda.device(dev):
             # any fp32 vector is a valid centre; the mean row is the one that shrinks the items most
             self.center = self.item_emb.mean(dim=0, dtype=torch.float64).float().contiguous() if center else None
@@ -140,7 +152,7 @@ class FusedScorer:
             if n_bad:
                 bad_uids = bad if uids is None else uids[bad]
                 sub_excl = self._exclusions(bad_uids, filter_items) if excl[0] is not None else (None, None)
-                sel2 = min(32, k + 12)
+                sel2 = min(32, k + self.tier2_margin)
                 # the second tensor-core pass slices the item range of its few user tiles over the CTAs
                 # (SplitPlan in csrc/score_fused.cu), so it is cheap for any count; only a handful of users
                 # go straight to the exact kernel (which splits the catalog over CTAs too)
@@ -191,8 +203,8 @@ class FusedScorer:
         """Tier 2 on a fixed number of slots, no host round trip (see topk).  ids_full / sc_full carry one spare
         row at index `total` that absorbs the write-back of the unused slots."""
         dev = self.item_emb.device
-        slots = min(total, TIER2_SLOTS)
-        sel2 = min(32, k + 12)
+        slots = min(total, max(TIER2_SLOTS, int(total * self.tier2_share)))
+        sel2 = min(32, k + self.tier2_margin)
         bad = torch.nonzero_static(cert != 1, size=slots, fill_value=-1).view(-1)       # device-side compaction
         valid = bad >= 0
         safe = bad.clamp(min=0)

@@ -222,7 +222,7 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
 #define HNM_FUSED_DIM 64            /* K chunk of the tensor-core path; supported embedding dimensions: 64, 128, 256 */
 #define HNM_FUSED_USER_TILE 128     /* users per accumulator (UMMA M); users_padded must be a multiple */
 #define HNM_FUSED_ITEM_TILE 128     /* items per MMA tile (UMMA N); items_padded must be a multiple */
-#define HNM_FUSED_CAND_MAX 256      /* largest cand_cap (entries per user) */
+#define HNM_FUSED_CAND_MAX 1024     /* largest cand_cap (entries per user) */
 #define HNM_FUSED_CAND_BYTES 20     /* bytes per candidate entry (16 in the q array + 4 in the col array) */
 #define HNM_FUSED_SIG_WORDS 32      /* uint32 words of a user's exclusion signature (1 024 bits) */
 
