@@ -65,8 +65,8 @@ def ncu_dram_bytes():
 def config_dict(name, world, shard_mode="users"):
     """The workload description; identical for the GPU arm and the reference arm of the same run."""
     par = "single GPU" if world == 1 else (
-        f"{shard_mode}-sharded scoring + user-partitioned propagation (one 27 MB all-reduce of the item block "
-        f"per layer) x{world}")
+        f"{shard_mode}-sharded scoring + user-partitioned propagation (item-row partial sums exchanged through "
+        f"NVLink peer memory inside the layer kernels) x{world}")
     return {"workload": name, "top_k": K_TOP, "embedding_init": "xavier_uniform seed 42",
             "l2": "inputs larger than L2 (378 MB embedding table, 175 MB fp16 user operand); no explicit flush",
             "parallelism": par}
@@ -494,6 +494,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # NCCL's version banner goes to stdout; the line below is the output
         dist.init_process_group("nccl", device_id=dev)
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
@@ -530,25 +531,28 @@ def run_gpu(args):
         return sharded.recommend_all() if sharded else model.recommend_all()
 
     if sharded and sharded.mode == "users":
-        # a rank only reads its own users' rows and the item block of the table, and owns one slice of the result
+        # the table crosses PCIe once over the job: a rank uploads its own users' rows and its 1/G slice of the item
+        # block (completed over NVLink: ShardedLightGCN.load_embeddings_from_host), and owns one slice of the result
         u0, u1 = sharded.plan.user_rows[rank]
-        h2d_rows = [(u0, u1), (u, u + i)]
+        h2d_rows = [(u0, u1), sharded.plan.item_rows[rank]]
         d2h_rows = (u0, u1)
+    elif sharded:
+        h2d_rows = [sharded.plan.user_rows[rank], sharded.plan.item_rows[rank]]
+        d2h_rows = (0, u) if rank == 0 else (0, 0)
     else:
         h2d_rows = [(0, u + i)]
-        d2h_rows = (0, u) if rank == 0 else (0, 0)
+        d2h_rows = (0, u)
     h2d_bytes = sum(b - a for a, b in h2d_rows) * DIM * 4
     d2h_bytes = (d2h_rows[1] - d2h_rows[0]) * K_TOP * 8
 
     def step_e2e():
-        wt = model.embeddings.weight.data
-        for a, b in h2d_rows:
-            wt[a:b].copy_(w_host[a:b], non_blocking=True)                   # H2D of the step's input
         if sharded:
+            sharded.load_embeddings_from_host(w_host)                       # H2D of the step's input (+ NVLink)
             ids = sharded.recommend_all()
             a, b = d2h_rows
             out_host[a:b].copy_(ids[a:b], non_blocking=True)                # D2H of the step's result
         else:
+            model.embeddings.weight.data.copy_(w_host, non_blocking=True)   # H2D of the step's input
             model.recommend_all(out_host=out_host)                          # D2H streamed chunk by chunk
         torch.cuda.current_stream().synchronize()
 
@@ -560,10 +564,19 @@ def run_gpu(args):
     launches = _lib.LAUNCHES // max(1, args.steps + args.warmup)
     ms_e2e = cuda_ms(step_e2e, max(2, args.steps // 2), 1, barrier) if not sweep else float("nan")
     clocks = sampler.stop() if rank == 0 else None
+    # the upload alone (same copies as in step_e2e), to split the e2e overhead into PCIe and the rest
+    h2d_ms = float("nan")
+    if not sweep:
+        def upload():
+            if sharded:
+                sharded.load_embeddings_from_host(w_host)
+            else:
+                model.embeddings.weight.data.copy_(w_host, non_blocking=True)
+        h2d_ms = cuda_ms(upload, 3, 1, barrier)
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, h2d_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+        ms, ms_e2e, h2d_ms = t.tolist()
         t = torch.tensor([h2d_bytes, d2h_bytes], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         h2d_bytes, d2h_bytes = (int(x) for x in t.tolist())
@@ -598,6 +611,9 @@ def run_gpu(args):
 
     # per-stage kernel times on this rank (CUDA events on the launching stream)
     stages = hdist.profile_stages(model, sharded, steps=max(2, args.steps // 2))
+    if sharded is None and not sweep:
+        # the serving default of the reference (scripts/serve.py:350-352): every user's own purchases filtered out
+        stages["filtered_step_ms"] = cuda_ms(lambda: model.recommend_all(filter_purchased=True), 2, 1, None)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -624,7 +640,13 @@ def run_gpu(args):
         "data": "synthetic",
         "config": config_dict(name, world, sharded.mode if sharded else "users"),
         "e2e": ({"value": u / ms_e2e * 1e3, "unit": "users/s", "ms_per_step": ms_e2e,
-                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)} if not sweep else
+                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                 "h2d_ms_alone": h2d_ms,
+                 "how": ("every rank uploads its own users' rows and its 1/G slice of the item block from pinned host "
+                         "memory (the table crosses PCIe once over the job), the item block is completed over NVLink; "
+                         "every rank reads its own slice of the all-gathered result back" if world > 1 else
+                         "whole table uploaded from pinned host memory, result streamed back chunk by chunk")}
+                if not sweep else
                 {"value": None, "unit": "users/s", "note": "not measured for configs[4]: the table is initialised on the device"}),
         "gpu_launches": launches,
         "clocks": clocks,

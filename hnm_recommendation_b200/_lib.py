@@ -43,6 +43,8 @@ _SIGNATURES = {
     "hnm_score_pack_items": (C.c_int, [P, I64, I64, I32, P, P, P, P]),
     "hnm_score_pack_users": (C.c_int, [P, P, I64, I64, I32, P, P, P]),
     "hnm_absmax": (C.c_int, [P, I64, P, I32, P, P]),
+    "hnm_column_mean": (C.c_int, [P, I64, I32, P, P, I64, P]),
+    "hnm_column_mean_workspace_bytes": (C.c_int64, [I32]),
     "hnm_score_topk_fused": (C.c_int, [P, I64, I64, P, I64, I64, I32, I32, P, I32, P, P, P, P, I64, P]),
     "hnm_exclusion_signature": (C.c_int, [P, P, I64, I64, I64, P, P]),
     "hnm_score_topk_fused_workspace_bytes": (C.c_int64, [I64, I64]),
@@ -95,7 +97,7 @@ def check(fn: str, code: int) -> None:
 
 
 LAUNCHES = 0          # kernels launched through call() since the counter was last reset (bench.py reads it)
-_LAUNCHES_PER_CALL = {"hnm_graph_build": 3}
+_LAUNCHES_PER_CALL = {"hnm_graph_build": 3, "hnm_column_mean": 2}
 
 
 def call(fn: str, *args) -> None:

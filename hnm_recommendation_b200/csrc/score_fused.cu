@@ -11,28 +11,29 @@
 //                                 per-slice lists of the user tiles whose item range was sliced over the CTAs
 //   hnm_rescore_topk            : exact fp64 scores of the survivors, canonical top-k, certificate
 //
-// Kernel shape (DESIGN.md "score_topk"): one persistent CTA per SM, 16 warps:
-//   warp 0   TMA producer      A: 3 user tiles x [128 x 64] fp16 per "super tile" (double buffered),
-//                              B: item tiles [128 x 64] fp16 through a 6-stage ring
-//   warps 1-3 MMA issuers      warp 1+m issues user tile m; work item w = (item tile, user tile m),
-//                              accumulator slot = w mod 4: 4 x tcgen05.mma M128 N128 K16 into TMEM
-//                              columns [128 slot, 128 slot + 128); warp 2 also owns the TMEM allocation
-//   warps 4..15  epilogue, 3 warpgroups; warpgroup m drains every accumulator of user tile m,
-//                thread = one user row (TMEM lane).
-// Three user tiles share each 16 KB item tile (L2 -> smem stream ~40 GB/s per SM at full rate).  Each
-// user tile owns one accumulator, its own issuer thread and its own epilogue warpgroup: while
-// warpgroup m drains its accumulator the tensor pipe works for the other two user tiles.
+// Kernel shape: one persistent CTA per SM, 20 warps = 640 threads:
+//   warp 0   TMA producer      A: 2 user tiles x KC chunks of [128 x 64] fp16 per pass (double buffered up to
+//                              d = 128), B: (item tile, K chunk) stages [128 x 64] fp16 through a ring
+//   warps 1-2  MMA issuers     warp 1+m, one elected thread, issues user tile m: per item tile 4 x KC
+//                              tcgen05.mma M128 N128 K16 into one of the tile's two accumulators
+//                              (2 x 2 x 128 = all 512 TMEM columns); warp 2 also owns the TMEM allocation
+//   warp 3     idle; the four control warps hand registers to the epilogue (setmaxnreg)
+//   warps 4..19  epilogue: 2 threads per user row (TMEM lane), each draining 64 of an accumulator's 128
+//                columns; the two threads of a row share the row's threshold through shared memory and a
+//                64-thread named barrier.
+// While the epilogue drains one accumulator of a user tile the tensor pipe fills the other one.
 //
-// Select (per user row, all in registers): 32 bucket maxima (bucket = position of the 4-column
-// group inside an item tile).  Bucket maxima belong to distinct items, so the kth_sel-th
-// largest of them, tau, is a lower bound on the kth_sel-th best score seen so far.  A column group
-// is inspected element-wise only if its maximum exceeds tau; survivors are appended to the user's
-// candidate list in global memory.  tau is refreshed (in-place sorting network over the bucket
-// registers) every time the number of item tiles seen has grown by 1/4.  The first kBootTiles item
-// tiles are run twice: once to seed the buckets, once to collect.
+// Select (per user row): 32 bucket maxima in shared memory (bucket = position of a 4-column group inside an
+// item tile), 16 per thread of the row.  Bucket maxima belong to distinct items, so the kth_sel-th largest of
+// them, tau, is a lower bound on the kth_sel-th best score seen so far.  The hot path of a 32-column chunk is
+// 8 group maxima, their maximum and one compare; only a chunk that beats tau updates the buckets and appends
+// ONE entry to the user's candidate list in global memory (the 8 group maxima cut to bf16 + the first column).
+// tau is refreshed (32-wide sorting network) every time the number of item tiles seen has grown by 1/4.  The
+// first seed tiles (kBootTiles, more for large catalogs) are run twice: once to seed the buckets, once to collect.
 //
-// Work distribution (SplitPlan below): whole passes of 3 user tiles x the whole catalog per CTA, and the
-// left-over tiles in triples whose item range is cut into slices, one (triple, slice) per CTA.
+// Work distribution (SplitPlan below): whole passes of 2 user tiles x the whole catalog per CTA, and the
+// left-over tiles in pairs whose item range is cut into slices, one (pair, slice) per CTA; merge_split_kernel
+// then builds one list per sliced user.
 #include <algorithm>
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -711,20 +712,56 @@ __device__ __forceinline__ uint32_t cand_half(const uint4& q, int h) {     // 16
   return (h & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
+// The sub-lists of a user are short (a slice sees a fraction of the catalog), so walking them one by one leaves
+// most lanes idle and chains four dependent global loads per sub-list.  Instead the counts are loaded once,
+// lane-parallel, into exclusive prefix sums in shared memory, and both sweeps run over the FLAT entry index
+// (32 entries per step whatever sub-list they belong to; a lane finds its sub-list by bisection in shared
+// memory), two steps' loads in flight at a time.
+struct FlatLists {
+  const int32_t* pre;    // [lists + 1] exclusive prefix sums of the counts (shared memory)
+  int lists;
+  __device__ __forceinline__ void locate(int f, int& l, int& i) const {      // largest l with pre[l] <= f
+    int lo = 0, hi = lists;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (pre[mid] <= f) lo = mid; else hi = mid;
+    }
+    l = lo;
+    i = f - pre[lo];
+  }
+};
+
 __global__ void __launch_bounds__(128)
 merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand, int cap,
                    int32_t* __restrict__ cand_count, float* __restrict__ cand_thresh) {
+  extern __shared__ int32_t merge_pre[];
   const int lane = threadIdx.x & 31;
-  const int lu = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int wib = threadIdx.x >> 5;
+  const int lu = (int)blockIdx.x * 4 + wib;
   const int row = sp.tile0 * kUserTile + lu;
-  if (row >= num_users) return;
+  if (row >= num_users) return;                      // warps are independent: no block-wide barrier below
   const size_t base = (size_t)lu * sp.slices;
   const int half_cap = sp.cap / kHalves;
   const int lists = sp.slices * kHalves;             // sub-list l = (slice l / 2, column half l % 2)
+  int32_t* pre = merge_pre + wib * (lists + 1);
   float thr = -INFINITY;
   bool over = false;
   for (int s = lane; s < sp.slices; s += 32) thr = fmaxf(thr, sp.thresh[base + s]);
-  for (int l = lane; l < lists; l += 32) over |= sp.count[base * kHalves + l] > half_cap;
+  int entries = 0;
+  for (int l0 = 0; l0 < lists; l0 += 32) {
+    const int l = l0 + lane;
+    const int c = l < lists ? sp.count[base * kHalves + l] : 0;
+    over |= c > half_cap;
+    int incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (l < lists) pre[l] = entries + incl - c;
+    entries += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) pre[lists] = entries;
 #pragma unroll
   for (int off = 16; off; off >>= 1) thr = fmaxf(thr, __shfl_xor_sync(0xffffffffu, thr, off));
   over = __any_sync(0xffffffffu, over);
@@ -736,21 +773,36 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand
     }
     return;
   }
+  __syncwarp();
+  const FlatLists fl{pre, lists};
+  auto entry_of = [&](int f, uint4& q, uint32_t& col, bool want_col) {
+    int l, i;
+    fl.locate(f, l, i);
+    const CandList in = sp.cand.at((base + (l >> 1)) * sp.cap + (l & 1) * half_cap);
+    q = in.q[i];
+    if (want_col) col = in.col[i];
+  };
   // kth_sel-th largest stored group maximum (its lower bound: the stored 16 bits are a truncation):
   // running top 32 over all sub-lists, lane i = (i+1)-th largest
   float top = -INFINITY;
-  for (int l = 0; l < lists; ++l) {
-    const int cnt = sp.count[base * kHalves + l];
-    const CandList in = sp.cand.at((base + (l >> 1)) * sp.cap + (l & 1) * half_cap);
-    for (int i0 = 0; i0 < cnt; i0 += 32) {
-      const bool have = i0 + lane < cnt;
-      uint4 q = make_uint4(0u, 0u, 0u, 0u);
-      if (have) q = in.q[i0 + lane];
+  for (int f0 = 0; f0 < entries; f0 += 64) {
+    uint4 qs[2];
+    bool have[2];
+    uint32_t unused = 0u;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int f = f0 + 32 * j + lane;
+      have[j] = f < entries;
+      qs[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (have[j]) entry_of(f, qs[j], unused, false);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
 #pragma unroll 1
       for (int h = 0; h < 8; ++h) {
         float lo, hi;
-        cand_bounds(cand_half(q, h), lo, hi);
-        float v = have ? lo : -INFINITY;
+        cand_bounds(cand_half(qs[j], h), lo, hi);
+        float v = have[j] ? lo : -INFINITY;
         if (!__any_sync(0xffffffffu, v > thr)) continue;        // nothing here can move a threshold above thr0
 #pragma unroll
         for (int size = 2; size <= 32; size <<= 1) {
@@ -771,29 +823,34 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand
   // row's ordinary storage as ONE list: all `cap` entries belong to the first half, the second stays empty
   const CandList out = cand.at((size_t)row * cap);
   int total = 0;
-  for (int l = 0; l < lists; ++l) {
-    const int cnt = sp.count[base * kHalves + l];
-    const CandList in = sp.cand.at((base + (l >> 1)) * sp.cap + (l & 1) * half_cap);
-    for (int i0 = 0; i0 < cnt; i0 += 32) {
-      const int i = i0 + lane;
-      uint4 q = make_uint4(0u, 0u, 0u, 0u);
-      uint32_t col = 0u;
+  for (int f0 = 0; f0 < entries; f0 += 64) {
+    uint4 qs[2];
+    uint32_t cols[2];
+    bool have[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int f = f0 + 32 * j + lane;
+      have[j] = f < entries;
+      qs[j] = make_uint4(0u, 0u, 0u, 0u);
+      cols[j] = 0u;
+      if (have[j]) entry_of(f, qs[j], cols[j], true);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
       bool keep = false;
-      if (i < cnt) {
-        q = in.q[i];
-        col = in.col[i];
+      if (have[j]) {
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
           float lo, hi;
-          cand_bounds(cand_half(q, h), lo, hi);
+          cand_bounds(cand_half(qs[j], h), lo, hi);
           keep |= hi > thr;
         }
       }
       const unsigned mask = __ballot_sync(0xffffffffu, keep);
       const int pos = total + __popc(mask & ((1u << lane) - 1u));
       if (keep && pos < cap) {
-        out.q[pos] = q;
-        out.col[pos] = col;
+        out.q[pos] = qs[j];
+        out.col[pos] = cols[j];
       }
       total += __popc(mask);
     }
@@ -1335,7 +1392,65 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim) {
   return r == CUDA_SUCCESS ? HNM_OK : HNM_E_DRIVER;
 }
 
+
+// Column means of a [rows, D] table in two deterministic steps (fp64 sums: block partials over contiguous row
+// ranges, then the partials in block order) -- the centre of the item shard for hnm_score_pack_items.
+template <int D>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, int64_t rows, double* __restrict__ partial) {
+  constexpr int C4 = D / 4, RL = 256 / C4;
+  __shared__ double sm[RL][D];
+  const int c = threadIdx.x % C4, r = threadIdx.x / C4;
+  const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t b = (int64_t)blockIdx.x * per, e = min(rows, b + per);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int64_t i = b + r; i < e; i += RL) {
+    const float4 v = ldg_f4(x + (size_t)i * D + c * 4);
+    a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+  }
+  sm[r][c * 4 + 0] = a0; sm[r][c * 4 + 1] = a1; sm[r][c * 4 + 2] = a2; sm[r][c * 4 + 3] = a3;
+  __syncthreads();
+  for (int t = threadIdx.x; t < D; t += 256) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < RL; ++j) acc += sm[j][t];
+    partial[(size_t)blockIdx.x * D + t] = acc;
+  }
+}
+
+__global__ void colmean_finish_kernel(const double* __restrict__ partial, int blocks, int dim, int64_t rows,
+                                      float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= dim) return;
+  double acc = 0.0;
+  for (int b = 0; b < blocks; ++b) acc += partial[(size_t)b * dim + t];
+  out[t] = (float)(acc / (double)rows);
+}
 }  // namespace
+
+extern "C" int64_t hnm_column_mean_workspace_bytes(int32_t dim) {
+  if (dim <= 0) return -1;
+  return (int64_t)hnm_num_sms() * 4 * dim * (int64_t)sizeof(double);
+}
+
+extern "C" int hnm_column_mean(const float* emb, int64_t rows, int32_t dim, float* out_mean, void* workspace,
+                               int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!emb || !out_mean || !workspace) return HNM_E_NULL;
+  if (dim != 64 && dim != 128 && dim != 256) return HNM_E_DIM;
+  if (rows <= 0) return HNM_E_RANGE;
+  if (!hnm_aligned16(emb) || (reinterpret_cast<uintptr_t>(workspace) & 7)) return HNM_E_ALIGN;
+  if (workspace_bytes < hnm_column_mean_workspace_bytes(dim)) return HNM_E_WORKSPACE;
+  const int blocks = (int)std::min<int64_t>((int64_t)hnm_num_sms() * 4, (rows + 63) / 64);
+  double* partial = reinterpret_cast<double*>(workspace);
+  if (dim == 64) colsum_kernel<64><<<blocks, 256, 0, stream>>>(emb, rows, partial);
+  else if (dim == 128) colsum_kernel<128><<<blocks, 256, 0, stream>>>(emb, rows, partial);
+  else colsum_kernel<256><<<blocks, 256, 0, stream>>>(emb, rows, partial);
+  HNM_LAUNCH_CHECK();
+  colmean_finish_kernel<<<(dim + 63) / 64, 64, 0, stream>>>(partial, blocks, dim, rows, out_mean);
+  HNM_LAUNCH_CHECK();
+  return HNM_OK;
+}
 
 extern "C" int hnm_absmax(const float* emb, int64_t count, const float* center, int32_t dim, float* out_absmax,
                           void* stream_) {
@@ -1474,7 +1589,8 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   // Seed tiles: the number of chunks a row nominates grows like (k + 3) ln(#item tiles / #seed tiles), so the seed
   // scales with the catalog (2 % of it, at least 16 tiles): at 1 M items 16 seed tiles left 3 % of the users with
   // an overflowing list (profiles/r2_sweep_n8_first.json), for 2 % more MMA work nobody overflows.
-  const int boot_tiles = boot_env ? boot_env : std::max(kBootTiles, num_tiles / 48);
+  // seed tiles: 16 up to ~1 000 item tiles (the H&M catalog), then 1/48 of the catalog in steps of 16 (162 -> 160 at 1 M items)
+  const int boot_tiles = boot_env ? boot_env : std::max(kBootTiles, num_tiles / 48 / 16 * 16);
   const int grid = fused_grid(num_user_tiles);
   SplitPlan sp = make_plan(num_user_tiles, num_tiles, grid);
   size_t off_count = 0, off_thresh = 0;
@@ -1503,7 +1619,7 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
     const int64_t split_users = std::min<int64_t>((int64_t)sp.triples * sp.mu * kUserTile,
                                                   num_users - (int64_t)sp.tile0 * kUserTile);
     if (split_users > 0) {
-      merge_split_kernel<<<(unsigned)((split_users + 3) / 4), 128, 0, stream>>>(sp, (int)num_users, kth_sel, cand_list(cand, (size_t)num_users, cand_cap), cand_cap,
+      merge_split_kernel<<<(unsigned)((split_users + 3) / 4), 128, 4 * (sp.slices * kHalves + 1) * sizeof(int32_t), stream>>>(sp, (int)num_users, kth_sel, cand_list(cand, (size_t)num_users, cand_cap), cand_cap,
                                                                                 cand_count, cand_thresh);
       HNM_LAUNCH_CHECK();
     }

@@ -177,6 +177,31 @@ class ShardedLightGCN:
         self._scorer = None
         return final[: m.num_users], final[m.num_users:]
 
+    # ---------------------------------------------------------------- parameters from the host
+    def load_embeddings_from_host(self, table: torch.Tensor) -> int:
+        """Upload a new embedding table ([U + I, d] fp32, pinned host memory, the same on every rank) so that it
+        crosses PCIe ONCE over the whole job: every rank copies the rows it owns -- its users and its 1/G slice of
+        the item block -- and the item block (all of which every rank reads) is completed over NVLink with one
+        in-place all-gather.  In "items" mode the user rows are all-gathered too.  Enqueued on the current stream,
+        no host synchronisation.  Returns the host-to-device bytes of this rank."""
+        m, p = self.model, self.plan
+        w = m.embeddings.weight.data
+        if tuple(table.shape) != tuple(w.shape) or table.dtype != w.dtype:
+            raise ValueError("table must have the shape and dtype of embeddings.weight")
+        rows = 0
+        for a, b in (p.user_rows[p.rank], p.item_rows[p.rank]):
+            if b > a:
+                w[a:b].copy_(table[a:b], non_blocking=True)
+                rows += b - a
+        if self.coll.world > 1:
+            self.coll.allgather_rows(w, p.item_rows)
+            if self.mode != "users":
+                self.coll.allgather_rows(w, p.user_rows)
+        if hasattr(m, "invalidate"):
+            m.invalidate()
+        self._scorer = None
+        return rows * w.size(1) * w.element_size()
+
     # ---------------------------------------------------------------- recommend
     def recommend_all(self, k: Optional[int] = None, return_scores: bool = False):
         m, p = self.model, self.plan

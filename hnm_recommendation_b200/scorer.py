@@ -28,7 +28,7 @@ SEL_MARGIN = 3                 # tau tracks the (k + margin)-th best bucket maxi
 SEL_MARGIN_BIG = 5             # ... catalogs beyond ~250 k items: the top scores lie closer together (profiles/r2_margin_sweep_configs4.jsonl)
 MAX_USERS_PER_LAUNCH = 1 << 21
 TIER2_MIN_USERS = 32            # fewer uncertified users go straight to the exact kernel
-TIER2_SLOTS = 2048              # size of the second pass when it is enqueued without knowing the count (no host sync)
+TIER2_SLOTS = 512               # smallest second pass when it is enqueued without knowing the count (no host sync)
 TIER2_MARGIN = 12               # tau of the second pass tracks the (k + 12)-th best bucket maximum
 
 
@@ -61,10 +61,16 @@ class FusedScorer:
         # share of the users the sync-free second pass has slots for: near-ties between the k-th score and tau
         # become more frequent with the catalog size and the embedding dimension (0.07 % of the users at the
         # H&M shape, 0.7 % at 1 M items x 256)
-        self.tier2_share = 1.0 / 64 if big else 1.0 / 512
+        self.tier2_share = 1.0 / 64 if big else 1.0 / 256
         with torch.cuda.device(dev):
             # any fp32 vector is a valid centre; the mean row is the one that shrinks the items most
-            self.center = self.item_emb.mean(dim=0, dtype=torch.float64).float().contiguous() if center else None
+            self.center = None
+            if center:
+                self.center = torch.empty(self.dim, dtype=torch.float32, device=dev)
+                ws_bytes = int(_lib.load().hnm_column_mean_workspace_bytes(self.dim))
+                ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
+                call("hnm_column_mean", ptr(self.item_emb), self.num_items, self.dim, ptr(self.center), ptr(ws),
+                     ws_bytes, stream())
             # {absmax, scale, max ||x - c||^2, -} of the shard: produced and consumed on the device, so the
             # set-up needs no host synchronisation (two .tolist()/.max() round trips in round 1)
             self.item_params = torch.zeros(4, dtype=torch.float32, device=dev)
@@ -203,7 +209,8 @@ class FusedScorer:
         """Tier 2 on a fixed number of slots, no host round trip (see topk).  ids_full / sc_full carry one spare
         row at index `total` that absorbs the write-back of the unused slots."""
         dev = self.item_emb.device
-        slots = min(total, max(TIER2_SLOTS, int(total * self.tier2_share)))
+        slots = max(TIER2_SLOTS, int(total * self.tier2_share))
+        slots = min(total, -(-slots // (2 * USER_BLOCK)) * 2 * USER_BLOCK)          # whole pairs of user tiles
         sel2 = min(32, k + self.tier2_margin)
         bad = torch.nonzero_static(cert != 1, size=slots, fill_value=-1).view(-1)       # device-side compaction
         valid = bad >= 0

@@ -226,6 +226,12 @@ HNM_API int hnm_topk_exact(const float* user_emb, const float* item_emb, const i
 #define HNM_FUSED_CAND_BYTES 20     /* bytes per candidate entry (16 in the q array + 4 in the col array) */
 #define HNM_FUSED_SIG_WORDS 32      /* uint32 words of a user's exclusion signature (1 024 bits) */
 
+/* Column means of a [rows, dim] fp32 table (fp64 sums in a fixed order: deterministic) -> out_mean[dim].
+ * The centre of the item shard; replaces item_embeddings.mean(dim=0) in eager PyTorch.  dim 64, 128 or 256;
+ * workspace of hnm_column_mean_workspace_bytes(dim) bytes, 8-byte aligned. */
+HNM_API int64_t hnm_column_mean_workspace_bytes(int32_t dim);
+HNM_API int hnm_column_mean(const float* emb, int64_t rows, int32_t dim, float* out_mean, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 /* max |x - center[col]| over `count` floats of a [rows, dim] table -> *out_absmax (device float,
  * zeroed by the caller).  center NULL = no centring. */
 HNM_API int hnm_absmax(const float* emb, int64_t count, const float* center, int32_t dim, float* out_absmax,

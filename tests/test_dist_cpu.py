@@ -94,6 +94,18 @@ def _worker(rank, world, port, q):
         ue_u, ie_u = sh_u.forward(all_rows=False)
         a, b = sh_u.plan.user_rows[rank]
         ok = ok and torch.allclose(ue_u[a:b], ou[a:b], rtol=1e-6, atol=1e-8) and torch.allclose(ie_u, oi, rtol=1e-6, atol=1e-8)
+        # a new table from the host: a rank uploads only the rows it owns, the item block is completed by exchange
+        w_old = w.clone()
+        w2 = torch.randn(U + I, d, generator=torch.Generator().manual_seed(5))
+        nbytes = sh_u.load_embeddings_from_host(w2)
+        i0, i1 = sh_u.plan.item_rows[rank]
+        ok = ok and nbytes == ((b - a) + (i1 - i0)) * d * 4
+        ok = ok and torch.equal(w[a:b], w2[a:b]) and torch.equal(w[U:], w2[U:])
+        other = [r for r in range(world) if r != rank][0]
+        oa, ob = sh_u.plan.user_rows[other]
+        ok = ok and torch.equal(w[oa:ob], w_old[oa:ob])                 # nobody sent what this rank does not read
+        sh.load_embeddings_from_host(w2)                                # "items" mode reads every row
+        ok = ok and torch.equal(w, w2)
         q.put((rank, bool(ok), ""))
     except Exception as exc:  # noqa: BLE001
         import traceback

@@ -341,3 +341,23 @@ def test_fused_topk_wide_embeddings_bit_exact(hnm_lib, dim):
     chk = torch.cat([torch.arange(0, U2, 97), torch.arange(U2 - 700, U2)]).cuda()
     x_ids, x_s = engine.topk_exact(ue2.cuda(), ie[900:].cuda().contiguous(), chk, 7, item_begin=900)
     assert torch.equal(ids2[chk], x_ids) and torch.equal(s2[chk], x_s)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [64, 128, 256])
+def test_column_mean_matches_fp64_mean(hnm_lib, dim):
+    """hnm_column_mean (the item centre): fp64 sums in a fixed order -> equal to torch's fp64 mean after the
+    rounding to fp32, and identical from run to run."""
+    from hnm_recommendation_b200._lib import call, ptr, stream
+    torch.manual_seed(3)
+    x = (torch.randn(70_001, dim, device="cuda") * 3 + 0.25).contiguous()
+    ws_bytes = int(hnm_lib.hnm_column_mean_workspace_bytes(dim))
+    ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device="cuda")
+    outs = []
+    for _ in range(2):
+        out = torch.empty(dim, dtype=torch.float32, device="cuda")
+        call("hnm_column_mean", ptr(x), x.size(0), dim, ptr(out), ptr(ws), ws_bytes, stream())
+        outs.append(out)
+    want = x.mean(dim=0, dtype=torch.float64)
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0].double() - want).abs().max().item() <= 2.0 ** -22 * want.abs().max().item() + 1e-12
