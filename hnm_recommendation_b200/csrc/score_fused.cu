@@ -717,6 +717,7 @@ __device__ __forceinline__ uint32_t cand_half(const uint4& q, int h) {     // 16
 // lane-parallel, into exclusive prefix sums in shared memory, and both sweeps run over the FLAT entry index
 // (32 entries per step whatever sub-list they belong to; a lane finds its sub-list by bisection in shared
 // memory), two steps' loads in flight at a time.
+constexpr int kMergeBuf = 512;      // survivors buffered per warp before the sorting network runs (>= 2 x 256)
 struct FlatLists {
   const int32_t* pre;    // [lists + 1] exclusive prefix sums of the counts (shared memory)
   int lists;
@@ -735,6 +736,7 @@ __global__ void __launch_bounds__(128)
 merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand, int cap,
                    int32_t* __restrict__ cand_count, float* __restrict__ cand_thresh) {
   extern __shared__ int32_t merge_pre[];
+  __shared__ float merge_buf[4][kMergeBuf];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int lu = (int)blockIdx.x * 4 + wib;
@@ -782,9 +784,31 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand
     q = in.q[i];
     if (want_col) col = in.col[i];
   };
-  // kth_sel-th largest stored group maximum (its lower bound: the stored 16 bits are a truncation):
-  // running top 32 over all sub-lists, lane i = (i+1)-th largest
+  // kth_sel-th largest stored group maximum (its lower bound: the stored 16 bits are a truncation): running
+  // top 32 over all sub-lists, lane i = (i+1)-th largest.  Only values above `floor` = max(thr0, 32nd largest so
+  // far) can matter, and they are rare (a lane or two per 32 entries), so they are first compacted into a small
+  // shared-memory buffer and the 32-wide sorting network runs once per 32 SURVIVORS, not once per group column
+  // of every step that holds one.
   float top = -INFINITY;
+  float floor_v = thr;
+  float* buf = merge_buf[wib];
+  int nbuf = 0;
+  auto flush = [&]() {
+    for (int c = 0; c < nbuf; c += 32) {
+      float v = c + lane < nbuf ? buf[c + lane] : -INFINITY;
+#pragma unroll
+      for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_lane(v, lane, stride, (lane & size) == 0);
+      }
+      top = fmaxf(top, __shfl_sync(0xffffffffu, v, 31 - lane));
+#pragma unroll
+      for (int stride = 16; stride > 0; stride >>= 1) cmpx_lane(top, lane, stride, true);
+    }
+    nbuf = 0;
+    floor_v = fmaxf(thr, __shfl_sync(0xffffffffu, top, 31));
+    __syncwarp();
+  };
   for (int f0 = 0; f0 < entries; f0 += 64) {
     uint4 qs[2];
     bool have[2];
@@ -798,23 +822,38 @@ merge_split_kernel(SplitPlan sp, int num_users, int kth_sel, const CandList cand
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-#pragma unroll 1
-      for (int h = 0; h < 8; ++h) {
+      uint32_t kmask = 0u;
+      if (have[j]) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          float lo, hi;
+          cand_bounds(cand_half(qs[j], h), lo, hi);
+          kmask |= lo > floor_v ? (1u << h) : 0u;
+        }
+      }
+      if (!__any_sync(0xffffffffu, kmask != 0u)) continue;
+      const int mine_cnt = __popc(kmask);
+      int incl = mine_cnt;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+      }
+      const int found = __shfl_sync(0xffffffffu, incl, 31);         // <= 256
+      if (nbuf + found > kMergeBuf) flush();                         // (values at or below the new floor are harmless)
+      int pos = nbuf + incl - mine_cnt;
+      while (kmask) {
+        const int h = __ffs(kmask) - 1;
+        kmask &= kmask - 1;
         float lo, hi;
         cand_bounds(cand_half(qs[j], h), lo, hi);
-        float v = have[j] ? lo : -INFINITY;
-        if (!__any_sync(0xffffffffu, v > thr)) continue;        // nothing here can move a threshold above thr0
-#pragma unroll
-        for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-          for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_lane(v, lane, stride, (lane & size) == 0);
-        }
-        top = fmaxf(top, __shfl_sync(0xffffffffu, v, 31 - lane));
-#pragma unroll
-        for (int stride = 16; stride > 0; stride >>= 1) cmpx_lane(top, lane, stride, true);
+        buf[pos++] = lo;
       }
+      nbuf += found;
+      __syncwarp();
     }
   }
+  flush();
   // An unsliced row's tau is the kth_sel-th largest of 32 BUCKET maxima, which sits near the (kth_sel + 4)-th
   // best score because good items share buckets.  Taking the exact kth_sel-th best group here would leave less
   // room between the k-th score and the threshold, and 30x more sliced users failed their certificate.
@@ -1418,13 +1457,28 @@ colsum_kernel(const float* __restrict__ x, int64_t rows, double* __restrict__ pa
   }
 }
 
-__global__ void colmean_finish_kernel(const double* __restrict__ partial, int blocks, int dim, int64_t rows,
-                                      float* __restrict__ out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= dim) return;
-  double acc = 0.0;
-  for (int b = 0; b < blocks; ++b) acc += partial[(size_t)b * dim + t];
-  out[t] = (float)(acc / (double)rows);
+// One CTA of 1024 threads: thread (j, t) adds the partials of the blocks b = j, j + J, ... of column t, then
+// the J sub-sums are added in the order of j -- a fixed order, so the centre is identical from run to run.
+__global__ void __launch_bounds__(1024)
+colmean_finish_kernel(const double* __restrict__ partial, int blocks, int dim, int64_t rows,
+                      float* __restrict__ out) {
+  __shared__ double sm[1024];
+  const int t = threadIdx.x % dim, j = threadIdx.x / dim, J = 1024 / dim;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int b = j;
+  for (; b + 3 * J < blocks; b += 4 * J) {            // four loads in flight
+    const double v0 = partial[(size_t)b * dim + t], v1 = partial[(size_t)(b + J) * dim + t];
+    const double v2 = partial[(size_t)(b + 2 * J) * dim + t], v3 = partial[(size_t)(b + 3 * J) * dim + t];
+    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+  }
+  for (; b < blocks; b += J) a0 += partial[(size_t)b * dim + t];
+  sm[threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (j == 0) {
+    double acc = 0.0;
+    for (int jj = 0; jj < J; ++jj) acc += sm[jj * dim + t];
+    out[t] = (float)(acc / (double)rows);
+  }
 }
 }  // namespace
 
@@ -1447,7 +1501,7 @@ extern "C" int hnm_column_mean(const float* emb, int64_t rows, int32_t dim, floa
   else if (dim == 128) colsum_kernel<128><<<blocks, 256, 0, stream>>>(emb, rows, partial);
   else colsum_kernel<256><<<blocks, 256, 0, stream>>>(emb, rows, partial);
   HNM_LAUNCH_CHECK();
-  colmean_finish_kernel<<<(dim + 63) / 64, 64, 0, stream>>>(partial, blocks, dim, rows, out_mean);
+  colmean_finish_kernel<<<1, 1024, 0, stream>>>(partial, blocks, dim, rows, out_mean);
   HNM_LAUNCH_CHECK();
   return HNM_OK;
 }
