@@ -415,7 +415,7 @@ struct SplitPlan {
   int full_passes;      // passes of mu tiles over the whole catalog, per CTA
   int tile0;            // first left-over user tile (= gridDim.x * mu * full_passes)
   int triples;          // ceil(left-over tiles / mu)
-  int slices;           // item-range slices per triple; triples * slices <= gridDim.x
+  int slices;           // item-range slices per triple; unit (triple, slice) u runs on CTA u % gridDim.x
   CandList cand;        // [left-over users][slices][cap]
   int cap;
   int32_t* count;       // [left-over users][slices]
@@ -445,8 +445,11 @@ __device__ __forceinline__ bool pass_desc(int n, int num_user_tiles, int num_ite
     p.boot = min(num_item_tiles, boot_tiles);
     return true;
   }
-  if (n > sp.full_passes || b >= sp.triples * sp.slices) return false;
-  const int j = b / sp.slices, sl = b - j * sp.slices;
+  // left-over units (pair of user tiles, item slice): unit u = b, b + grid, ... (SplitPlan: several rounds when
+  // that balances better than one unsliced round on half of the CTAs)
+  const int unit = b + (n - sp.full_passes) * (int)gridDim.x;
+  if (unit >= sp.triples * sp.slices) return false;
+  const int j = unit / sp.slices, sl = unit - j * sp.slices;
   p.t0 = sp.tile0 + j * sp.mu;
   p.mc = min(sp.mu, num_user_tiles - p.t0);
   p.i0 = (int)(((long long)sl * num_item_tiles) / sp.slices);
@@ -1558,6 +1561,15 @@ constexpr int kMinSliceTiles = 32;  // an item slice is at least this many item 
 
 int fused_mu() { return kMU; }
 
+// Seed tiles: the number of chunks a row nominates grows like (k + 3) ln(#item tiles / #seed tiles), so the seed
+// scales with the catalog: 16 tiles up to ~1 000 item tiles (the H&M catalog), then 1/48 of the catalog in steps
+// of 16 (160 at 1 M items, where 16 seed tiles left 3 % of the users with an overflowing list:
+// profiles/r2_sweep_n8_first.json); 2 % more MMA work.
+int seed_tiles(int num_item_tiles) {
+  static const int boot_env = getenv("HNM_FUSED_BOOT") ? std::max(1, atoi(getenv("HNM_FUSED_BOOT"))) : 0;
+  return boot_env ? boot_env : std::max(kBootTiles, num_item_tiles / 48 / 16 * 16);
+}
+
 // The work distribution of one launch (see SplitPlan); pointers are filled in by the caller.
 SplitPlan make_plan(int num_user_tiles, int num_item_tiles, int grid) {
   const int kMU = fused_mu();
@@ -1570,7 +1582,20 @@ SplitPlan make_plan(int num_user_tiles, int num_item_tiles, int grid) {
   sp.triples = (left + kMU - 1) / kMU;
   sp.slices = 0;
   if (sp.triples > 0) {
-    sp.slices = std::max(1, std::min(grid / sp.triples, num_item_tiles / kMinSliceTiles));
+    // slices per left-over pair: the count that minimises the length of the tail, rounds x (tiles + seed tiles of
+    // a slice), over 1 .. min(grid, tiles / 32).  171 498 users (the H&M shape on 8 GPUs) leave 78 pairs for 148
+    // CTAs: unsliced that is a whole extra pass on half of the GPU, three slices each run in two rounds of a
+    // fraction of a pass.
+    const int boot = seed_tiles(num_item_tiles);
+    const int max_slices = std::max(1, std::min(grid, num_item_tiles / kMinSliceTiles));
+    long long best = -1;
+    for (int sl = 1; sl <= max_slices; ++sl) {
+      const int ni = (num_item_tiles + sl - 1) / sl;
+      const int b = sl > 1 ? std::max(1, std::min(boot, ni / 4)) : std::min(ni, boot);
+      const long long rounds = ((long long)sp.triples * sl + grid - 1) / grid;
+      const long long cost = rounds * (ni + b) * (100 + sl);       // 1 % per slice: near-ties go to fewer slices (less to merge)
+      if (best < 0 || cost < best) { best = cost; sp.slices = sl; }
+    }
     if (no_split) sp.slices = 1;
   }
   sp.cap = kSplitCap;
@@ -1635,16 +1660,11 @@ extern "C" int hnm_score_topk_fused(const void* users_f16, int64_t num_users, in
   if ((rc = make_map(&map_u, users_f16, users_padded, dim)) != HNM_OK) return rc;
   if ((rc = make_map(&map_i, items_f16, items_padded, dim)) != HNM_OK) return rc;
   static const int debug_mode = getenv("HNM_FUSED_DEBUG") ? atoi(getenv("HNM_FUSED_DEBUG")) : 0;
-  static const int boot_env = getenv("HNM_FUSED_BOOT") ? std::max(1, atoi(getenv("HNM_FUSED_BOOT"))) : 0;
   static const int refresh_div = getenv("HNM_FUSED_REFRESH") ? std::max(1, atoi(getenv("HNM_FUSED_REFRESH"))) : 4;
   static const uint32_t wait_hint = getenv("HNM_FUSED_WAIT_NS") ? (uint32_t)atoi(getenv("HNM_FUSED_WAIT_NS")) : kWaitHintNs;
   const int num_user_tiles = (int)(users_padded / kUserTile);
   const int num_tiles = (int)(items_padded / kItemTile);
-  // Seed tiles: the number of chunks a row nominates grows like (k + 3) ln(#item tiles / #seed tiles), so the seed
-  // scales with the catalog (2 % of it, at least 16 tiles): at 1 M items 16 seed tiles left 3 % of the users with
-  // an overflowing list (profiles/r2_sweep_n8_first.json), for 2 % more MMA work nobody overflows.
-  // seed tiles: 16 up to ~1 000 item tiles (the H&M catalog), then 1/48 of the catalog in steps of 16 (162 -> 160 at 1 M items)
-  const int boot_tiles = boot_env ? boot_env : std::max(kBootTiles, num_tiles / 48 / 16 * 16);
+  const int boot_tiles = seed_tiles(num_tiles);
   const int grid = fused_grid(num_user_tiles);
   SplitPlan sp = make_plan(num_user_tiles, num_tiles, grid);
   size_t off_count = 0, off_thresh = 0;

@@ -46,6 +46,13 @@ def even_ranges(n: int, parts: int) -> List[Tuple[int, int]]:
     return out
 
 
+def chunk_ranges(n: int, parts: int) -> List[Tuple[int, int]]:
+    """Split [0, n) into `parts` contiguous ranges of ceil(n / parts) rows, the last one(s) shorter: slices of one
+    size laid out back to back, so that ONE in-place all-gather assembles [0, n) with the padding at the very end."""
+    size = -(-n // parts) if n > 0 else 0
+    return [(min(n, p * size), min(n, (p + 1) * size)) for p in range(parts)]
+
+
 @dataclass
 class ShardPlan:
     world: int
@@ -57,7 +64,7 @@ class ShardPlan:
 
     @staticmethod
     def make(num_users: int, num_items: int, world: int, rank: int) -> "ShardPlan":
-        ur = even_ranges(num_users, world)
+        ur = chunk_ranges(num_users, world)     # users: equal chunks (the result all-gather needs no compaction)
         ir = even_ranges(num_items, world)
         return ShardPlan(world, rank, ur, [(num_users + a, num_users + b) for a, b in ir], ir, ur)
 
@@ -116,23 +123,27 @@ class Collectives:
                 out[r] = full[r][a:b]
         return out
 
-    def allgather_slices(self, mine: torch.Tensor, slices: Sequence[Tuple[int, int]], total: int) -> torch.Tensor:
+    def allgather_slices(self, mine: torch.Tensor, slices: Sequence[Tuple[int, int]], total: int,
+                         dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """Every rank holds the rows `slices[rank]` of a [total, ...] result: return all of it on every rank,
+        optionally converted to `dtype` on the way in (int64 item ids travel as int32).
+
+        Slices of one size with only the tail shorter (chunk_ranges) take ONE in-place all-gather into a buffer of
+        world x size rows whose first `total` rows ARE the result: no staging copy of the input (the conversion
+        writes it in place) and no compaction afterwards (round 2 first padded uneven slices and dropped the
+        padding with an index_select: 0.18 ms per 16 MB, a tenth of the 8-GPU step)."""
+        dtype = dtype or mine.dtype
         sizes = [b - a for a, b in slices]
-        if self.world > 1 and len(set(sizes)) > 1 and max(sizes) > 0:
-            # slices that differ by a row or two (1 371 980 users over 8 ranks): pad them to one size so that a
-            # single all-gather kernel does the exchange instead of 2 (G - 1) point-to-point operations per rank
-            rows = max(sizes)
-            padded = torch.empty((self.world, rows) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
-            padded[self.rank, :sizes[self.rank]] = mine
-            flat = padded.view((self.world * rows,) + tuple(mine.shape[1:]))
-            dist.all_gather_into_tensor(flat, padded[self.rank], group=self.group)
-            # drop the padding rows with ONE gather kernel (index cached per partition) instead of a cat of slices
-            key = (tuple(sizes), str(mine.device))
-            cache = self.__dict__.setdefault("_keep_index", {})
-            if key not in cache:
-                cache[key] = torch.cat([torch.arange(r * rows, r * rows + sizes[r]) for r in range(self.world)]).to(mine.device)
-            return flat.index_select(0, cache[key])
-        out = torch.empty((total,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        rows = sizes[0] if sizes else 0
+        starts_ok = all(slices[r][0] == min(total, r * rows) for r in range(self.world))
+        if self.world > 1 and rows > 0 and starts_ok and all(sz <= rows for sz in sizes):
+            flat = torch.empty((self.world * rows,) + tuple(mine.shape[1:]), dtype=dtype, device=mine.device)
+            lo = self.rank * rows
+            flat[lo:lo + sizes[self.rank]].copy_(mine)
+            src = flat[lo:lo + rows]
+            dist.all_gather_into_tensor(flat, src if self.nccl else src.clone(), group=self.group)
+            return flat[:total]
+        out = torch.empty((total,) + tuple(mine.shape[1:]), dtype=dtype, device=mine.device)
         a, b = slices[self.rank]
         out[a:b] = mine
         self.allgather_rows(out, slices)
@@ -216,7 +227,7 @@ class ShardedLightGCN:
                 def gather():
                     if m.num_items < 2 ** 31:
                         # item ids fit 32 bits: half the bytes on the wire (66 instead of 132 MB at the H&M shape)
-                        return self.coll.allgather_slices(ids.to(torch.int32), p.user_slices, m.num_users).long()
+                        return self.coll.allgather_slices(ids, p.user_slices, m.num_users, dtype=torch.int32).long()
                     return self.coll.allgather_slices(ids, p.user_slices, m.num_users)
 
                 out_ids = gather()

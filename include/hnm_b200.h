@@ -272,7 +272,8 @@ HNM_API int hnm_exclusion_signature(const int64_t* excl_ptr, const int64_t* excl
  * merges into `cand` (at most ~240 MB at the H&M catalog).  < 0 on bad sizes. */
 HNM_API int64_t hnm_score_topk_fused_workspace_bytes(int64_t users_padded, int64_t items_padded);
 /* Host only: how the launch distributes its work.  out6 = {grid, full passes per CTA (T user tiles x whole
- * catalog each), first left-over user tile, left-over groups of T tiles, item slices per group, T}. */
+ * catalog each), first left-over user tile, left-over groups of T tiles, item slices per group, T}.  Left-over
+ * unit (group j, slice s) = j * slices + s runs on CTA unit % grid (several rounds when that shortens the tail). */
 HNM_API int hnm_score_topk_fused_plan(int64_t users_padded, int64_t items_padded, int32_t* out6);
 HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb /* local shard rows */,
                      const int64_t* user_ids /* NULL = identity */, int64_t batch, int32_t dim /* 64 */,

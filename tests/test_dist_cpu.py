@@ -133,6 +133,11 @@ def test_even_ranges_and_plan():
     from hnm_recommendation_b200.dist import ShardPlan, even_ranges
     assert even_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert even_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    from hnm_recommendation_b200.dist import chunk_ranges
+    assert chunk_ranges(10, 3) == [(0, 4), (4, 8), (8, 10)]
+    assert chunk_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert chunk_ranges(9, 4) == [(0, 3), (3, 6), (6, 9), (9, 9)]
+    assert chunk_ranges(1371980, 8)[7] == (7 * 171498, 1371980)
     p = ShardPlan.make(1371980, 105542, 8, 3)
     assert p.user_rows[7][1] == 1371980 and p.item_rows[0][0] == 1371980 and p.item_rows[7][1] == 1371980 + 105542
     sizes = [b - a for a, b in p.item_shards]

@@ -117,19 +117,23 @@ def test_fused_work_plan_covers_every_tile_pair_once(hnm_lib, user_tiles, item_t
     assert grid >= 1 and tile0 == grid * mu * full and 0 <= user_tiles - tile0 < mu * grid
     assert triples == -(-(user_tiles - tile0) // mu)
     if triples:
-        assert 1 <= slices and triples * slices <= grid
+        assert 1 <= slices <= grid
     seen = np.zeros((user_tiles, item_tiles), dtype=np.int32)
     for b in range(grid):
         for n in range(full):                       # CTA b, pass n: tiles (b*full + n)*mu .. +mu, all items
             t0 = (b * full + n) * mu
             seen[t0:t0 + mu, :] += 1
-        if b < triples * slices:
-            j, sl = divmod(b, slices)
+        for unit in range(b, triples * slices, grid):       # left-over units (group, slice): b, b + grid, ...
+            j, sl = divmod(unit, slices)
             t0 = tile0 + mu * j
             i0, i1 = sl * item_tiles // slices, (sl + 1) * item_tiles // slices
             assert i1 > i0
             seen[t0:min(t0 + mu, user_tiles), i0:i1] += 1
     assert (seen == 1).all()
+    if triples and slices > 1:
+        # the tail is shorter than the unsliced one: rounds x slice length (seed tiles included) < one whole pass
+        rounds = -(-triples * slices // grid)
+        assert rounds * -(-item_tiles // slices) < item_tiles or rounds == 1
     ws = hnm_lib.hnm_score_topk_fused_workspace_bytes(user_tiles * 128, item_tiles * 128)
     need = triples * mu * 128 * slices * (256 * 20 + 12) if slices > 1 else 0    # 256 entries of 20 B + 2 counts + tau
     assert ws >= need and ws <= need + 4096
