@@ -281,12 +281,13 @@ topk_dense_kernel(const float* __restrict__ scores, int64_t num_items, const int
 }
 
 // ------------------------------------------------------------------ merge of sorted per-shard lists
+constexpr int kMaxMergeShards = 64;   // a list per GPU of one node, or per item split of hnm_topk_exact (<= 64)
 __global__ void merge_topk_kernel(const int64_t* __restrict__ in_ids, const double* __restrict__ in_s, int shards,
                                   int64_t batch, int k, int64_t* __restrict__ out_ids,
                                   double* __restrict__ out_s) {
   const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  int head[16];
+  int head[kMaxMergeShards];
   for (int g = 0; g < shards; ++g) head[g] = 0;
   for (int t = 0; t < k; ++t) {
     int best = -1;
@@ -367,7 +368,7 @@ extern "C" int hnm_merge_topk(const int64_t* in_ids, const double* in_scores, in
   cudaStream_t stream = (cudaStream_t)stream_;
   if (batch == 0) return HNM_OK;
   if (!in_ids || !in_scores || !out_ids || !out_scores) return HNM_E_NULL;
-  if (num_shards <= 0 || num_shards > 16 || batch < 0 || k <= 0) return HNM_E_RANGE;
+  if (num_shards <= 0 || num_shards > kMaxMergeShards || batch < 0 || k <= 0) return HNM_E_RANGE;
   merge_topk_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(in_ids, in_scores, num_shards, batch, k,
                                                                        out_ids, out_scores);
   HNM_LAUNCH_CHECK();

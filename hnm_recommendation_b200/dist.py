@@ -245,7 +245,19 @@ class ShardedLightGCN:
                 return out_ids
             ue, ie = self.forward()
             i0, i1 = p.item_shards[p.rank]
-            ids, sc = self.backend.local_topk(self, ue, ie[i0:i1], i0, k)           # [U, k] vs my item shard
+            if k > m.num_items:
+                raise ValueError(f"top_k = {k} exceeds the catalog ({m.num_items} items)")
+            # a shard smaller than k (tiny catalogs, many ranks) contributes all it has; the rest of its list is
+            # (-inf, INT64_MAX) sentinels, which the merge's (score desc, id asc) order puts behind every item
+            k_loc = min(k, i1 - i0)
+            if k_loc > 0:
+                ids, sc = self.backend.local_topk(self, ue, ie[i0:i1], i0, k_loc)   # [U, k_loc] vs my item shard
+            else:
+                ids = torch.empty(m.num_users, 0, dtype=torch.int64, device=ue.device)
+                sc = torch.empty(m.num_users, 0, dtype=torch.float64, device=ue.device)
+            if k_loc < k:
+                ids = torch.cat([ids, ids.new_full((m.num_users, k - k_loc), torch.iinfo(torch.int64).max)], dim=1)
+                sc = torch.cat([sc, sc.new_full((m.num_users, k - k_loc), float("-inf"))], dim=1)
             ids_x = self.coll.exchange_by_user_slice(ids, p.user_slices)           # [G, n_mine, k]
             sc_x = self.coll.exchange_by_user_slice(sc, p.user_slices)
             m_ids, m_sc = self.backend.merge(ids_x, sc_x)                          # [n_mine, k]

@@ -293,8 +293,9 @@ HNM_API int hnm_rescore_topk(const float* user_emb, const float* item_emb /* loc
 /* ------------------------------------------------------------------------
  * Multi-GPU merge of per-shard exact top-k lists (no reference counterpart;
  * BASELINE.json north_star: item-catalog shards + allgather + merge).
- * in_ids/in_scores: [num_shards, batch, k]; output the global top-k by
- * (score desc, id asc).
+ * in_ids/in_scores: [num_shards, batch, k] (1 <= num_shards <= 64), every list
+ * sorted by (score desc, id asc); a short list is padded with (-inf, INT64_MAX).
+ * Output: the global top-k in the same order.
  * ---------------------------------------------------------------------- */
 HNM_API int hnm_merge_topk(const int64_t* in_ids, const double* in_scores, int32_t num_shards, int64_t batch,
                    int32_t k, int64_t* out_ids, double* out_scores, void* stream);

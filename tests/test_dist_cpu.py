@@ -106,6 +106,20 @@ def _worker(rank, world, port, q):
         ok = ok and torch.equal(w[oa:ob], w_old[oa:ob])                 # nobody sent what this rank does not read
         sh.load_embeddings_from_host(w2)                                # "items" mode reads every row
         ok = ok and torch.equal(w, w2)
+        # item shards smaller than k: every shard hands in what it has, sentinels fill the rest of its list
+        U2, I2, k2 = 37, 9, 6                                           # shards of 5 and 4 items
+        w3 = torch.randn(U2 + I2, d, generator=torch.Generator().manual_seed(7)) * 0.1
+        u3 = torch.randint(0, U2, (200,), generator=g)
+        i3 = torch.randint(0, I2, (200,), generator=g) + U2
+        ei3 = torch.stack([torch.cat([u3, i3]), torch.cat([i3, u3])])
+        small = SimpleNamespace(num_users=U2, num_items=I2, top_k=k2, num_layers=L, alpha=O.layer_weights(L),
+                                graph=O.build_norm_adj(ei3, None, U2 + I2), embeddings=SimpleNamespace(weight=w3))
+        sh_s = hdist.ShardedLightGCN(small, backend=OracleBackend(), mode="items")
+        ids_s, sc_s = sh_s.recommend_all(return_scores=True)
+        rp3, c3, v3, _ = small.graph
+        ou3, oi3 = O.forward(w3, rp3, c3, v3, U2, L, small.alpha)
+        want_i3, want_s3 = O.recommend_exact(ou3, oi3, torch.arange(U2), k2)
+        ok = ok and torch.equal(ids_s, want_i3) and torch.allclose(sc_s, want_s3, rtol=1e-12, atol=0)
         q.put((rank, bool(ok), ""))
     except Exception as exc:  # noqa: BLE001
         import traceback
