@@ -696,7 +696,7 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu and not sweep:
         line["gpu_comparators"] = gpu_comparators(model)
         cores = host_threads()
-        cpu = CpuArm(u, i, e).step(16384 if args.config == "hm" else u)
+        cpu = CpuArm(u, i, e).step(65536 if args.config == "hm" else u)    # a 65 536-user slice
         line["cpu_baseline"] = {
             "value": cpu["users_per_s"], "unit": "users/s", "cores": cores, "kind": "port",
             "sample": (f"oracle forward() at full shape ({cpu['t_forward_s']:.2f} s) + score/top-12 for the first "

@@ -147,6 +147,29 @@ def test_config1_topk_all_users_bit_exact(hnm_lib):
     assert torch.equal(mi.cpu(), want_ids) and torch.equal(ms.cpu(), want_s)
 
 
+def test_merge_many_short_lists_with_sentinels(hnm_lib):
+    """hnm_merge_topk: 24 item shards of 7 items each, k = 12 > shard size -- every list is the shard's exact
+    top-7 followed by (-inf, INT64_MAX) sentinels (what ShardedLightGCN's item mode hands in for a shard smaller
+    than k); the merge equals the exact top-12 of the whole catalog, and more than 64 lists are refused."""
+    from hnm_recommendation_b200 import engine
+    from hnm_recommendation_b200._lib import HnmError
+    g = torch.Generator().manual_seed(11)
+    U, shards, per, k, d = 300, 24, 7, 12, 32
+    ue = torch.randn(U, d, generator=g)
+    ie = torch.randn(shards * per, d, generator=g)
+    ie[5] = ie[100]                                              # an exact tie across two shards: id ascending
+    want_ids, want_s = O.recommend_exact(ue, ie, torch.arange(U), k)
+    ids = torch.full((shards, U, k), torch.iinfo(torch.int64).max, dtype=torch.int64, device="cuda")
+    sc = torch.full((shards, U, k), float("-inf"), dtype=torch.float64, device="cuda")
+    for s in range(shards):
+        a, b = engine.topk_exact(ue.cuda(), ie[s * per:(s + 1) * per].cuda().contiguous(), None, per, item_begin=s * per)
+        ids[s, :, :per], sc[s, :, :per] = a, b
+    mi, ms = engine.merge_topk(ids, sc)
+    assert torch.equal(mi.cpu(), want_ids) and torch.equal(ms.cpu(), want_s)
+    with pytest.raises(HnmError):
+        engine.merge_topk(ids.repeat(3, 1, 1), sc.repeat(3, 1, 1))          # 72 lists
+
+
 def test_ties_and_filter_edge_cases(hnm_lib):
     from hnm_recommendation_b200 import engine
     # identical item rows -> exact ties -> id ascending
