@@ -14,6 +14,10 @@ outputs of the reference's *own* ``src/models/lightgcn.py`` and
 stand-ins for the three absent third-party packages
 (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``).  See DESIGN.md
 section "Oracle" for exactly what those stand-ins supply.
+
+``oracle/c/hnm_oracle.c`` (wrapper: ``oracle.c_oracle``) is a second, independent restatement of the same path
+in plain C -- scalar loops, no tensor library -- pinned against the same golden vectors and required to agree
+with this package bit for bit on index work and exact scores (tests/test_oracle_c.py).
 """
 from .lightgcn_oracle import (  # noqa: F401
     layer_weights, add_self_loops, build_norm_adj, propagate, forward,
