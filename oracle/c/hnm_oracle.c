@@ -97,13 +97,17 @@ HNM_ORACLE_API int hnm_oracle_forward(const int64_t* rowptr, const int64_t* col,
  * canonical order of BASELINE.json: score descending, item id ascending; scores are the exact dot products
  * of the fp32 embeddings accumulated in fp64 for k = 0..d-1 (each fp32 x fp32 product is exact in fp64).
  * excl_ptr [b+1] / excl_items: per listed user the item ids to filter (any order); NULL = no filter.
+ * item_bias [num_items] fp32 or NULL: MatrixFactorization's b_i, added in fp64 after the chain
+ * (src/models/matrix_factorization.py:108-131; b_u and the global bias are the same for every item of a user
+ * and cannot change its ranking).
  * out_ids [b, k] int64 item indices, out_scores [b, k] fp64.  Returns -3 when k exceeds the catalog.
  * ------------------------------------------------------------------------------------------------------- */
 static int before(double sa, int64_t ia, double sb, int64_t ib) { return sa > sb || (sa == sb && ia < ib); }
 
 HNM_ORACLE_API int hnm_oracle_topk_exact(const float* user_emb, const float* item_emb, const int64_t* user_ids, int64_t b,
                                          int64_t num_items, int32_t d, int32_t k, const int64_t* excl_ptr,
-                                         const int64_t* excl_items, int64_t* out_ids, double* out_scores) {
+                                         const int64_t* excl_items, const float* item_bias, int64_t* out_ids,
+                                         double* out_scores) {
   if (k < 1 || k > num_items) return -3;                                                /* what torch.topk raises */
   double* s = (double*)malloc((size_t)num_items * sizeof(double));
   if (!s) return -1;
@@ -113,7 +117,7 @@ HNM_ORACLE_API int hnm_oracle_topk_exact(const float* user_emb, const float* ite
       const float* v = item_emb + j * d;
       double acc = 0.0;
       for (int32_t q = 0; q < d; ++q) acc += (double)u[q] * (double)v[q];
-      s[j] = acc;
+      s[j] = item_bias ? acc + (double)item_bias[j] : acc;
     }
     if (excl_ptr)
       for (int64_t p = excl_ptr[r]; p < excl_ptr[r + 1]; ++p)

@@ -76,8 +76,9 @@ def forward(weight, rowptr, col, val, num_users: int, num_layers: int, alphas):
     return final[:num_users], final[num_users:]
 
 
-def topk_exact(user_emb, item_emb, user_ids, k: int, filter_items: Optional[Dict[int, set]] = None):
-    """(ids int64 [B, k], scores fp64 [B, k]) by (score desc, id asc); src/models/lightgcn.py:199-202,349-356."""
+def topk_exact(user_emb, item_emb, user_ids, k: int, filter_items: Optional[Dict[int, set]] = None, item_bias=None):
+    """(ids int64 [B, k], scores fp64 [B, k]) by (score desc, id asc); src/models/lightgcn.py:199-202,349-356.
+    item_bias: MatrixFactorization's b_i (src/models/matrix_factorization.py:108-131), added to the exact score."""
     ue, ie = _arr(user_emb, np.float32), _arr(item_emb, np.float32)
     uids = _arr(user_ids, np.int64)
     b = uids.shape[0]
@@ -91,7 +92,8 @@ def topk_exact(user_emb, item_emb, user_ids, k: int, filter_items: Optional[Dict
     ids = np.empty((b, k), np.int64)
     sc = np.empty((b, k), np.float64)
     rc = load().hnm_oracle_topk_exact(_p(ue), _p(ie), _p(uids), C.c_int64(b), C.c_int64(ie.shape[0]), C.c_int32(ie.shape[1]),
-                                      C.c_int32(k), _p(ex_ptr), _p(ex_items), _p(ids), _p(sc))
+                                      C.c_int32(k), _p(ex_ptr), _p(ex_items),
+                                      _p(None if item_bias is None else _arr(item_bias, np.float32).ravel()), _p(ids), _p(sc))
     if rc == -3:
         raise RuntimeError("selected index k out of range")
     if rc:

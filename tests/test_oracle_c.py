@@ -85,3 +85,25 @@ def test_c_ncf_forward_matches_reference_golden(path):
     uu = np.repeat(g["all_user_ids"], ni)
     ii = np.tile(np.arange(ni), nu)
     assert_close(CO.ncf_forward(state, uu, ii).reshape(nu, ni), g["all_scores"], what="all_scores vs the reference")
+
+
+@pytest.mark.parametrize("path", golden_files("mf"), ids=lambda p: p.split("mf_")[-1][:-4])
+def test_c_mf_ranking_matches_torch_oracle_and_reference_lists(path):
+    """MatrixFactorization (src/models/matrix_factorization.py:108-131,217-245): exact dot product + b_i decides."""
+    g = load_golden(path)
+    state = {k[len("state."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state.")}
+    uids = torch.from_numpy(g["all_user_ids"])
+    k = int(g["top_k"])
+    filt = {}
+    for r, i in zip(g["filter_rows"].tolist(), g["filter_items"].tolist()):
+        filt.setdefault(int(g["all_user_ids"][r]), set()).add(int(i))
+    for f in (None, filt):
+        ids, sc = CO.topk_exact(state["user_embeddings.weight"], state["item_embeddings.weight"], uids, k, f,
+                                item_bias=state["item_bias.weight"])
+        want = O.mf_recommend_exact(state, uids, k, f)
+        assert np.array_equal(ids, want.numpy())
+        s64 = O.mf_rank_scores_fp64(state, uids)
+        assert np.array_equal(sc, torch.gather(s64, 1, want).numpy())                           # the fp64 bits too
+    ids, _ = CO.topk_exact(state["user_embeddings.weight"], state["item_embeddings.weight"], uids, k,
+                           item_bias=state["item_bias.weight"])
+    assert int((ids != g["topk_canonical"]).any(axis=1).sum()) <= max(1, len(uids) // 10)       # near-ties only
