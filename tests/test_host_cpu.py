@@ -287,3 +287,71 @@ def test_graft_entry_build_runs_here():
     checks its ABI version against the host side's."""
     import __graft_entry__ as entry
     entry.build()
+
+
+def test_entry_points_validate_arguments_before_touching_the_device(hnm_lib):
+    """The error contract of include/hnm_b200.h (0 / negative argument error / positive cudaError_t): argument errors
+    are reported before any CUDA call, so they can be checked here without a GPU.  The pointers are never read."""
+    import ctypes as C
+    L = hnm_lib
+    E_NULL, E_RANGE, E_DIM, E_ALIGN = -1, -2, -3, -5
+    p, odd = C.c_void_p(0x10000), C.c_void_p(0x10008)            # non-NULL; `odd` is 8- but not 16-byte aligned
+    N = None
+    # LightGCN.predict (src/models/lightgcn.py:166-186)
+    assert L.hnm_pair_scores(N, p, p, p, 4, 64, 10, 10, p, N, N) == E_NULL
+    assert L.hnm_pair_scores(p, p, p, p, 0, 64, 10, 10, p, N, N) == 0                       # empty batch: nothing to do
+    assert L.hnm_pair_scores(p, p, p, p, -1, 64, 10, 10, p, N, N) == E_RANGE
+    assert L.hnm_pair_scores(p, p, p, p, 4, 0, 10, 10, p, N, N) == E_RANGE
+    # predict_all_items (:188-204)
+    assert L.hnm_score_all_items(p, p, N, 0, 100, 64, p, N) == 0
+    assert L.hnm_score_all_items(p, N, N, 4, 100, 64, p, N) == E_NULL
+    assert L.hnm_score_all_items(p, p, N, 4, 100, 0, p, N) == E_RANGE
+    # exact top-k (:349-356): exclusion CSR needs both arrays; k within [1, items]
+    assert L.hnm_topk_exact(p, p, N, 4, 0, 100, 64, 12, p, N, 1, p, p, N) == E_NULL
+    assert L.hnm_topk_exact(p, p, N, 4, 0, 100, 64, 0, N, N, 1, p, p, N) == E_RANGE
+    assert L.hnm_topk_exact(p, p, N, 4, 0, 8, 64, 12, N, N, 1, p, p, N) == E_RANGE          # torch.topk: k out of range
+    assert L.hnm_topk_exact(p, p, N, 4, 5, 5, 64, 1, N, N, 1, p, p, N) == E_RANGE           # empty item shard
+    assert L.hnm_topk_exact(p, p, N, 0, 0, 100, 64, 12, N, N, 1, p, p, N) == 0
+    # merge of per-shard lists (multi-GPU item shards)
+    assert L.hnm_merge_topk(p, p, 0, 4, 12, p, p, N) == E_RANGE
+    assert L.hnm_merge_topk(p, p, 65, 4, 12, p, p, N) == E_RANGE
+    assert L.hnm_merge_topk(p, N, 2, 4, 12, p, p, N) == E_NULL
+    assert L.hnm_merge_topk(p, p, 2, 0, 12, p, p, N) == 0
+    # dense select (NeuralCF.recommend, src/models/neural_cf.py:300-326)
+    assert L.hnm_topk_dense(p, 4, 10, N, N, 12, p, N, N) == E_RANGE
+    assert L.hnm_topk_dense(p, 4, 100, p, N, 12, p, N, N) == E_NULL
+    assert L.hnm_topk_dense(N, 4, 100, N, N, 12, p, N, N) == E_NULL
+    # fused score/select: padded sizes are whole tiles, operands 128-byte aligned
+    a = [p, 1000, 1024, p, 500, 512, 64, 15, p, 192, p, p, N, N, 0, N]
+    assert L.hnm_score_topk_fused(*a) not in (E_NULL, E_RANGE, E_ALIGN)                     # arguments fine: fails later, on the device check
+    bad = list(a); bad[2] = 1000
+    assert L.hnm_score_topk_fused(*bad) == E_RANGE
+    bad = list(a); bad[7] = 33
+    assert L.hnm_score_topk_fused(*bad) == E_RANGE                                           # kth_sel beyond the 32 buckets
+    bad = list(a); bad[9] = 191
+    assert L.hnm_score_topk_fused(*bad) == E_RANGE                                           # odd list capacity
+    bad = list(a); bad[0] = odd
+    assert L.hnm_score_topk_fused(*bad) == E_ALIGN
+    bad = list(a); bad[8] = N
+    assert L.hnm_score_topk_fused(*bad) == E_NULL
+    assert L.hnm_score_topk_fused_plan(1024, 512, N) == E_NULL
+    assert L.hnm_score_topk_fused_workspace_bytes(1000, 512) < 0
+    # exact rescoring: dimension, k, capacity, alignment
+    r = [p, p, N, 4, 64, 0, 500, p, 192, p, p, p, p, N, N, N, 12, p, p, p, N]
+    bad = list(r); bad[4] = 96
+    assert L.hnm_rescore_topk(*bad) == E_DIM
+    bad = list(r); bad[16] = 33
+    assert L.hnm_rescore_topk(*bad) == E_RANGE
+    bad = list(r); bad[8] = 193
+    assert L.hnm_rescore_topk(*bad) == E_RANGE
+    bad = list(r); bad[1] = odd
+    assert L.hnm_rescore_topk(*bad) == E_ALIGN
+    bad = list(r); bad[14] = p                                                               # excl_ptr without excl_items
+    assert L.hnm_rescore_topk(*bad) == E_NULL
+    bad = list(r); bad[3] = 0
+    assert L.hnm_rescore_topk(*bad) == 0
+    # propagation: a layer cannot run in place (rows are gathered while others are written)
+    assert L.hnm_lightgcn_layer(p, p, N, p, p, p, p, 0.25, 100, 64, 0, 100, N, 0, 0, 1024, 0, N) == E_RANGE
+    # every code has its own message
+    msgs = {c: L.hnm_strerror(c).decode() for c in (0, -1, -2, -3, -4, -5, -6, -7)}
+    assert all(msgs.values()) and len(set(msgs.values())) == len(msgs)
