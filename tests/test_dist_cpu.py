@@ -107,7 +107,7 @@ def _worker(rank, world, port, q):
         sh.load_embeddings_from_host(w2)                                # "items" mode reads every row
         ok = ok and torch.equal(w, w2)
         # item shards smaller than k: every shard hands in what it has, sentinels fill the rest of its list
-        U2, I2, k2 = 37, 9, 6                                           # shards of 5 and 4 items
+        U2, I2, k2 = 37, 9, 6                                           # shards of 5 + 4 items (world 2) or 3 + 3 + 3 (world 3)
         w3 = torch.randn(U2 + I2, d, generator=torch.Generator().manual_seed(7)) * 0.1
         u3 = torch.randint(0, U2, (200,), generator=g)
         i3 = torch.randint(0, I2, (200,), generator=g) + U2
@@ -128,15 +128,16 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
-def test_sharded_lightgcn_world2_gloo():
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_lightgcn_gloo(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=100) for _ in procs]
+    results = [q.get(timeout=150) for _ in procs]
     for p in procs:
         p.join(timeout=30)
     for rank, ok, err in results:
