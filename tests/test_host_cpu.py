@@ -352,6 +352,19 @@ def test_entry_points_validate_arguments_before_touching_the_device(hnm_lib):
     assert L.hnm_rescore_topk(*bad) == 0
     # propagation: a layer cannot run in place (rows are gathered while others are written)
     assert L.hnm_lightgcn_layer(p, p, N, p, p, p, p, 0.25, 100, 64, 0, 100, N, 0, 0, 1024, 0, N) == E_RANGE
+    # set_graph (:81-112): outputs and workspace required, edge weights and CSR weights go together, sizes sane,
+    # workspace at least hnm_graph_build_workspace_bytes
+    nh = (C.c_int32 * 1)()
+    assert L.hnm_graph_build(p, p, N, 10, 5, N, p, N, p, 1024, p, nh, p, 1 << 20, N) == E_NULL
+    assert L.hnm_graph_build(N, p, N, 10, 5, p, p, N, p, 1024, p, nh, p, 1 << 20, N) == E_NULL
+    assert L.hnm_graph_build(p, p, p, 10, 5, p, p, N, p, 1024, p, nh, p, 1 << 20, N) == E_NULL     # edge_w without csr_w
+    assert L.hnm_graph_build(p, p, N, 10, 0, p, p, N, p, 1024, p, nh, p, 1 << 20, N) == E_RANGE
+    assert L.hnm_graph_build(p, p, N, 2 ** 31, 5, p, p, N, p, 1024, p, nh, p, 1 << 20, N) == E_RANGE  # nnz beyond int32
+    need = L.hnm_graph_build_workspace_bytes(5, 10, 0)
+    assert need > 0 and L.hnm_graph_build(p, p, N, 10, 5, p, p, N, p, 1024, p, nh, p, need - 1, N) == -4
+    # NeuralCF (src/models/neural_cf.py:112-141,143-208)
+    assert L.hnm_ncf_score_pairs(p, p, p, p, p, p, 2, p, 0.0, N, p, 4, 64, p, N) == E_NULL
+    assert L.hnm_ncf_score_candidates(p, p, p, p, p, p, 2, p, 0.0, p, 4, p, 0, 64, p, N) == E_RANGE
     # every code has its own message
     msgs = {c: L.hnm_strerror(c).decode() for c in (0, -1, -2, -3, -4, -5, -6, -7)}
     assert all(msgs.values()) and len(set(msgs.values())) == len(msgs)
